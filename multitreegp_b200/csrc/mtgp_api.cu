@@ -1,0 +1,473 @@
+// mtgp_api.cu -- the extern "C" surface of libmtgp_b200.so (declared in include/mtgp.h).
+//
+// Validates arguments, carves the caller's workspace, and enqueues encode -> lower -> evaluate
+// on the caller's stream.  No entry point synchronises except the *_host ones, none allocates
+// device memory except the *_host ones (a per-device scratch cache, grown on demand).
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "mtgp_internal.cuh"
+
+int mtgp_rollout_slot_map(const mtgp_rollout_desc& d, int T, int* n_data, int* n_latent);
+
+// ---- errors --------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void mtgp_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int mtgp_check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    mtgp_set_error("%s launch failed: %s", what, cudaGetErrorString(e));
+    return MTGP_ERR_CUDA;
+  }
+  return MTGP_OK;
+}
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Carver {
+  unsigned char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<unsigned char*>(p)) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = align_up(off, 256);
+    T* r = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return r;
+  }
+};
+
+struct Workspace {
+  mtgp_bytecode bc;
+  uint2* prog;
+  uint32_t* meta;
+  float* Xt;
+  float* Yt;
+  size_t bytes;
+};
+
+// layout shared by mtgp_workspace_bytes and every entry point
+Workspace carve(void* ws, int P, int T, int N, int n_points_padded, int n_vars) {
+  Carver c(ws);
+  Workspace w{};
+  const size_t rows = (size_t)P * T * N, trees = (size_t)P * T;
+  w.bc.op = c.take<uint8_t>(rows);
+  w.bc.a = c.take<int16_t>(rows);
+  w.bc.b = c.take<int16_t>(rows);
+  w.bc.coef = c.take<float>(rows);
+  w.bc.live = c.take<int32_t>(trees);
+  w.bc.flags = c.take<uint8_t>(trees);
+  w.prog = c.take<uint2>(trees * (size_t)mtgp_lstride(N));
+  w.meta = c.take<uint32_t>(trees);
+  w.Xt = c.take<float>((size_t)n_points_padded * (n_vars > 0 ? n_vars : 0));
+  w.Yt = c.take<float>((size_t)n_points_padded * T);
+  w.bytes = align_up(c.off, 256);
+  return w;
+}
+
+int validate_table(const mtgp_node_table* t) {
+  if (!t || t->n_ids < 2 || t->n_ids > MTGP_MAX_NODE_IDS) {
+    mtgp_set_error("node table: n_ids must be in [2, %d]", MTGP_MAX_NODE_IDS);
+    return MTGP_ERR_INVALID_ARGUMENT;
+  }
+  if (t->opcode[0] != MTGP_OP_EMPTY || t->opcode[1] != MTGP_OP_COEF) {
+    mtgp_set_error("node table: id 0 must be the empty node and id 1 the coefficient leaf (genetic_programming.py:135)");
+    return MTGP_ERR_INVALID_ARGUMENT;
+  }
+  for (int i = 2; i < t->n_ids; i++) {
+    if (t->opcode[i] < MTGP_OP_VAR || t->opcode[i] >= MTGP_OP_COUNT_) {
+      mtgp_set_error("node table: id %d has unknown opcode %d", i, (int)t->opcode[i]);
+      return MTGP_ERR_INVALID_ARGUMENT;
+    }
+  }
+  return MTGP_OK;
+}
+
+int validate_shape(int P, int T, int N) {
+  if (P < 0 || T < 1 || N < 1) {
+    mtgp_set_error("population shape must satisfy P >= 0, T >= 1, N >= 1 (got P=%d T=%d N=%d)", P, T, N);
+    return MTGP_ERR_INVALID_ARGUMENT;
+  }
+  if (N > MTGP_MAX_NODES) {
+    mtgp_set_error("max_nodes=%d exceeds MTGP_MAX_NODES=%d", N, MTGP_MAX_NODES);
+    return MTGP_ERR_UNSUPPORTED;
+  }
+  return MTGP_OK;
+}
+
+int check_vars(const mtgp_node_table* t, int n_data) {
+  for (int i = 2; i < t->n_ids; i++) {
+    if (t->opcode[i] == MTGP_OP_VAR && (t->arg[i] < 0 || t->arg[i] >= n_data)) {
+      mtgp_set_error("variable node id %d reads data[%d] but the data vector has %d entries", i, t->arg[i], n_data);
+      return MTGP_ERR_INVALID_ARGUMENT;
+    }
+  }
+  return MTGP_OK;
+}
+
+int validate_rollout(const mtgp_rollout_desc* d, int T, int N, const mtgp_node_table* table, int* tmp_base) {
+  if (!d) { mtgp_set_error("rollout descriptor is NULL"); return MTGP_ERR_INVALID_ARGUMENT; }
+  if (d->B < 1 || d->K < 2) {
+    mtgp_set_error("need B >= 1 trajectories and K >= 2 time points (got B=%d K=%d)", d->B, d->K);
+    return MTGP_ERR_INVALID_ARGUMENT;
+  }
+  if (!d->x0 || !d->ts) { mtgp_set_error("x0 / ts must not be NULL"); return MTGP_ERR_INVALID_ARGUMENT; }
+  if (!(d->dt0 > 0.0f) || d->max_steps < 1) {
+    mtgp_set_error("dt0 must be > 0 and max_steps >= 1");
+    return MTGP_ERR_INVALID_ARGUMENT;
+  }
+  int envD = 0, envP = 0;
+  switch (d->env_id) {
+    case MTGP_ENV_NONE: break;
+    case MTGP_ENV_ACROBOT: envD = 4; envP = 4; break;
+    case MTGP_ENV_HARMONIC: envD = 2; envP = 2; break;
+    case MTGP_ENV_REACTOR: envD = 3; envP = 8; break;
+    default: mtgp_set_error("unknown environment id %d", d->env_id); return MTGP_ERR_INVALID_ARGUMENT;
+  }
+  if (d->kind == MTGP_EVAL_SR) {
+    if (d->env_id != MTGP_ENV_NONE || d->D != T || !d->ys_true) {
+      mtgp_set_error("SR evaluator: env must be NONE, state dimension D (%d) must equal the number of trees (%d), ys_true required", d->D, T);
+      return MTGP_ERR_INVALID_ARGUMENT;
+    }
+  } else if (d->kind == MTGP_EVAL_STATIC || d->kind == MTGP_EVAL_DYNAMIC) {
+    if (d->env_id == MTGP_ENV_NONE || d->D != envD || d->n_params != envP || !d->params) {
+      mtgp_set_error("control evaluator: environment %d needs D=%d and %d parameters per trajectory (got D=%d, n_params=%d)",
+                     d->env_id, envD, envP, d->D, d->n_params);
+      return MTGP_ERR_INVALID_ARGUMENT;
+    }
+    if (d->n_obs < 1 || d->n_obs > d->D) {
+      mtgp_set_error("n_obs must be in [1, D]");
+      return MTGP_ERR_INVALID_ARGUMENT;
+    }
+    const int want_targets = d->env_id == MTGP_ENV_ACROBOT ? 0 : 1;
+    if (d->n_targets != want_targets || (want_targets && !d->targets)) {
+      mtgp_set_error("environment %d expects %d target(s)", d->env_id, want_targets);
+      return MTGP_ERR_INVALID_ARGUMENT;
+    }
+    if (d->obs_noise != 0.0f && !d->obs_keys) {
+      mtgp_set_error("obs_noise != 0 needs obs_keys");
+      return MTGP_ERR_INVALID_ARGUMENT;
+    }
+    const int S = d->kind == MTGP_EVAL_DYNAMIC ? d->state_size : 0;
+    if (d->kind == MTGP_EVAL_DYNAMIC && S < 1) {
+      mtgp_set_error("dynamic evaluator needs state_size >= 1");
+      return MTGP_ERR_INVALID_ARGUMENT;
+    }
+    if (T - S != 1) {  // jnp.squeeze(u) must be a scalar for these environments (acrobot.py:52, reactor.py:80)
+      mtgp_set_error("the environment takes n_control = 1 control: expected %d trees, got %d", S + 1, T);
+      return MTGP_ERR_INVALID_ARGUMENT;
+    }
+  } else {
+    mtgp_set_error("unknown evaluator kind %d", d->kind);
+    return MTGP_ERR_INVALID_ARGUMENT;
+  }
+  int n_data, n_latent;
+  *tmp_base = mtgp_rollout_slot_map(*d, T, &n_data, &n_latent);
+  if (*tmp_base + mtgp_tmp_bound(N) > MTGP_MAX_SLOTS) {
+    mtgp_set_error("max_nodes=%d needs %d value-file slots, more than %d", N, *tmp_base + mtgp_tmp_bound(N), MTGP_MAX_SLOTS);
+    return MTGP_ERR_UNSUPPORTED;
+  }
+  return check_vars(table, n_data);
+}
+
+}  // namespace
+
+// ---- exported ------------------------------------------------------------------------------------
+extern "C" {
+
+int mtgp_abi_version(void) { return MTGP_ABI_VERSION; }
+const char* mtgp_last_error(void) { return g_err; }
+
+static int padded_points(int n_points) { return (int)align_up((size_t)(n_points > 0 ? n_points : 0), 256); }
+
+size_t mtgp_workspace_bytes(int P, int T, int N, const mtgp_rollout_desc* rollout) {
+  (void)rollout;
+  return carve(nullptr, P, T, N, 0, 0).bytes;
+}
+
+size_t mtgp_workspace_bytes_pointwise(int P, int T, int N, int n_points, int n_vars) {
+  return carve(nullptr, P, T, N, padded_points(n_points), n_vars).bytes;
+}
+
+size_t mtgp_bytecode_bytes(int P, int T, int N) {
+  // a caller that wants its own mtgp_bytecode arrays: op(1) + a(2) + b(2) + coef(4) per row, live(4) + flags(1) per tree
+  return (size_t)P * T * N * 9 + (size_t)P * T * 5;
+}
+
+int mtgp_encode(const float* nodes, int nodes_stride, const float* coef, int coef_stride, int P, int T, int N,
+                const mtgp_node_table* table, mtgp_bytecode out, void* stream) {
+  int rc = validate_shape(P, T, N);
+  if (rc) return rc;
+  if ((rc = validate_table(table))) return rc;
+  if (!nodes || !coef || nodes_stride < 3 || coef_stride < 1) {
+    mtgp_set_error("mtgp_encode: nodes/coef must not be NULL, strides must be >= 3 / >= 1");
+    return MTGP_ERR_INVALID_ARGUMENT;
+  }
+  if (!out.op || !out.a || !out.b || !out.coef || !out.live || !out.flags) {
+    mtgp_set_error("mtgp_encode: every array of the output bytecode must be allocated");
+    return MTGP_ERR_INVALID_ARGUMENT;
+  }
+  return mtgp_launch_encode(nodes, nodes_stride, coef, coef_stride, P, T, N, table, out, (cudaStream_t)stream);
+}
+
+int mtgp_decode(mtgp_bytecode in, int P, int T, int N, float* trees_out, void* stream) {
+  int rc = validate_shape(P, T, N);
+  if (rc) return rc;
+  if (!trees_out || !in.op || !in.a || !in.b || !in.coef) {
+    mtgp_set_error("mtgp_decode: NULL buffer");
+    return MTGP_ERR_INVALID_ARGUMENT;
+  }
+  return mtgp_launch_decode(in, P, T, N, trees_out, (cudaStream_t)stream);
+}
+
+// Lowered programs of a bytecode, for tests and tools: prog_out [P*T, lstride] uint2, meta_out [P*T].
+int mtgp_lower(mtgp_bytecode bc, int P, int T, int N, const mtgp_node_table* table, int tmp_base,
+               void* prog_out, uint32_t* meta_out, void* stream) {
+  int rc = validate_shape(P, T, N);
+  if (rc) return rc;
+  if ((rc = validate_table(table))) return rc;
+  return mtgp_launch_lower(bc, P, T, N, table, tmp_base, mtgp_lstride(N), static_cast<uint2*>(prog_out), meta_out,
+                           (cudaStream_t)stream);
+}
+int mtgp_program_stride(int N) { return mtgp_lstride(N); }
+
+int mtgp_rollout(mtgp_bytecode bc, int P, int T, int N, const mtgp_node_table* table,
+                 const mtgp_rollout_desc* desc, float* fitness, const mtgp_trajectory_out* traj,
+                 unsigned long long* steps_done, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = validate_shape(P, T, N);
+  if (rc) return rc;
+  if ((rc = validate_table(table))) return rc;
+  int tmp_base = 0;
+  if ((rc = validate_rollout(desc, T, N, table, &tmp_base))) return rc;
+  if (!fitness) { mtgp_set_error("fitness is NULL"); return MTGP_ERR_INVALID_ARGUMENT; }
+  Workspace w = carve(workspace, P, T, N, 0, 0);
+  if (!workspace || workspace_bytes < w.bytes) {
+    mtgp_set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+    return MTGP_ERR_WORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((rc = mtgp_launch_lower(bc, P, T, N, table, tmp_base, mtgp_lstride(N), w.prog, w.meta, s))) return rc;
+  mtgp_programs progs{w.prog, w.meta, mtgp_lstride(N), tmp_base, mtgp_tmp_bound(N)};
+  return mtgp_launch_rollout(progs, nullptr, P, T, N, *desc, 0.0f, fitness, traj, steps_done, s);
+}
+
+int mtgp_population_fitness_ex(const float* nodes, int nodes_stride, const float* coef, int coef_stride, int P,
+                               int T, int N, const mtgp_node_table* table, const mtgp_rollout_desc* desc,
+                               float size_parsimony, float* fitness, const mtgp_trajectory_out* traj,
+                               unsigned long long* steps_done, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  int rc = validate_shape(P, T, N);
+  if (rc) return rc;
+  if ((rc = validate_table(table))) return rc;
+  int tmp_base = 0;
+  if ((rc = validate_rollout(desc, T, N, table, &tmp_base))) return rc;
+  if (!fitness || !nodes || !coef) { mtgp_set_error("NULL population / fitness buffer"); return MTGP_ERR_INVALID_ARGUMENT; }
+  Workspace w = carve(workspace, P, T, N, 0, 0);
+  if (!workspace || workspace_bytes < w.bytes) {
+    mtgp_set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+    return MTGP_ERR_WORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((rc = mtgp_launch_encode(nodes, nodes_stride, coef, coef_stride, P, T, N, table, w.bc, s))) return rc;
+  if ((rc = mtgp_launch_lower(w.bc, P, T, N, table, tmp_base, mtgp_lstride(N), w.prog, w.meta, s))) return rc;
+  mtgp_programs progs{w.prog, w.meta, mtgp_lstride(N), tmp_base, mtgp_tmp_bound(N)};
+  return mtgp_launch_rollout(progs, w.bc.live, P, T, N, *desc, size_parsimony, fitness, traj, steps_done, s);
+}
+
+int mtgp_population_fitness(const float* nodes, int nodes_stride, const float* coef, int coef_stride, int P, int T,
+                            int N, const mtgp_node_table* table, const mtgp_rollout_desc* desc,
+                            float size_parsimony, float* fitness, unsigned long long* steps_done, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  return mtgp_population_fitness_ex(nodes, nodes_stride, coef, coef_stride, P, T, N, table, desc, size_parsimony,
+                                    fitness, nullptr, steps_done, workspace, workspace_bytes, stream);
+}
+
+int mtgp_eval_pointwise(mtgp_bytecode bc, int P, int T, int N, const mtgp_node_table* table, const float* X,
+                        const float* Y, int n_points, int n_vars, float max_fitness, float* fitness, float* pred,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = validate_shape(P, T, N);
+  if (rc) return rc;
+  if ((rc = validate_table(table))) return rc;
+  if (!X || !Y || !fitness || n_points < 1 || n_vars < 1) {
+    mtgp_set_error("pointwise: X, Y, fitness must not be NULL; n_points, n_vars >= 1");
+    return MTGP_ERR_INVALID_ARGUMENT;
+  }
+  if ((rc = check_vars(table, n_vars))) return rc;
+  const int tmp_base = n_vars + T;
+  if (tmp_base + mtgp_tmp_bound(N) > MTGP_MAX_SLOTS) {
+    mtgp_set_error("max_nodes=%d needs too many value-file slots", N);
+    return MTGP_ERR_UNSUPPORTED;
+  }
+  const int npad = padded_points(n_points);
+  Workspace w = carve(workspace, P, T, N, npad, n_vars);
+  if (!workspace || workspace_bytes < w.bytes) {
+    mtgp_set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+    return MTGP_ERR_WORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((rc = mtgp_launch_transpose_points(X, Y, n_points, npad, n_vars, T, w.Xt, w.Yt, s))) return rc;
+  if ((rc = mtgp_launch_lower(bc, P, T, N, table, tmp_base, mtgp_lstride(N), w.prog, w.meta, s))) return rc;
+  mtgp_programs progs{w.prog, w.meta, mtgp_lstride(N), tmp_base, mtgp_tmp_bound(N)};
+  return mtgp_launch_pointwise(progs, nullptr, P, T, N, w.Xt, w.Yt, n_points, npad, n_vars, max_fitness, 0.0f,
+                               fitness, pred, s);
+}
+
+int mtgp_population_fitness_pointwise(const float* nodes, int nodes_stride, const float* coef, int coef_stride,
+                                      int P, int T, int N, const mtgp_node_table* table, const float* X,
+                                      const float* Y, int n_points, int n_vars, float max_fitness,
+                                      float size_parsimony, float* fitness, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  int rc = validate_shape(P, T, N);
+  if (rc) return rc;
+  if ((rc = validate_table(table))) return rc;
+  if (!X || !Y || !fitness || !nodes || !coef || n_points < 1 || n_vars < 1) {
+    mtgp_set_error("pointwise: NULL buffer or empty data set");
+    return MTGP_ERR_INVALID_ARGUMENT;
+  }
+  if ((rc = check_vars(table, n_vars))) return rc;
+  const int tmp_base = n_vars + T;
+  if (tmp_base + mtgp_tmp_bound(N) > MTGP_MAX_SLOTS) {
+    mtgp_set_error("max_nodes=%d needs too many value-file slots", N);
+    return MTGP_ERR_UNSUPPORTED;
+  }
+  const int npad = padded_points(n_points);
+  Workspace w = carve(workspace, P, T, N, npad, n_vars);
+  if (!workspace || workspace_bytes < w.bytes) {
+    mtgp_set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+    return MTGP_ERR_WORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((rc = mtgp_launch_encode(nodes, nodes_stride, coef, coef_stride, P, T, N, table, w.bc, s))) return rc;
+  if ((rc = mtgp_launch_transpose_points(X, Y, n_points, npad, n_vars, T, w.Xt, w.Yt, s))) return rc;
+  if ((rc = mtgp_launch_lower(w.bc, P, T, N, table, tmp_base, mtgp_lstride(N), w.prog, w.meta, s))) return rc;
+  mtgp_programs progs{w.prog, w.meta, mtgp_lstride(N), tmp_base, mtgp_tmp_bound(N)};
+  return mtgp_launch_pointwise(progs, w.bc.live, P, T, N, w.Xt, w.Yt, n_points, npad, n_vars, max_fitness,
+                               size_parsimony, fitness, nullptr, s);
+}
+
+// ---- host-buffer entry points: H2D copies + evaluation + D2H, one call ---------------------------
+namespace {
+struct DeviceScratch {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+std::mutex g_scratch_mu;
+DeviceScratch g_scratch[64];
+
+int scratch_for_device(size_t bytes, void** out) {
+  int dev = 0;
+  MTGP_CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_scratch_mu);
+  DeviceScratch& s = g_scratch[dev & 63];
+  if (s.bytes < bytes) {
+    if (s.ptr) MTGP_CUDA_TRY(cudaFree(s.ptr));
+    s.ptr = nullptr;
+    s.bytes = 0;
+    MTGP_CUDA_TRY(cudaMalloc(&s.ptr, bytes));
+    s.bytes = bytes;
+  }
+  *out = s.ptr;
+  return MTGP_OK;
+}
+}  // namespace
+
+int mtgp_population_fitness_host(const float* population_host, int P, int T, int N, const mtgp_node_table* table,
+                                 const mtgp_rollout_desc* dh, float size_parsimony, float* fitness_host,
+                                 void* stream) {
+  int rc = validate_shape(P, T, N);
+  if (rc) return rc;
+  if (!dh || !population_host || !fitness_host) { mtgp_set_error("NULL host buffer"); return MTGP_ERR_INVALID_ARGUMENT; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t pop_bytes = (size_t)P * T * N * 4 * sizeof(float);
+  const size_t ws_bytes = mtgp_workspace_bytes(P, T, N, dh);
+  const size_t B = dh->B, K = dh->K, D = dh->D;
+  Carver c(nullptr);
+  // layout of the scratch: population | fitness | data arrays | workspace
+  size_t off_pop = 0, off_fit, off_x0, off_ts, off_tg, off_keys, off_par, off_ys, off_ws, total;
+  {
+    size_t o = align_up(pop_bytes, 256);
+    off_fit = o; o = align_up(o + (size_t)P * 4, 256);
+    off_x0 = o; o = align_up(o + B * D * 4, 256);
+    off_ts = o; o = align_up(o + K * 4, 256);
+    off_tg = o; o = align_up(o + B * (size_t)dh->n_targets * 4, 256);
+    off_keys = o; o = align_up(o + B * 8, 256);
+    off_par = o; o = align_up(o + B * (size_t)dh->n_params * 4, 256);
+    off_ys = o; o = align_up(o + (dh->ys_true ? B * K * D * 4 : 0), 256);
+    off_ws = o; total = o + ws_bytes;
+  }
+  void* base_v = nullptr;
+  if ((rc = scratch_for_device(total, &base_v))) return rc;
+  unsigned char* base = static_cast<unsigned char*>(base_v);
+  mtgp_rollout_desc dd = *dh;
+#define H2D(field, off, bytes)                                                                          \
+  if (dh->field && (bytes) > 0) {                                                                       \
+    MTGP_CUDA_TRY(cudaMemcpyAsync(base + off, dh->field, (bytes), cudaMemcpyHostToDevice, s));          \
+    dd.field = reinterpret_cast<decltype(dd.field)>(base + off);                                        \
+  } else {                                                                                              \
+    dd.field = nullptr;                                                                                 \
+  }
+  MTGP_CUDA_TRY(cudaMemcpyAsync(base + off_pop, population_host, pop_bytes, cudaMemcpyHostToDevice, s));
+  H2D(x0, off_x0, B * D * 4)
+  H2D(ts, off_ts, K * 4)
+  H2D(targets, off_tg, B * (size_t)dh->n_targets * 4)
+  H2D(obs_keys, off_keys, B * 8)
+  H2D(params, off_par, B * (size_t)dh->n_params * 4)
+  H2D(ys_true, off_ys, B * K * D * 4)
+#undef H2D
+  const float* pop_d = reinterpret_cast<const float*>(base + off_pop);
+  float* fit_d = reinterpret_cast<float*>(base + off_fit);
+  rc = mtgp_population_fitness(pop_d, 4, pop_d + 3, 4, P, T, N, table, &dd, size_parsimony, fit_d, nullptr,
+                               base + off_ws, ws_bytes, stream);
+  if (rc) return rc;
+  MTGP_CUDA_TRY(cudaMemcpyAsync(fitness_host, fit_d, (size_t)P * 4, cudaMemcpyDeviceToHost, s));
+  MTGP_CUDA_TRY(cudaStreamSynchronize(s));
+  return MTGP_OK;
+}
+
+int mtgp_population_fitness_pointwise_host(const float* population_host, int P, int T, int N,
+                                           const mtgp_node_table* table, const float* X_host, const float* Y_host,
+                                           int n_points, int n_vars, float max_fitness, float size_parsimony,
+                                           float* fitness_host, void* stream) {
+  int rc = validate_shape(P, T, N);
+  if (rc) return rc;
+  if (!population_host || !fitness_host || !X_host || !Y_host || n_points < 1 || n_vars < 1) {
+    mtgp_set_error("NULL host buffer or empty data set");
+    return MTGP_ERR_INVALID_ARGUMENT;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t pop_bytes = (size_t)P * T * N * 4 * sizeof(float);
+  const size_t ws_bytes = mtgp_workspace_bytes_pointwise(P, T, N, n_points, n_vars);
+  size_t o = align_up(pop_bytes, 256);
+  const size_t off_fit = o; o = align_up(o + (size_t)P * 4, 256);
+  const size_t off_x = o; o = align_up(o + (size_t)n_points * n_vars * 4, 256);
+  const size_t off_y = o; o = align_up(o + (size_t)n_points * T * 4, 256);
+  const size_t off_ws = o;
+  void* base_v = nullptr;
+  if ((rc = scratch_for_device(o + ws_bytes, &base_v))) return rc;
+  unsigned char* base = static_cast<unsigned char*>(base_v);
+  MTGP_CUDA_TRY(cudaMemcpyAsync(base, population_host, pop_bytes, cudaMemcpyHostToDevice, s));
+  MTGP_CUDA_TRY(cudaMemcpyAsync(base + off_x, X_host, (size_t)n_points * n_vars * 4, cudaMemcpyHostToDevice, s));
+  MTGP_CUDA_TRY(cudaMemcpyAsync(base + off_y, Y_host, (size_t)n_points * T * 4, cudaMemcpyHostToDevice, s));
+  const float* pop_d = reinterpret_cast<const float*>(base);
+  float* fit_d = reinterpret_cast<float*>(base + off_fit);
+  rc = mtgp_population_fitness_pointwise(pop_d, 4, pop_d + 3, 4, P, T, N, table,
+                                         reinterpret_cast<const float*>(base + off_x),
+                                         reinterpret_cast<const float*>(base + off_y), n_points, n_vars, max_fitness,
+                                         size_parsimony, fit_d, base + off_ws, ws_bytes, stream);
+  if (rc) return rc;
+  MTGP_CUDA_TRY(cudaMemcpyAsync(fitness_host, fit_d, (size_t)P * 4, cudaMemcpyDeviceToHost, s));
+  MTGP_CUDA_TRY(cudaStreamSynchronize(s));
+  return MTGP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,194 @@
+// mtgp_pointwise.cu -- K1: pointwise tree evaluation over a data set (symbolic-regression scale-up).
+//
+// Oracle: pred = vmap(vmap_foriloop, in_axes=[None, 0])(candidate, X)   (genetic_programming.py:390-401)
+//         fitness = mean_n sum_t (pred - Y)^2, where(nan|inf, max_fitness), clip   (SR_evaluator.py:24,42-45)
+//
+// Mapping: a CTA owns G individuals and ALL data points; its warps stride over 32*R-point chunks.
+// For each chunk a warp loads the variables once (coalesced float4 from the transposed data set,
+// which is L2-resident) into its shared-memory value file and then runs the programs of all G
+// individuals on it, so every data byte fetched from L2 is used G times.  Each lane evaluates R
+// points per dispatched instruction, which amortises the (warp-uniform) decode over 32*R points.
+#include "mtgp_internal.cuh"
+
+namespace {
+
+constexpr int kPwWarps = 4;
+constexpr int kPwGroup = 8;
+
+struct PointwiseParams {
+  const uint2* prog;
+  const uint32_t* meta;
+  const int32_t* live;
+  int lstride;
+  int P, T;
+  const float* Xt;  // [n_vars, npad]
+  const float* Yt;  // [T, npad]
+  int n_points, npad, n_vars;
+  float max_fitness, size_parsimony;
+  float* fitness;
+  float* pred;
+  int tmp_base;    // = n_vars + T
+  int n_tmp;       // temporaries provisioned per warp
+  int min_need;    // this launch handles individuals whose max temporaries are in (min_need-1, n_tmp]
+  int slots_per_warp;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int R>
+__global__ void __launch_bounds__(kPwWarps * 32) k_pointwise(const PointwiseParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_need[kPwGroup];
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  const int ind0 = blockIdx.x * kPwGroup;
+  const int G = min(kPwGroup, P.P - ind0);
+  const int words_per_ind = P.T * P.lstride;
+
+  uint2* prog_s = reinterpret_cast<uint2*>(smem_raw);
+  float* acc_s = reinterpret_cast<float*>(smem_raw + (size_t)kPwGroup * words_per_ind * sizeof(uint2));
+  float* vf = acc_s + kPwGroup * kPwWarps * 32 + (size_t)wic * P.slots_per_warp * 32 * R;
+
+  // which individuals of the group belong to this launch (by temporaries needed)
+  if (threadIdx.x < kPwGroup) {
+    int need = -1;
+    if ((int)threadIdx.x < G) {
+      need = 0;
+      for (int t = 0; t < P.T; t++) need = max(need, (int)(P.meta[(size_t)(ind0 + threadIdx.x) * P.T + t] >> 16));
+    }
+    s_need[threadIdx.x] = need;
+  }
+  __syncthreads();
+  bool any = false;
+  for (int g = 0; g < G; g++) any |= (s_need[g] >= P.min_need && s_need[g] <= P.n_tmp);
+  if (!any) return;
+
+  // stage the programs of the group (contiguous in global memory) -- plain vector copies
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(P.prog + (size_t)ind0 * words_per_ind);
+    uint4* dst = reinterpret_cast<uint4*>(prog_s);
+    const int n16 = G * words_per_ind / 2;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+  for (int i = threadIdx.x; i < kPwGroup * kPwWarps * 32; i += blockDim.x) acc_s[i] = 0.0f;
+  __syncthreads();
+
+  float* lb = vf + lane * R;
+  const int chunk_pts = 32 * R;
+  const int n_chunks = P.npad / chunk_pts;
+  for (int c = wic; c < n_chunks; c += kPwWarps) {
+    const int pt0 = c * chunk_pts + lane * R;
+    // variables and targets of this chunk -> value file slots [0, n_vars) and [n_vars, n_vars+T)
+    for (int v = 0; v < P.n_vars + P.T; v++) {
+      const float* src = (v < P.n_vars) ? P.Xt + (size_t)v * P.npad : P.Yt + (size_t)(v - P.n_vars) * P.npad;
+      Vec<R> d;
+      if constexpr (R % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < R / 4; i++) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(src + pt0) + i);
+          d.v[4 * i] = t4.x; d.v[4 * i + 1] = t4.y; d.v[4 * i + 2] = t4.z; d.v[4 * i + 3] = t4.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < R; i++) d.v[i] = __ldg(src + pt0 + i);
+      }
+      vf_store<R>(lb, v, d);
+    }
+    for (int g = 0; g < G; g++) {
+      if (s_need[g] < P.min_need || s_need[g] > P.n_tmp) continue;
+      float row[R];
+#pragma unroll
+      for (int r = 0; r < R; r++) row[r] = 0.0f;
+      for (int t = 0; t < P.T; t++) {
+        const Vec<R> pr = mtgp_interpret<R>(prog_s + (size_t)g * words_per_ind + (size_t)t * P.lstride, lb);
+        const Vec<R> yt = vf_load<R>(lb, P.n_vars + t);
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const float e = pr.v[r] - yt.v[r];
+          row[r] = row[r] + e * e;
+          if (P.pred && pt0 + r < P.n_points)
+            P.pred[((size_t)(ind0 + g) * P.n_points + pt0 + r) * P.T + t] = pr.v[r];
+        }
+      }
+      float s = 0.0f;
+#pragma unroll
+      for (int r = 0; r < R; r++) s = s + ((pt0 + r < P.n_points) ? row[r] : 0.0f);
+      acc_s[(g * kPwWarps + wic) * 32 + lane] += s;
+    }
+  }
+  __syncthreads();
+  for (int g = wic; g < G; g += kPwWarps) {
+    if (s_need[g] < P.min_need || s_need[g] > P.n_tmp) continue;
+    float s = 0.0f;
+    for (int w = 0; w < kPwWarps; w++) s = s + acc_s[(g * kPwWarps + w) * 32 + lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s = s + __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    if (lane == 0) {
+      float f = s / (float)P.n_points;
+      if (!mtgp_isfinitef(f)) f = P.max_fitness;
+      f = f < 0.0f ? 0.0f : (f > P.max_fitness ? P.max_fitness : f);
+      if (P.live) {
+        int cnt = 0;
+        for (int t = 0; t < P.T; t++) cnt += P.live[(size_t)(ind0 + g) * P.T + t];
+        f = f + P.size_parsimony * (float)cnt;
+      }
+      P.fitness[ind0 + g] = f;
+    }
+  }
+}
+
+// X [n, n_vars] -> Xt [n_vars, npad], Y [n, T] -> Yt [T, npad]; the pad is zero-filled
+__global__ void k_transpose_points(const float* __restrict__ X, const float* __restrict__ Y, int n, int npad,
+                                   int n_vars, int T, float* __restrict__ Xt, float* __restrict__ Yt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npad) return;
+  for (int v = 0; v < n_vars; v++) Xt[(size_t)v * npad + i] = (i < n) ? X[(size_t)i * n_vars + v] : 0.0f;
+  for (int t = 0; t < T; t++) Yt[(size_t)t * npad + i] = (i < n) ? Y[(size_t)i * T + t] : 0.0f;
+}
+
+template <int R>
+int launch_pw(PointwiseParams pp, int n_tmp, int min_need, cudaStream_t stream) {
+  pp.n_tmp = n_tmp;
+  pp.min_need = min_need;
+  pp.slots_per_warp = pp.tmp_base + n_tmp;
+  const size_t smem = (size_t)kPwGroup * pp.T * pp.lstride * sizeof(uint2) + (size_t)kPwGroup * kPwWarps * 32 * 4 +
+                      (size_t)kPwWarps * pp.slots_per_warp * 32 * R * 4;
+  if (smem > 227 * 1024) {
+    mtgp_set_error("pointwise kernel needs %zu bytes of shared memory per CTA: over the 227 KB limit", smem);
+    return MTGP_ERR_UNSUPPORTED;
+  }
+  auto kern = k_pointwise<R>;
+  MTGP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned blocks = (unsigned)((pp.P + kPwGroup - 1) / kPwGroup);
+  kern<<<blocks, kPwWarps * 32, smem, stream>>>(pp);
+  return mtgp_check_launch("k_pointwise");
+}
+
+}  // namespace
+
+int mtgp_launch_transpose_points(const float* X, const float* Y, int n_points, int n_points_padded, int n_vars,
+                                 int T, float* Xt, float* Yt, cudaStream_t stream) {
+  k_transpose_points<<<(n_points_padded + 255) / 256, 256, 0, stream>>>(X, Y, n_points, n_points_padded, n_vars, T,
+                                                                       Xt, Yt);
+  return mtgp_check_launch("k_transpose_points");
+}
+
+int mtgp_launch_pointwise(const mtgp_programs& progs, const int32_t* live, int P, int T, int N, const float* Xt,
+                          const float* Yt, int n_points, int n_points_padded, int n_vars, float max_fitness,
+                          float size_parsimony, float* fitness, float* pred, cudaStream_t stream) {
+  if (P == 0) return MTGP_OK;
+  PointwiseParams pp{};
+  pp.prog = progs.prog; pp.meta = progs.meta; pp.live = live; pp.lstride = progs.lstride;
+  pp.P = P; pp.T = T;
+  pp.Xt = Xt; pp.Yt = Yt; pp.n_points = n_points; pp.npad = n_points_padded; pp.n_vars = n_vars;
+  pp.max_fitness = max_fitness; pp.size_parsimony = size_parsimony;
+  pp.fitness = fitness; pp.pred = pred;
+  pp.tmp_base = progs.tmp_base;
+  // fast path: up to kFastTmp temporaries with R points per lane; anything deeper (only trees
+  // grown into long combs by mutation) runs one point per lane with the worst-case bound.
+  const int kFastTmp = 8;
+  const int bound = mtgp_tmp_bound(N);
+  int rc = launch_pw<8>(pp, bound < kFastTmp ? bound : kFastTmp, 0, stream);
+  if (rc != MTGP_OK) return rc;
+  if (bound > kFastTmp) rc = launch_pw<1>(pp, bound, kFastTmp + 1, stream);
+  return rc;
+}

@@ -1,0 +1,714 @@
+// mtgp_rollout.cu -- K2: the fused fixed-step rollout kernel.
+//
+// One warp = one individual, lanes = trajectories (initial conditions): every lane of a warp runs
+// the SAME tree programs, so interpreter dispatch is warp-uniform and divergence-free.  Fused in
+// one kernel, with the state in registers / the warp's shared-memory value file for ALL steps:
+//
+//   diffrax.diffeqsolve(Euler, ConstantStepSize, SaveAt(ts), Event(cond_fn_nan), throw=False)
+//        (call sites: SR_evaluator.py:76-79, feedforward_evaluate.py:90-93, dynamic_evaluate.py:93-96;
+//         loop semantics: SURVEY.md App. C -- THIRD-PARTY, restated identically in oracle/mtgp_oracle.c)
+//   _drift: env.f_obs -> trees -> env.drift          (feedforward_evaluate.py:104-110,
+//                                                      dynamic_evaluate.py:107-118, SR_evaluator.py:85-88)
+//   post-pass at the save points + env.fitness_function
+//                                                     (feedforward_evaluate.py:95-99, dynamic_evaluate.py:98-103)
+//   where(nan|inf, max_fitness) -> mean over B -> clip (feedforward_evaluate.py:48-51 and siblings)
+//   + size_parsimony * live rows                      (genetic_programming.py:424)
+//
+// Programs are staged into shared memory with cp.async.bulk (TMA 1-D bulk copy) + mbarrier.
+// Arithmetic order follows the reference source literally (see the oracle for the same
+// expressions); the file is compiled with -fmad=false so nothing is contracted.
+#include "mtgp_internal.cuh"
+
+namespace {
+
+constexpr int kWarpsPerCta = 4;
+
+struct RolloutParams {
+  const uint2* prog;
+  const uint32_t* meta;
+  const int32_t* live;
+  int lstride;
+  int P, T;
+  int B, K, n_obs, n_targets, n_params, state_size, max_steps;
+  float dt0, max_fitness, obs_noise, size_parsimony;
+  int partitionable;
+  const float *x0, *ts, *targets, *params, *ys_true;
+  const uint32_t* obs_keys;
+  float* fitness;
+  float *xs_o, *ys_o, *us_o, *act_o, *tf_o;
+  unsigned long long* steps_done;
+  int n_latent;        // state kept in the value file: SR -> T, DYNAMIC -> state_size, STATIC -> 0
+  int slot_lat;        // data-vector slot of latent component 0
+  int slot_u;          // data-vector slot of the control (control evaluators)
+  int slot_target;     // data-vector slot of target 0
+  int slot_out;        // n_latent slots: y1 of the latent state
+  int slot_state;      // n_latent slots: master copy of the latent state
+  int slots_per_warp;
+  int prog_words_per_warp;
+};
+
+// ---- PTX helpers: mbarrier + 1-D bulk async copy (TMA) ------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// ---- jax.random on the device (THIRD-PARTY semantics; same as the oracle) -----
+__device__ __forceinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t& o0,
+                                             uint32_t& o1) {
+  const uint32_t k2 = k0 ^ k1 ^ 0x1BD11BDAu;
+#define TF_ROUND(r)                    \
+  x0 += x1;                            \
+  x1 = __funnelshift_l(x1, x1, r);     \
+  x1 ^= x0;
+  x0 += k0; x1 += k1;
+  TF_ROUND(13) TF_ROUND(15) TF_ROUND(26) TF_ROUND(6)
+  x0 += k1; x1 += k2 + 1u;
+  TF_ROUND(17) TF_ROUND(29) TF_ROUND(16) TF_ROUND(24)
+  x0 += k2; x1 += k0 + 2u;
+  TF_ROUND(13) TF_ROUND(15) TF_ROUND(26) TF_ROUND(6)
+  x0 += k0; x1 += k1 + 3u;
+  TF_ROUND(17) TF_ROUND(29) TF_ROUND(16) TF_ROUND(24)
+  x0 += k1; x1 += k2 + 4u;
+  TF_ROUND(13) TF_ROUND(15) TF_ROUND(26) TF_ROUND(6)
+  x0 += k2; x1 += k0 + 5u;
+#undef TF_ROUND
+  o0 = x0; o1 = x1;
+}
+
+__device__ __forceinline__ float bits_to_normal(uint32_t bits) {
+  const float lo = -0.99999994f;
+  const float scale = 1.0f - lo;
+  const float f = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
+  float u = f * scale + lo;
+  u = (u > lo) ? u : lo;
+  return 1.41421356f * mtgp_erfinvf(u);
+}
+
+// normal(fold_in(key, bits(t)), (n,)) for n <= 4
+template <int NMAXOBS>
+__device__ __forceinline__ void obs_normal(uint32_t key0, uint32_t key1, float t, int n, int partitionable,
+                                           float* out) {
+  uint32_t f0, f1;
+  threefry2x32(key0, key1, 0u, __float_as_uint(t), f0, f1);
+  uint32_t bits[NMAXOBS];
+  if (partitionable) {
+#pragma unroll
+    for (int i = 0; i < NMAXOBS; i++) {
+      if (i < n) {
+        uint32_t o0, o1;
+        threefry2x32(f0, f1, 0u, (uint32_t)i, o0, o1);
+        bits[i] = o0 ^ o1;
+      }
+    }
+  } else {
+    const int half = (n + 1) >> 1;
+#pragma unroll
+    for (int i = 0; i < (NMAXOBS + 1) / 2; i++) {
+      if (i < half) {
+        uint32_t o0, o1;
+        const uint32_t c1 = (half + i < n) ? (uint32_t)(half + i) : 0u;
+        threefry2x32(f0, f1, (uint32_t)i, c1, o0, o1);
+#pragma unroll
+        for (int j = 0; j < NMAXOBS; j++) {
+          if (j == i) bits[j] = o0;
+          if (j == half + i && j < n) bits[j] = o1;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NMAXOBS; i++)
+    if (i < n) out[i] = bits_to_normal(bits[i]);
+}
+
+__device__ __forceinline__ float clip_jnp(float v, float lo, float hi) {
+  if (v != v) return v;
+  v = v > lo ? v : lo;
+  return v < hi ? v : hi;
+}
+
+__device__ __forceinline__ void sincos_contract(float x, float& s, float& c) {
+  // identical to mtgp_sinf(x), mtgp_cosf(x): one shared argument reduction
+  int q;
+  const float r = mtgp_trig_reduce(x, &q);
+  const float sk = mtgp_sin_kernel(r), ck = mtgp_cos_kernel(r);
+  const float sv = (q & 1) ? ck : sk;
+  const float cv = (q & 1) ? sk : ck;
+  s = (q & 2) ? -sv : sv;
+  c = ((q + 1) & 2) ? -cv : cv;
+}
+
+// ---- environments --------------------------------------------------------------------------------
+template <int ENV>
+struct EnvDim { static constexpr int D = 1; };
+template <> struct EnvDim<MTGP_ENV_ACROBOT> { static constexpr int D = 4; };
+template <> struct EnvDim<MTGP_ENV_HARMONIC> { static constexpr int D = 2; };
+template <> struct EnvDim<MTGP_ENV_REACTOR> { static constexpr int D = 3; };
+
+template <int ENV>
+struct Env {
+  static constexpr int D = EnvDim<ENV>::D;
+  float p[8];
+  float target;
+  uint32_t key0, key1;
+  // cost accumulators
+  float sum, sum0, u_d;
+  int fs;
+
+  __device__ __forceinline__ void init(const RolloutParams& P, int b) {
+    if (ENV == MTGP_ENV_ACROBOT) {
+      const float l1 = P.params[b * P.n_params + 0], l2 = P.params[b * P.n_params + 1];
+      const float m1 = P.params[b * P.n_params + 2], m2 = P.params[b * P.n_params + 3];
+      p[0] = l1; p[1] = l2; p[2] = m1; p[3] = m2;
+      p[4] = 0.5f * l1;  // lc1
+      p[5] = 0.5f * l2;  // lc2
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) p[i] = (i < P.n_params) ? P.params[b * P.n_params + i] : 0.0f;
+    }
+    target = (P.n_targets > 0) ? P.targets[b * P.n_targets] : 0.0f;
+    key0 = P.obs_keys ? P.obs_keys[2 * b] : 0u;
+    key1 = P.obs_keys ? P.obs_keys[2 * b + 1] : 0u;
+    sum = 0.0f; sum0 = 0.0f; fs = -1;
+    if (ENV == MTGP_ENV_HARMONIC) {
+      // u_d = -pinv(b) @ A @ x_d, x_d = [target, 0]   (harmonic_oscillator.py:77-79)
+      const float r0 = ((-0.0f) * 0.0f) + ((-1.0f) * (-p[0]));
+      const float r1 = ((-0.0f) * 1.0f) + ((-1.0f) * (-p[1]));
+      u_d = (r0 * target) + (r1 * 0.0f);
+    }
+  }
+
+  // EnvironmentBase.f_obs (control_environment_base.py:43-48) + Acrobot.f_obs (acrobot.py:29-32)
+  template <bool NOISE>
+  __device__ __forceinline__ void f_obs(float t, const float* x, float* y, int n_obs, float obs_noise,
+                                        int partitionable) const {
+    float nrm[D];
+    if (NOISE) obs_normal<D>(key0, key1, t, n_obs, partitionable, nrm);
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      if (i < n_obs) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < D; j++) {  // C @ x, literally (0 * inf = NaN must survive)
+          const float term = ((i == j) ? 1.0f : 0.0f) * x[j];
+          acc = (j == 0) ? term : acc + term;
+        }
+        if (NOISE) {
+          float nacc = 0.0f;
+#pragma unroll
+          for (int j = 0; j < D; j++) {  // normal @ W
+            if (j < n_obs) {
+              float w = (i == j) ? obs_noise : 0.0f;
+              if (ENV == MTGP_ENV_REACTOR) w = w * (i == 2 ? 0.1f : 15.0f);
+              const float term = nrm[j] * w;
+              nacc = (j == 0) ? term : nacc + term;
+            }
+          }
+          acc = acc + nacc;
+        }
+        y[i] = acc;
+      }
+    }
+    if (ENV == MTGP_ENV_ACROBOT) {
+      const float pi = 3.14159274f, two_pi = 6.28318548f;
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+        if (i < n_obs) y[i] = mtgp_remainderf_py(y[i] + pi, two_pi) - pi;
+    }
+  }
+
+  __device__ __forceinline__ void drift(const float* s, float u_in, float* ds) const {
+    if (ENV == MTGP_ENV_ACROBOT) {  // acrobot.py:51-72
+      const float control = clip_jnp(u_in, -1.0f, 1.0f);
+      const float theta1 = s[0], theta2 = s[1], theta1_dot = s[2], theta2_dot = s[3];
+      const float l1 = p[0], m1 = p[2], m2 = p[3], lc1 = p[4], lc2 = p[5];
+      const float g = 9.81f, moi1 = 1.0f, moi2 = 1.0f, half_pi = 1.57079637f;
+      float s2, c2;
+      sincos_contract(theta2, s2, c2);
+      const float d1 = m1 * (lc1 * lc1) + m2 * (((l1 * l1) + (lc2 * lc2)) + ((2.0f * l1) * lc2) * c2) + moi1 + moi2;
+      const float d2 = m2 * ((lc2 * lc2) + (l1 * lc2) * c2) + moi2;
+      const float phi2 = ((m2 * lc2) * g) * mtgp_cosf((theta1 + theta2) - half_pi);
+      const float phi1 = ((((-m2) * l1) * lc2) * (theta2_dot * theta2_dot)) * s2 -
+                         (((((2.0f * m2) * l1) * lc2) * theta1_dot) * theta2_dot) * mtgp_sinf(theta1) +
+                         (((m1 * lc1) + (m2 * l1)) * g) * mtgp_cosf(theta1 - half_pi) + phi2;
+      const float theta2_acc =
+          (((control + (d2 / d1) * phi1) - (((m2 * l1) * lc2) * (theta1_dot * theta1_dot)) * s2) - phi2) /
+          (((m2 * (lc2 * lc2)) + moi2) - (d2 * d2) / d1);
+      const float theta1_acc = (-((d2 * theta2_acc) + phi1)) / d1;
+      ds[0] = theta1_dot; ds[1] = theta2_dot; ds[2] = theta1_acc; ds[3] = theta2_acc;
+    } else if (ENV == MTGP_ENV_HARMONIC) {  // harmonic_oscillator.py:61-63,70-71
+      const float A10 = -p[0], A11 = -p[1];
+      ds[0] = ((0.0f * s[0]) + (1.0f * s[1])) + (0.0f * u_in);
+      ds[1] = ((A10 * s[0]) + (A11 * s[1])) + (1.0f * u_in);
+    } else if (ENV == MTGP_ENV_REACTOR) {  // reactor.py:78-87
+      const float Vol = p[0], Cp = p[1], dHr = p[2], UA = p[3], q = p[4], Tf = p[5], Tcf = p[6], Volc = p[7];
+      const float Tc = s[0], T = s[1], c = s[2];
+      const float control = clip_jnp(u_in, 0.0f, 300.0f);
+      const float mEaR = (float)(-72750.0 / 8.314);
+      const float kT = 7.2e10f * mtgp_expf(mEaR / T);
+      const float dc = ((q / Vol) * (1.0f - c)) - (kT * c);
+      const float dT = (((q / Vol) * (Tf - T)) + ((((-dHr) / Cp) * kT) * c)) + (((UA / Vol) / Cp) * (Tc - T));
+      const float dTc = ((control / Volc) * (Tcf - Tc)) + (((UA / Volc) / Cp) * (T - Tc));
+      ds[0] = dTc; ds[1] = dT; ds[2] = dc;
+    }
+  }
+
+  // cond_fn_nan on the env part of the state (the latent part is OR-ed in by the caller)
+  __device__ __forceinline__ bool bad_state(const float* y) const {
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < D; i++) bad |= !mtgp_isfinitef(y[i]);
+    if (ENV == MTGP_ENV_ACROBOT) bad |= (mtgp_absf(y[2]) > 25.1327419f) | (mtgp_absf(y[3]) > 56.5486679f);
+    return bad;
+  }
+
+  // one save point of env.fitness_function; fs_known >= 0 selects the exact second pass (Acrobot)
+  __device__ __forceinline__ void cost_add(int k, float qk, const float* xs, float u, int fs_known) {
+    if (ENV == MTGP_ENV_ACROBOT) {  // acrobot.py:77-84
+      const float c = (u * 0.01f) * u;
+      if (fs_known >= 0) {
+        if (!(qk > (float)fs_known)) sum = sum + c;
+        return;
+      }
+      const bool reached = ((-mtgp_cosf(xs[0])) - mtgp_cosf(xs[0] + xs[1])) > 1.5f;
+      if (!(qk > 0.0f)) sum0 = sum0 + c;
+      if (fs < 0) {
+        if (reached) {
+          fs = k;
+          if (!(qk > (float)k)) sum = sum + c;
+        } else {
+          sum = sum + c;
+        }
+      } else if (!(qk > (float)fs)) {
+        sum = sum + c;
+      }
+    } else if (ENV == MTGP_ENV_HARMONIC) {  // harmonic_oscillator.py:76-81
+      const float v0 = xs[0] - target, v1 = xs[1] - 0.0f;
+      const float w0 = (v0 * 0.5f) + (v1 * 0.0f), w1 = (v0 * 0.0f) + (v1 * 0.0f);
+      const float quad = (w0 * v0) + (w1 * v1);
+      const float du = u - u_d;
+      sum = sum + (quad + ((du * 0.5f) * du));
+    } else if (ENV == MTGP_ENV_REACTOR) {  // reactor.py:92-96
+      const float v[3] = {xs[0] - 0.0f, xs[1] - target, xs[2] - 0.0f};
+      float w[3];
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          const float term = v[i] * ((i == j) ? (i == 1 ? 0.01f : 0.0f) : 0.0f);
+          acc = (i == 0) ? term : acc + term;
+        }
+        w[j] = acc;
+      }
+      const float quad = ((w[0] * v[0]) + (w[1] * v[1])) + (w[2] * v[2]);
+      sum = sum + (quad + ((u * 0.0001f) * u));
+    }
+  }
+
+  __device__ __forceinline__ float cost_finish(int K, int fs_known) const {
+    if (ENV == MTGP_ENV_ACROBOT) {
+      if (fs_known >= 0) return (float)(fs_known + (fs_known == 0 ? K : 0)) + sum;
+      if (fs < 0) return (float)K + sum0;
+      return (float)(fs + (fs == 0 ? K : 0)) + sum;
+    }
+    return sum;
+  }
+};
+
+// ---- the kernel ----------------------------------------------------------------------------------
+template <int KIND, int ENV, bool NOISE>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) k_rollout(const RolloutParams P) {
+  constexpr int D = (KIND == MTGP_EVAL_SR) ? 0 : EnvDim<ENV>::D;
+  constexpr int DR = D > 0 ? D : 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  const int ind = blockIdx.x * kWarpsPerCta + wic;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  uint2* prog_s = reinterpret_cast<uint2*>(smem_raw + 16 * kWarpsPerCta) + (size_t)wic * P.prog_words_per_warp;
+  float* vf = reinterpret_cast<float*>(smem_raw + 16 * kWarpsPerCta +
+                                       (size_t)kWarpsPerCta * P.prog_words_per_warp * sizeof(uint2)) +
+              (size_t)wic * P.slots_per_warp * 32;
+  if (ind >= P.P) return;  // whole warp leaves together (no block-wide barrier below)
+
+  // ---- stage this individual's programs: cp.async.bulk -> shared, completion on an mbarrier ----
+  uint64_t* bar = bars + 2 * wic;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    uint32_t total = 0;
+    for (int t = 0; t < P.T; t++) {
+      const uint32_t n = P.meta[(size_t)ind * P.T + t] & 0xFFFFu;
+      total += ((n + 2u) & ~1u) * 8u;
+    }
+    mbar_expect_tx(bar, total);
+    for (int t = 0; t < P.T; t++) {
+      const uint32_t n = P.meta[(size_t)ind * P.T + t] & 0xFFFFu;
+      bulk_g2s(prog_s + (size_t)t * P.lstride, P.prog + ((size_t)ind * P.T + t) * P.lstride,
+               ((n + 2u) & ~1u) * 8u, bar);
+    }
+  }
+  __syncwarp();
+  float* lb = vf + lane;  // lane base of the value file (R = 1)
+  for (int s = 0; s < P.slots_per_warp; s++) lb[s * 32] = 0.0f;
+  mbar_wait(bar, 0);
+
+  const float* ts = P.ts;
+  const int K = P.K, NL = P.n_latent;
+  const float t0 = ts[0], t1 = ts[K - 1];
+  const float dts = (K > 1) ? ts[1] - ts[0] : 0.0f;  // ts[1]-ts[0], acrobot.py:82
+  float fit_sum = 0.0f;
+  unsigned long long my_steps = 0;
+
+  for (int b0 = 0; b0 < P.B; b0 += 32) {  // B > 32: the warp takes 32 trajectories at a time
+    const int b = b0 + lane;
+    const bool lane_valid = b < P.B;
+    const int bb = lane_valid ? b : P.B - 1;  // idle lanes shadow a valid trajectory
+    Env<ENV> env;
+    if (KIND != MTGP_EVAL_SR) env.init(P, bb);
+    if (KIND != MTGP_EVAL_SR)
+      for (int i = 0; i < P.n_targets; i++) lb[(P.slot_target + i) * 32] = P.targets[bb * P.n_targets + i];
+
+    int fs_known = -1;
+    bool viol = false;
+    float traj_fitness = 0.0f;
+    for (int pass = 0; pass < 2; pass++) {
+      // ---------------- one trajectory solve ----------------
+      float x[DR], x1[DR];
+      if (KIND != MTGP_EVAL_SR) {
+#pragma unroll
+        for (int i = 0; i < D; i++) x[i] = P.x0[bb * D + i];
+      }
+      for (int j = 0; j < NL; j++) {
+        const float v = (KIND == MTGP_EVAL_SR) ? P.x0[bb * NL + j] : 0.0f;  // a0 = 0 (dynamic_evaluate.py:89)
+        lb[(P.slot_state + j) * 32] = v;
+        lb[(P.slot_lat + j) * 32] = v;
+      }
+      if (KIND != MTGP_EVAL_SR) { env.sum = 0.0f; env.sum0 = 0.0f; env.fs = -1; }
+      float sr_total = 0.0f;
+      bool ev_old_bad;
+      {
+        bool bad = false;
+        if (KIND != MTGP_EVAL_SR) bad = env.bad_state(x);
+        for (int j = 0; j < NL; j++) bad |= !mtgp_isfinitef(lb[(P.slot_state + j) * 32]);
+        ev_old_bad = bad;  // Event: cond_fn at (t0, y0)
+      }
+      bool alive = true;
+      float tprev = t0, tnext = t0 + P.dt0;
+      tnext = tnext < t1 ? tnext : t1;
+      int steps = 0, k = 0;
+      while (tprev < t1 && steps < P.max_steps) {
+        if (__ballot_sync(0xFFFFFFFFu, alive && lane_valid) == 0u) break;
+        const float dt = tnext - tprev;
+        float u = 0.0f;
+        float y[DR];
+        if (KIND != MTGP_EVAL_SR) {
+          env.template f_obs<NOISE>(tprev, x, y, P.n_obs, P.obs_noise, P.partitionable);
+          if (KIND == MTGP_EVAL_STATIC) {
+#pragma unroll
+            for (int i = 0; i < D; i++)
+              if (i < P.n_obs) lb[i * 32] = y[i];
+            u = mtgp_interpret<1>(prog_s, lb).v[0];
+          } else {
+#pragma unroll
+            for (int i = 0; i < D; i++)
+              if (i < P.n_obs) lb[i * 32] = 0.0f;
+            lb[P.slot_u * 32] = 0.0f;
+            u = mtgp_interpret<1>(prog_s + (size_t)P.state_size * P.lstride, lb).v[0];  // readout (:113)
+          }
+          float dx[DR];
+          env.drift(x, u, dx);
+#pragma unroll
+          for (int i = 0; i < D; i++) x1[i] = x[i] + dt * dx[i];
+          if (KIND == MTGP_EVAL_DYNAMIC) {
+#pragma unroll
+            for (int i = 0; i < D; i++)
+              if (i < P.n_obs) lb[i * 32] = y[i];
+            lb[P.slot_u * 32] = u;
+          }
+        }
+        for (int j = 0; j < NL; j++) {  // latent trees: state equation (:116) / SR vector field
+          const float f = mtgp_interpret<1>(prog_s + (size_t)j * P.lstride, lb).v[0];
+          lb[(P.slot_out + j) * 32] = lb[(P.slot_state + j) * 32] + dt * f;
+        }
+        const float new_tprev = tnext < t1 ? tnext : t1;
+        float new_tnext = tnext + P.dt0;
+        new_tnext = (new_tnext > t1 - 1e-6f) ? t1 : new_tnext;  // _clip_to_end
+        // ---- SaveAt(ts): dense (linear) output for every ts[k] <= tnext ----
+        while (k < K && ts[k] <= tnext) {
+          const float tk = ts[k];
+          const float coeff = (tprev == tnext) ? 0.0f : (tk - tprev) / (tnext - tprev);
+          float xs[DR];
+          if (KIND != MTGP_EVAL_SR) {
+#pragma unroll
+            for (int i = 0; i < D; i++) xs[i] = alive ? x[i] + coeff * (x1[i] - x[i]) : mtgp_inff();
+          }
+          float row = 0.0f;
+          for (int j = 0; j < NL; j++) {
+            const float a0 = lb[(P.slot_state + j) * 32], a1 = lb[(P.slot_out + j) * 32];
+            const float lat = alive ? a0 + coeff * (a1 - a0) : mtgp_inff();
+            if (KIND == MTGP_EVAL_SR) {
+              const float e = lat - P.ys_true[((size_t)bb * K + k) * NL + j];
+              row = row + e * e;
+              if (P.xs_o && lane_valid && pass == 0) P.xs_o[(((size_t)ind * P.B + b) * K + k) * NL + j] = lat;
+            } else {
+              lb[(P.slot_lat + j) * 32] = lat;
+              if (P.act_o && lane_valid && pass == 0) P.act_o[(((size_t)ind * P.B + b) * K + k) * NL + j] = lat;
+            }
+          }
+          if (KIND == MTGP_EVAL_SR) {
+            sr_total = sr_total + row;
+          } else {
+            float ys[DR];
+            env.template f_obs<NOISE>(tk, xs, ys, P.n_obs, P.obs_noise, P.partitionable);
+#pragma unroll
+            for (int i = 0; i < D; i++)
+              if (i < P.n_obs) lb[i * 32] = ys[i];
+            float uk;
+            if (KIND == MTGP_EVAL_STATIC) {
+              uk = mtgp_interpret<1>(prog_s, lb).v[0];
+            } else {
+              lb[P.slot_u * 32] = 0.0f;  // zeros(control_size) (dynamic_evaluate.py:101)
+              uk = mtgp_interpret<1>(prog_s + (size_t)P.state_size * P.lstride, lb).v[0];
+            }
+            const float qk = (ENV == MTGP_ENV_ACROBOT) ? tk / dts : 0.0f;
+            if (ENV == MTGP_ENV_ACROBOT && qk > (float)(k + 1)) viol = true;
+            env.cost_add(k, qk, xs, uk, fs_known);
+            if (lane_valid && pass == 0) {
+              const size_t o = ((size_t)ind * P.B + b) * K + k;
+              if (P.xs_o)
+#pragma unroll
+                for (int i = 0; i < D; i++) P.xs_o[o * D + i] = xs[i];
+              if (P.ys_o)
+#pragma unroll
+                for (int i = 0; i < D; i++)
+                  if (i < P.n_obs) P.ys_o[o * P.n_obs + i] = ys[i];
+              if (P.us_o) P.us_o[o] = uk;
+            }
+          }
+          k++;
+        }
+        // ---- Event(cond_fn): sign change of cond_fn evaluated at (tnext, y1) ----
+        bool bad = false;
+        if (KIND != MTGP_EVAL_SR) bad = env.bad_state(x1);
+        for (int j = 0; j < NL; j++) bad |= !mtgp_isfinitef(lb[(P.slot_out + j) * 32]);
+        const bool fired = (bad != ev_old_bad);
+        // ---- commit ----
+        if (alive) {
+          ev_old_bad = bad;
+          my_steps += lane_valid ? 1ull : 0ull;
+          if (KIND != MTGP_EVAL_SR) {
+#pragma unroll
+            for (int i = 0; i < D; i++) x[i] = x1[i];
+          }
+        }
+        for (int j = 0; j < NL; j++) {
+          const float cur = lb[(P.slot_state + j) * 32];
+          const float nv = alive ? lb[(P.slot_out + j) * 32] : cur;
+          lb[(P.slot_state + j) * 32] = nv;
+          lb[(P.slot_lat + j) * 32] = nv;
+        }
+        if (alive && fired) alive = false;
+        tprev = new_tprev;
+        tnext = new_tnext;
+        steps++;
+      }
+      // ---- save points the solve never reached stay inf (SaveAt pre-fill) ----
+      alive = false;
+      while (k < K) {
+        const float tk = ts[k];
+        if (KIND == MTGP_EVAL_SR) {
+          float row = 0.0f;
+          for (int j = 0; j < NL; j++) {
+            const float e = mtgp_inff() - P.ys_true[((size_t)bb * K + k) * NL + j];
+            row = row + e * e;
+            if (P.xs_o && lane_valid && pass == 0) P.xs_o[(((size_t)ind * P.B + b) * K + k) * NL + j] = mtgp_inff();
+          }
+          sr_total = sr_total + row;
+        } else {
+          float xs[DR], ys[DR];
+#pragma unroll
+          for (int i = 0; i < D; i++) xs[i] = mtgp_inff();
+          for (int j = 0; j < NL; j++) {
+            lb[(P.slot_lat + j) * 32] = mtgp_inff();
+            if (P.act_o && lane_valid && pass == 0) P.act_o[(((size_t)ind * P.B + b) * K + k) * NL + j] = mtgp_inff();
+          }
+          env.template f_obs<NOISE>(tk, xs, ys, P.n_obs, P.obs_noise, P.partitionable);
+#pragma unroll
+          for (int i = 0; i < D; i++)
+            if (i < P.n_obs) lb[i * 32] = ys[i];
+          float uk;
+          if (KIND == MTGP_EVAL_STATIC) {
+            uk = mtgp_interpret<1>(prog_s, lb).v[0];
+          } else {
+            lb[P.slot_u * 32] = 0.0f;
+            uk = mtgp_interpret<1>(prog_s + (size_t)P.state_size * P.lstride, lb).v[0];
+          }
+          const float qk = (ENV == MTGP_ENV_ACROBOT) ? tk / dts : 0.0f;
+          if (ENV == MTGP_ENV_ACROBOT && qk > (float)(k + 1)) viol = true;
+          env.cost_add(k, qk, xs, uk, fs_known);
+          if (lane_valid && pass == 0) {
+            const size_t o = ((size_t)ind * P.B + b) * K + k;
+            if (P.xs_o)
+#pragma unroll
+              for (int i = 0; i < D; i++) P.xs_o[o * D + i] = xs[i];
+            if (P.ys_o)
+#pragma unroll
+              for (int i = 0; i < D; i++)
+                if (i < P.n_obs) P.ys_o[o * P.n_obs + i] = ys[i];
+            if (P.us_o) P.us_o[o] = uk;
+          }
+        }
+        k++;
+      }
+      traj_fitness = (KIND == MTGP_EVAL_SR) ? sr_total / (float)K : env.cost_finish(K, fs_known);
+      // Acrobot with a ts grid for which the running-prefix cost is not exact (ts[k]/dts > k+1
+      // somewhere): redo the solve with first_success known.  Warp-uniform decision.
+      if (ENV != MTGP_ENV_ACROBOT || pass == 1) break;
+      if (__ballot_sync(0xFFFFFFFFu, viol) == 0u) break;
+      fs_known = env.fs < 0 ? 0 : env.fs;
+    }
+    if (lane_valid) {
+      if (P.tf_o) P.tf_o[(size_t)ind * P.B + b] = traj_fitness;
+      fit_sum = fit_sum + (mtgp_isfinitef(traj_fitness) ? traj_fitness : P.max_fitness);
+    }
+  }
+  // mean over B (fixed shuffle tree), clip, parsimony
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) fit_sum = fit_sum + __shfl_xor_sync(0xFFFFFFFFu, fit_sum, o);
+  for (int o = 16; o > 0; o >>= 1) my_steps += __shfl_xor_sync(0xFFFFFFFFu, my_steps, o);
+  if (lane == 0) {
+    float f = clip_jnp(fit_sum / (float)P.B, 0.0f, P.max_fitness);
+    if (P.live) {
+      int cnt = 0;
+      for (int t = 0; t < P.T; t++) cnt += P.live[(size_t)ind * P.T + t];
+      f = f + P.size_parsimony * (float)cnt;
+    }
+    P.fitness[ind] = f;
+    if (P.steps_done) atomicAdd(P.steps_done, my_steps);
+  }
+}
+
+template <int KIND, int ENV>
+int launch_kind_env(const RolloutParams& rp, size_t smem, cudaStream_t stream) {
+  const unsigned blocks = (unsigned)((rp.P + kWarpsPerCta - 1) / kWarpsPerCta);
+  if (rp.obs_noise != 0.0f && KIND != MTGP_EVAL_SR) {
+    auto kern = k_rollout<KIND, ENV, true>;
+    MTGP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, kWarpsPerCta * 32, smem, stream>>>(rp);
+  } else {
+    auto kern = k_rollout<KIND, ENV, false>;
+    MTGP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, kWarpsPerCta * 32, smem, stream>>>(rp);
+  }
+  return mtgp_check_launch("k_rollout");
+}
+
+}  // namespace
+
+// Slot map of the value file (shared with the lowering pass through tmp_base):
+//   [0, n_data)                      the data vector the trees read
+//   [n_data, n_data + n_latent)      y1 of the latent state
+//   [.., + n_latent)                 master copy of the latent state
+//   [tmp_base, tmp_base + n_tmp)     temporaries of the programs
+int mtgp_rollout_slot_map(const mtgp_rollout_desc& d, int T, int* n_data, int* n_latent) {
+  if (d.kind == MTGP_EVAL_SR) {
+    *n_data = T;
+    *n_latent = T;
+  } else if (d.kind == MTGP_EVAL_STATIC) {
+    *n_data = d.n_obs + d.n_targets;
+    *n_latent = 0;
+  } else {
+    *n_data = d.n_obs + d.state_size + (T - d.state_size) + d.n_targets;
+    *n_latent = d.state_size;
+  }
+  return *n_data + 2 * (*n_latent);
+}
+
+int mtgp_launch_rollout(const mtgp_programs& progs, const int32_t* live, int P, int T, int N,
+                        const mtgp_rollout_desc& d, float size_parsimony, float* fitness,
+                        const mtgp_trajectory_out* traj, unsigned long long* steps_done,
+                        cudaStream_t stream) {
+  (void)N;
+  if (P == 0) return MTGP_OK;
+  RolloutParams rp{};
+  rp.prog = progs.prog; rp.meta = progs.meta; rp.live = live; rp.lstride = progs.lstride;
+  rp.P = P; rp.T = T;
+  rp.B = d.B; rp.K = d.K; rp.n_obs = d.n_obs; rp.n_targets = d.n_targets; rp.n_params = d.n_params;
+  rp.state_size = d.state_size; rp.max_steps = d.max_steps;
+  rp.dt0 = d.dt0; rp.max_fitness = d.max_fitness; rp.obs_noise = d.obs_noise; rp.size_parsimony = size_parsimony;
+  rp.partitionable = d.threefry_partitionable;
+  rp.x0 = d.x0; rp.ts = d.ts; rp.targets = d.targets; rp.params = d.params; rp.ys_true = d.ys_true;
+  rp.obs_keys = d.obs_keys;
+  rp.fitness = fitness;
+  if (traj) {
+    rp.xs_o = traj->xs; rp.ys_o = traj->ys; rp.us_o = traj->us; rp.act_o = traj->activities;
+    rp.tf_o = traj->traj_fitness;
+  }
+  rp.steps_done = steps_done;
+  int n_data, n_latent;
+  const int reserved = mtgp_rollout_slot_map(d, T, &n_data, &n_latent);
+  rp.n_latent = n_latent;
+  if (d.kind == MTGP_EVAL_SR) {
+    rp.slot_lat = 0; rp.slot_u = 0; rp.slot_target = 0;
+  } else if (d.kind == MTGP_EVAL_STATIC) {
+    rp.slot_lat = 0; rp.slot_u = 0; rp.slot_target = d.n_obs;
+  } else {
+    rp.slot_lat = d.n_obs;
+    rp.slot_u = d.n_obs + d.state_size;
+    rp.slot_target = d.n_obs + d.state_size + (T - d.state_size);
+  }
+  rp.slot_out = n_data;
+  rp.slot_state = n_data + n_latent;
+  if (reserved != progs.tmp_base) {
+    mtgp_set_error("internal: slot map mismatch (%d vs %d)", reserved, progs.tmp_base);
+    return MTGP_ERR_INVALID_ARGUMENT;
+  }
+  rp.slots_per_warp = progs.tmp_base + progs.n_tmp;
+  rp.prog_words_per_warp = T * progs.lstride;
+  const size_t smem = 16 * kWarpsPerCta + (size_t)kWarpsPerCta * rp.prog_words_per_warp * sizeof(uint2) +
+                      (size_t)kWarpsPerCta * rp.slots_per_warp * 32 * sizeof(float);
+  if (smem > 227 * 1024) {
+    mtgp_set_error("rollout needs %zu bytes of shared memory per CTA (T=%d, N=%d): over the 227 KB limit", smem, T, N);
+    return MTGP_ERR_UNSUPPORTED;
+  }
+#define DISPATCH(KIND, ENV) return launch_kind_env<KIND, ENV>(rp, smem, stream)
+  if (d.kind == MTGP_EVAL_SR) DISPATCH(MTGP_EVAL_SR, MTGP_ENV_NONE);
+  if (d.kind == MTGP_EVAL_STATIC) {
+    if (d.env_id == MTGP_ENV_ACROBOT) DISPATCH(MTGP_EVAL_STATIC, MTGP_ENV_ACROBOT);
+    if (d.env_id == MTGP_ENV_HARMONIC) DISPATCH(MTGP_EVAL_STATIC, MTGP_ENV_HARMONIC);
+    if (d.env_id == MTGP_ENV_REACTOR) DISPATCH(MTGP_EVAL_STATIC, MTGP_ENV_REACTOR);
+  }
+  if (d.kind == MTGP_EVAL_DYNAMIC) {
+    if (d.env_id == MTGP_ENV_ACROBOT) DISPATCH(MTGP_EVAL_DYNAMIC, MTGP_ENV_ACROBOT);
+    if (d.env_id == MTGP_ENV_HARMONIC) DISPATCH(MTGP_EVAL_DYNAMIC, MTGP_ENV_HARMONIC);
+    if (d.env_id == MTGP_ENV_REACTOR) DISPATCH(MTGP_EVAL_DYNAMIC, MTGP_ENV_REACTOR);
+  }
+#undef DISPATCH
+  mtgp_set_error("unknown evaluator kind %d / environment %d", d.kind, d.env_id);
+  return MTGP_ERR_INVALID_ARGUMENT;
+}

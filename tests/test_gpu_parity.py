@@ -1,0 +1,249 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Bar (BASELINE.json north_star): bytecode/tree decoding bit-exact; per-individual fp32 fitness within
+rtol 1e-5 with identical NaN/inf penalty handling.  Because oracle and kernels share the numerical
+contract (include/mtgp_math.h) and neither contracts FMAs, per-trajectory results are expected to
+be BIT-IDENTICAL; only the mean over the batch (shuffle tree vs sequential) may differ in the last ulp.
+"""
+import numpy as np
+import pytest
+
+from multitreegp_b200 import abi
+from tests import util
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def engine():
+    import torch
+    from multitreegp_b200.engine import FitnessEngine
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return FitnessEngine()
+
+
+def _dev(engine, a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).to(engine.device)
+
+
+def _gpu_rollout(engine, lib, pop, data, **kw):
+    from multitreegp_b200.engine import DeviceData
+    out = engine.rollout_fitness(_dev(engine, pop), lib.table(), DeviceData(data, engine.device), **kw)
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def _assert_fitness(gpu, ref, max_fitness):
+    assert np.isfinite(gpu).all() and np.isfinite(ref).all()
+    np.testing.assert_array_equal(gpu == max_fitness, ref == max_fitness)  # identical penalty handling
+    np.testing.assert_allclose(gpu, ref, rtol=RTOL, atol=0)
+
+
+def test_encode_decode_bit_exact(engine):
+    rng = np.random.default_rng(0)
+    lib, pop, _ = util.control_case("acrobot", abi.EVAL_DYNAMIC, rng, P=257, N=30)
+    # add rows the reference never produces but whose bits must survive: -0.0, denormals, nan coefficients
+    pop[3, 0, 5, 3] = -0.0
+    pop[4, 1, 7, 3] = np.float32(1e-42)
+    pop[5, 2, 29, 3] = np.nan
+    d = _dev(engine, pop)
+    bc, arrs = engine.encode(d, lib.table())
+    back = engine.decode(bc, *pop.shape[:3]).cpu().numpy()
+    assert (back.view(np.uint32) == pop.view(np.uint32)).all()
+    flags = arrs["flags"].cpu().numpy()
+    assert (flags & abi.BC_LOSSY == 0).all() and (flags & abi.BC_CANONICAL != 0).all()
+    np.testing.assert_array_equal(arrs["live"].cpu().numpy(), (pop[..., 0] != 0).sum(-1))
+    # split arrays (nodes [.,3], coefficients [.,1]) as shard_eval hands them over
+    bc2, arrs2 = engine.encode_split(_dev(engine, pop[..., :3]), _dev(engine, pop[..., 3:]), lib.table())
+    for k in arrs:
+        assert (arrs[k].cpu().numpy() == arrs2[k].cpu().numpy()).all() or k == "coef"
+    assert (arrs["coef"].cpu().numpy().view(np.uint32) == arrs2["coef"].cpu().numpy().view(np.uint32)).all()
+
+
+def test_encode_lossy_flag(engine):
+    rng = np.random.default_rng(1)
+    lib, pop, _ = util.sr_case(rng, P=4)
+    pop[1, 0, -1, 0] = 2.5      # non-integral node id
+    pop[2, 1, -1, 1] = 1e9      # index out of int16 range
+    _, arrs = engine.encode(_dev(engine, pop), lib.table())
+    flags = arrs["flags"].cpu().numpy()
+    assert flags[1, 0] & abi.BC_LOSSY and flags[2, 1] & abi.BC_LOSSY and not flags[0, 0] & abi.BC_LOSSY
+
+
+def test_sr_rollout_parity(engine, oracle):
+    rng = np.random.default_rng(2)
+    lib, pop, data = util.sr_case(rng, P=300, B=16, T_end=6.0, dt0=0.01)
+    ref = oracle.rollout_population(pop, lib.table(), data, trajectories=True)
+    gpu = _gpu_rollout(engine, lib, pop, data, trajectories=True, count_steps=True)
+    assert util.same_or_both_nan(gpu["traj_fitness"], ref["traj_fitness"]).all()
+    assert util.same_or_both_nan(gpu["xs"], ref["xs"]).all()
+    _assert_fitness(gpu["fitness"], ref["fitness"], 1e5)
+    assert int(gpu["steps"][0]) == ref["steps"]
+    assert (ref["fitness"] == 1e5).any() and (ref["fitness"] < 1e5).any()  # both branches exercised
+
+
+@pytest.mark.parametrize("env_name", ["harmonic", "acrobot", "reactor"])
+@pytest.mark.parametrize("kind", [abi.EVAL_STATIC, abi.EVAL_DYNAMIC])
+@pytest.mark.parametrize("obs_noise", [0.0, 0.1])
+def test_control_rollout_parity(engine, oracle, env_name, kind, obs_noise):
+    rng = np.random.default_rng(hash((env_name, kind, obs_noise > 0)) % 2 ** 32)
+    # the CSTR is stiff: explicit Euler needs a small step or every random policy ends in the penalty
+    grid = dict(T_end=2.0, dt_save=0.04, dt0=0.002) if env_name == "reactor" else dict(T_end=10.0, dt_save=0.2, dt0=0.05)
+    lib, pop, data = util.control_case(env_name, kind, rng, P=200, B=16, obs_noise=obs_noise,
+                                       param_mode="Constant" if env_name == "acrobot" else "Different", **grid)
+    ref = oracle.rollout_population(pop, lib.table(), data, trajectories=True)
+    gpu = _gpu_rollout(engine, lib, pop, data, trajectories=True, count_steps=True)
+    for k in ("xs", "ys", "us", "traj_fitness") + (("activities",) if kind == abi.EVAL_DYNAMIC else ()):
+        ok = util.same_or_both_nan(gpu[k], ref[k])
+        assert ok.all(), f"{k}: {(~ok).sum()} of {ok.size} elements differ"
+    _assert_fitness(gpu["fitness"], ref["fitness"], 1e4)
+    assert int(gpu["steps"][0]) == ref["steps"]
+
+
+def test_threefry_original_mode(engine, oracle):
+    rng = np.random.default_rng(5)
+    for env_name in ("acrobot", "reactor", "harmonic"):  # n_obs = 4, 3 (odd: zero pad), 2
+        lib, pop, data = util.control_case(env_name, abi.EVAL_STATIC, rng, P=40, B=8, T_end=3.0, obs_noise=0.1,
+                                           partitionable=False)
+        ref = oracle.rollout_population(pop, lib.table(), data)
+        gpu = _gpu_rollout(engine, lib, pop, data, trajectories=True)
+        assert util.same_or_both_nan(gpu["traj_fitness"], ref["traj_fitness"]).all()
+
+
+def test_batch_sizes_and_ragged_edges(engine, oracle):
+    rng = np.random.default_rng(6)
+    for B in (1, 5, 32, 33, 70):     # partial warps, exactly one warp, more than one pass
+        for P in (1, 3, 6):          # partial CTAs
+            lib, pop, data = util.control_case("harmonic", abi.EVAL_DYNAMIC, rng, P=P, B=B, T_end=3.0)
+            ref = oracle.rollout_population(pop, lib.table(), data)
+            gpu = _gpu_rollout(engine, lib, pop, data, trajectories=True)
+            assert util.same_or_both_nan(gpu["traj_fitness"], ref["traj_fitness"]).all()
+            _assert_fitness(gpu["fitness"], ref["fitness"], 1e4)
+
+
+def test_max_steps_and_odd_time_grids(engine, oracle):
+    rng = np.random.default_rng(7)
+    # dt0 larger than the save spacing (several saves per step), dt0 not dividing the horizon, max_steps hit
+    for dt0, max_steps in ((0.5, 16 ** 4), (0.07, 16 ** 4), (0.05, 37)):
+        lib, pop, data = util.control_case("harmonic", abi.EVAL_STATIC, rng, P=50, B=8, T_end=5.0, dt0=dt0,
+                                           max_steps=max_steps)
+        ref = oracle.rollout_population(pop, lib.table(), data, trajectories=True)
+        gpu = _gpu_rollout(engine, lib, pop, data, trajectories=True, count_steps=True)
+        assert util.same_or_both_nan(gpu["xs"], ref["xs"]).all()
+        assert util.same_or_both_nan(gpu["traj_fitness"], ref["traj_fitness"]).all()
+        assert int(gpu["steps"][0]) == ref["steps"]
+
+
+def test_acrobot_time_grid_not_starting_at_zero(engine, oracle):
+    """ts[k]/(ts[1]-ts[0]) > k+1: the kernel's running-prefix cost is not exact and it must take the
+    two-pass route (acrobot.py:82 evaluated literally)."""
+    rng = np.random.default_rng(8)
+    lib, pop, data = util.control_case("acrobot", abi.EVAL_STATIC, rng, P=100, B=8, T_end=4.0)
+    data.ts = (data.ts + np.float32(3.0)).astype(np.float32)
+    ref = oracle.rollout_population(pop, lib.table(), data)
+    gpu = _gpu_rollout(engine, lib, pop, data, trajectories=True)
+    assert util.same_or_both_nan(gpu["traj_fitness"], ref["traj_fitness"]).all()
+
+
+def test_parsimony_and_host_api(engine, oracle):
+    rng = np.random.default_rng(9)
+    lib, pop, data = util.control_case("acrobot", abi.EVAL_DYNAMIC, rng, P=64, B=16, T_end=5.0, obs_noise=0.1)
+    ref = oracle.rollout_population(pop, lib.table(), data)["fitness"] + np.float32(0.5) * oracle.live_count(pop)
+    host = engine.rollout_fitness_host(pop, lib.table(), data, size_parsimony=0.5)
+    np.testing.assert_allclose(host, ref, rtol=RTOL)
+    dev = _gpu_rollout(engine, lib, pop, data, size_parsimony=0.5)["fitness"]
+    np.testing.assert_array_equal(dev, host)
+
+
+def test_pointwise_parity(engine, oracle):
+    from multitreegp_b200.node_library import NodeLibrary
+    from multitreegp_b200.synthetic import pointwise_data, sample_population
+    rng = np.random.default_rng(10)
+    for n_vars, T, depth, N, n_points in ((2, 1, 8, 255, 1000), (3, 2, 4, 30, 257), (8, 1, 6, 63, 4096)):
+        lib = NodeLibrary(util.OPS_ALL, [[f"x{i}" for i in range(n_vars)]] * 1, [T])
+        pop = sample_population(rng, 120, lib, depth, N)
+        X, y = pointwise_data(rng, n_points, n_vars)
+        Y = np.repeat(y, T, axis=1).astype(np.float32)
+        ref_f, ref_p = oracle.pointwise_population(pop, lib.table(), X, Y, predictions=True)
+        fit, pred = engine.pointwise_fitness(_dev(engine, pop), lib.table(), _dev(engine, X), _dev(engine, Y),
+                                             predictions=True)
+        ok = util.same_or_both_nan(pred.cpu().numpy(), ref_p)
+        assert ok.all(), f"{(~ok).sum()} predictions differ"
+        _assert_fitness(fit.cpu().numpy(), ref_f, 1e5)
+        fit2 = engine.pointwise_fitness(_dev(engine, pop), lib.table(), _dev(engine, X), _dev(engine, Y))
+        np.testing.assert_array_equal(fit2.cpu().numpy(), fit.cpu().numpy())
+        host = engine.pointwise_fitness_host(pop, lib.table(), X, Y)
+        np.testing.assert_array_equal(host, fit.cpu().numpy())
+
+
+def test_deep_comb_trees_take_the_slow_pointwise_path(engine, oracle):
+    """Left-deep combs need ~N/2 temporaries: more than the fast kernel provisions."""
+    from multitreegp_b200.node_library import NodeLibrary
+    lib = NodeLibrary(util.OPS_SR, [["x0", "x1"]], [1])
+    N = 63
+    tree = np.zeros((N, 4), dtype=np.float32)
+    tree[:, 1:3] = -1
+    # right-nested chain: every operator's left child is an operator applied to two leaves
+    # rows (ascending): build  f_k = (x0 * x1) + f_{k-1}  so that many right operands stay live
+    rows = []
+
+    def emit(idv, a=-1, b=-1, c=0.0):
+        rows.append([idv, a, b, c])
+        return len(rows) - 1
+    ids = lib.string_to_node
+
+    def build(depth):
+        if depth == 0:
+            return emit(ids["x0"])
+        r = build(depth - 1)                      # right subtree first (postfix order)
+        l1 = emit(ids["x1"]); l0 = emit(1, c=0.5 + depth)
+        left = emit(ids["*"], l0, l1)             # a = i-1, b = i-2
+        return emit(ids["+"], left, r)
+    build(12)
+    tree[N - len(rows):] = np.array(rows, dtype=np.float32)
+    off = N - len(rows)
+    live = tree[off:]
+    live[:, 1] = np.where(live[:, 1] >= 0, live[:, 1] + off, -1)
+    live[:, 2] = np.where(live[:, 2] >= 0, live[:, 2] + off, -1)
+    pop = np.tile(tree[None, None], (9, 1, 1, 1)).astype(np.float32)
+    rng = np.random.default_rng(11)
+    X = rng.normal(size=(300, 2)).astype(np.float32)
+    Y = rng.normal(size=(300, 1)).astype(np.float32)
+    ref_f, ref_p = oracle.pointwise_population(pop, lib.table(), X, Y, predictions=True)
+    fit, pred = engine.pointwise_fitness(_dev(engine, pop), lib.table(), _dev(engine, X), _dev(engine, Y),
+                                         predictions=True)
+    assert util.same_or_both_nan(pred.cpu().numpy(), ref_p).all()
+    _assert_fitness(fit.cpu().numpy(), ref_f, 1e5)
+
+
+def test_evaluator_classes_drop_in(engine, oracle):
+    """The reference-facing classes: same constructor/call protocol as the reference evaluators."""
+    from multitreegp_b200.evaluators import dynamic_evaluate, feedforward_evaluate, SR_evaluator
+    from multitreegp_b200.environments.control_environments import Acrobot
+    rng = np.random.default_rng(12)
+    env = Acrobot(0.05, 0.1)
+    ops = [("+", lambda x, y: x + y, 2, 0.5), ("-", lambda x, y: x - y, 2, 0.1), ("*", lambda x, y: x * y, 2, 0.5),
+           ("sin", lambda x: np.sin(x), 1, 0.1), ("cos", lambda x: np.cos(x), 1, 0.1)]
+    variable_list = [["y1", "y2", "y3", "y4", "a1", "a2", "u"], ["a1", "a2"]]
+    ev = dynamic_evaluate.Evaluator(env, 2, 0.05).bind(ops, variable_list, [2, 1])
+    B = 8
+    x0, targets = env.sample_init_states(B, rng)
+    ts = np.arange(0, 5, 0.2, dtype=np.float32)
+    params = env.sample_params(B, "Constant", ts, rng)
+    keys = util.random_keys(rng, B)
+    data = (x0, ts, targets, keys, keys, params)
+    pop = util.sample_population(rng, 32, ev.library, 4, 30)
+    rd = ev.rollout_data(data)
+    ref = oracle.rollout_population(pop, ev.library.table(), rd, trajectories=True)
+    fit = ev(pop[..., 3:], pop[..., :3], data, tree_evaluator=None)            # vmapped call protocol
+    np.testing.assert_allclose(fit, ref["fitness"], rtol=RTOL)
+    one = ev(pop[5, :, :, 3:], pop[5, :, :, :3], data, None)                   # single-candidate protocol
+    np.testing.assert_allclose(one, ref["fitness"][5], rtol=RTOL)
+    xs, ys, us, act, f = ev.evaluate_candidate(pop[5], data, None)
+    assert xs.shape == (B, ts.size, 4) and us.shape == (B, ts.size, 1) and act.shape == (B, ts.size, 2)
+    assert util.same_or_both_nan(xs, ref["xs"][5]).all() and util.same_or_both_nan(f, ref["traj_fitness"][5]).all()
+    with pytest.raises(NotImplementedError):
+        feedforward_evaluate.Evaluator(env, 0.05, solver="Dopri5")
+    with pytest.raises(ValueError):
+        SR_evaluator.Evaluator().bind([("pow", 2)], [["x0"]], [1])
