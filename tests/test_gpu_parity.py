@@ -52,8 +52,18 @@ def test_encode_decode_bit_exact(engine):
     back = engine.decode(bc, *pop.shape[:3]).cpu().numpy()
     assert (back.view(np.uint32) == pop.view(np.uint32)).all()
     flags = arrs["flags"].cpu().numpy()
-    assert (flags & abi.BC_LOSSY == 0).all() and (flags & abi.BC_CANONICAL != 0).all()
+    assert (flags & abi.BC_LOSSY == 0).all()
     np.testing.assert_array_equal(arrs["live"].cpu().numpy(), (pop[..., 0] != 0).sum(-1))
+    # the lowering pass adds the canonical-layout flag (every tree the reference's operators make has it)
+    lib2, pop2, _ = util.control_case("acrobot", abi.EVAL_DYNAMIC, rng, P=64, N=30)
+    bc3, arrs3 = engine.encode(_dev(engine, pop2), lib2.table())
+    engine.lower(bc3, 64, 3, 30, lib2.table(), tmp_base=12)
+    assert (arrs3["flags"].cpu().numpy() == abi.BC_CANONICAL).all()
+    pop2[0, 0, -1, 1] = 3  # break a = i-1
+    bc3, arrs3 = engine.encode(_dev(engine, pop2), lib2.table())
+    engine.lower(bc3, 64, 3, 30, lib2.table(), tmp_base=12)
+    f3 = arrs3["flags"].cpu().numpy()
+    assert f3[0, 0] == 0 and (f3.reshape(-1)[1:] == abi.BC_CANONICAL).all()
     # split arrays (nodes [.,3], coefficients [.,1]) as shard_eval hands them over
     bc2, arrs2 = engine.encode_split(_dev(engine, pop[..., :3]), _dev(engine, pop[..., 3:]), lib.table())
     for k in arrs:
