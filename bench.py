@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the population fitness-evaluation hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c5|c3|c2|c4]
+
+One "step" = one pass of the hot path over one synthetic population: encode -> lower -> fused
+rollout (-> NCCL all-gather of the fitness shards for N > 1), i.e. what
+GeneticProgramming.evaluate_population does once per generation (genetic_programming.py:403-433).
+
+Default workload (N = 1): BASELINE.json configs[4], "DynamicPolicy rollout sweep": population
+65 536 x 32 initial conditions x 2 000 Euler steps, 3 trees (2 latent + 1 readout) of depth <= 6
+(max_nodes 63), Acrobot with observation noise 0.1 as in examples/DynamicPolicy.ipynb.  Under
+torchrun every rank evaluates its own 65 536-individual shard (weak scaling) and the fitness
+vector is all-gathered.  The same JSON line carries the pointwise-regression scale-up (configs[3])
+as `secondary`, the roofline of the dominant kernel, the CPU baseline and the end-to-end number.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from multitreegp_b200 import abi  # noqa: E402
+from multitreegp_b200.environments.control_environments import Acrobot  # noqa: E402
+from multitreegp_b200.node_library import NodeLibrary  # noqa: E402
+from multitreegp_b200.rollout_data import RolloutData  # noqa: E402
+from multitreegp_b200.synthetic import pointwise_data, random_keys, sample_population  # noqa: E402
+
+OPS_CONTROL = [("+", 2, 0.5), ("-", 2, 0.1), ("*", 2, 0.5), ("sin", 1, 0.1), ("cos", 1, 0.1)]
+OPS_SR = [("+", 2, 0.5), ("-", 2, 0.1), ("*", 2, 0.5), ("/", 2, 0.1)]
+
+WORKLOADS = {
+    # name: (description, kind, P, B, depth, N, T_end, dt_save, dt0, state_size)
+    "c5": ("DynamicPolicy rollout sweep: pop 65536 x 32 ICs x 2000 steps, depth<=6 (BASELINE configs[4])",
+           abi.EVAL_DYNAMIC, 65536, 32, 6, 63, 50.2, 0.2, 0.025, 2),
+    "c3": ("DynamicPolicy.ipynb: pop 4096 x 32 ICs x 1000 steps (BASELINE configs[2])",
+           abi.EVAL_DYNAMIC, 4096, 32, 4, 30, 50.2, 0.2, 0.05, 2),
+    "c2": ("StaticPolicy.ipynb: pop 1000 x 16 ICs, Euler dt0=0.05 (BASELINE configs[1])",
+           abi.EVAL_STATIC, 1000, 16, 4, 30, 50.0, 0.2, 0.05, 0),
+}
+C4 = dict(P=100_000, n_points=100_000, n_vars=2, depth=8, N=255)
+
+FP32_LANES_PER_SM, N_SM = 128, 148
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except OSError:
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+# ---- workloads ---------------------------------------------------------------------------------------
+def control_library(env, kind, state_size):
+    obs = [f"y{i + 1}" for i in range(env.n_obs)]
+    if kind == abi.EVAL_STATIC:
+        return NodeLibrary(OPS_CONTROL, [obs], [env.n_control])
+    lat = [f"a{i + 1}" for i in range(state_size)]
+    return NodeLibrary(OPS_CONTROL, [obs + lat + ["u"], lat], [state_size, env.n_control])  # DynamicPolicy.ipynb:100-102
+
+
+def make_rollout_workload(name, seed, P_override=None, obs_noise=0.1):
+    desc, kind, P, B, depth, N, T_end, dt_save, dt0, S = WORKLOADS[name]
+    P = P_override or P
+    rng = np.random.default_rng(seed)
+    env = Acrobot(0.05, obs_noise)
+    lib = control_library(env, kind, S)
+    pop = sample_population(rng, P, lib, depth, N)
+    x0, targets = env.sample_init_states(B, rng)
+    ts = np.arange(0, T_end, dt_save, dtype=np.float32)
+    params = np.stack(env.sample_params(B, "Constant", ts, rng), axis=1)
+    data = RolloutData(kind=kind, env_id=env.env_id, x0=x0, ts=ts, dt0=dt0, max_fitness=1e4, targets=targets,
+                       obs_keys=random_keys(rng, B), params=params, n_obs=env.n_obs, state_size=S,
+                       obs_noise=obs_noise)
+    return dict(name=name, desc=desc, lib=lib, pop=pop, data=data, env=env, kind=kind, B=B, N=N, S=S,
+                n_sched=len(_schedule(ts, dt0)))
+
+
+def _schedule(ts, dt0):
+    """Number of Euler steps of the diffrax loop in float32 (same arithmetic as the kernel)."""
+    f = np.float32
+    t1, tprev, dt0 = f(ts[-1]), f(ts[0]), f(dt0)
+    tnext = min(f(tprev + dt0), t1)
+    out = []
+    while tprev < t1:
+        out.append(tprev)
+        tprev = min(tnext, t1)
+        nn = f(tnext + dt0)
+        tnext = t1 if nn > f(t1 - f(1e-6)) else nn
+    return out
+
+
+def algorithmic_ops_per_step(w):
+    """algorithmic work of ONE rollout-step (every add/sub/mul/div/trig/... = 1)."""
+    pop, lib, data = w["pop"], w["lib"], w["data"]
+    arity = lib.slots[np.clip(pop[..., 0].astype(np.int64), 0, lib.n_ids - 1)]
+    tree_ops = float((arity > 0).sum()) / pop.shape[0]           # operator rows per individual (all trees)
+    D, n_obs, S = data.D, data.n_obs, w["S"]
+    flops = 75.0 + tree_ops + n_obs * (2 * D - 1) + 6.0 + 2.0 * (D + S)   # Acrobot drift, trees, C@x, wrap, Euler
+    int_ops = 0.0
+    if data.obs_noise != 0.0:
+        flops += n_obs * (2 * n_obs - 1) + n_obs + n_obs * 44.0   # normal@W, + noise, bits->normal (erfinv, log1p)
+        int_ops = (1 + n_obs) * 75.0                               # threefry2x32: fold_in + one block per value
+    return flops, int_ops, tree_ops
+
+
+# ---- clocks ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- CPU arms ---------------------------------------------------------------------------------------------
+def cpu_sample_size(w, target_s, n_threads=0):
+    """How many individuals the oracle evaluates in about target_s seconds on this host."""
+    from oracle import pyoracle as po
+    po.build()
+    probe = w["pop"][:32]
+    t = time.perf_counter(); po.rollout_population(probe, w["lib"].table(), w["data"], n_threads)
+    dt = time.perf_counter() - t
+    n = int(min(w["pop"].shape[0], max(32, 32 * target_s / max(dt, 1e-4))))
+    return max(32, n - n % 8)
+
+
+def cpu_time_rollout(w, target_s, n_threads=0, n=None):
+    """Times the oracle (CPU restatement, all host threads) on a bounded sample of the workload."""
+    from oracle import pyoracle as po
+    n = n or cpu_sample_size(w, target_s, n_threads)
+    sample = w["pop"][:n]
+    t = time.perf_counter(); out = po.rollout_population(sample, w["lib"].table(), w["data"], n_threads)
+    dt = time.perf_counter() - t
+    return out["steps"] / dt, n, out["steps"], dt, po.num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  JAX/diffrax are not
+    installable in this image, so this is the oracle port (oracle/mtgp_oracle.c, every row of every
+    tree evaluated like the reference's fori_loop, OpenMP over individuals) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = make_rollout_workload(args.workload, seed=1000, P_override=4096)
+    times, steps_total = [], 0
+    n = cpu_sample_size(w, args.ref_step_seconds)
+    for i in range(args.warmup + args.steps):
+        rate, n, steps, dt, cores = cpu_time_rollout(w, args.ref_step_seconds, n=n)
+        if i >= args.warmup:
+            times.append(dt); steps_total += steps
+    value = steps_total / sum(times)
+    sample = f"{n} of {WORKLOADS[args.workload][2]} individuals x {w['B']} trajectories x {w['n_sched']} steps per step"
+    line = {"impl": "reference", "metric": "rollout_steps_per_s", "value": value, "unit": "rollout-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "note": "CPU oracle port of the reference path (JAX not installable here)"},
+            "cpu_baseline": {"value": value, "unit": "rollout-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "rollout-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---- GPU arm --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--population", type=int, default=None, help="override the per-GPU population (debug)")
+    ap.add_argument("--obs-noise", type=float, default=0.1)
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ref-step-seconds", type=float, default=2.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from multitreegp_b200.engine import DeviceData, FitnessEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = args.steps, max(args.warmup, 3)
+
+    # population shards: every rank its own individuals (weak scaling: per-GPU work fixed)
+    w = make_rollout_workload(args.workload, seed=1000 + rank, P_override=args.population, obs_noise=args.obs_noise)
+    P = w["pop"].shape[0]
+    eng = FitnessEngine(dev)
+    table = w["lib"].table()
+    pop_pinned = torch.from_numpy(w["pop"]).pin_memory()
+    pop_d = pop_pinned.to(dev)
+    data_d = DeviceData(w["data"], dev)
+    fitness_all = torch.empty((world * P,), dtype=torch.float32, device=dev)
+
+    def step():
+        out = eng.rollout_fitness(pop_d, table, data_d, count_steps=True)
+        if world > 1:
+            dist.all_gather_into_tensor(fitness_all, out["fitness"])
+        return out
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(W):
+        step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms, steps_done = [], 0
+    sync_all()
+    ev0.record()
+    outs = [step() for _ in range(K)]
+    ev1.record()
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = ev0.elapsed_time(ev1)
+    steps_done = sum(int(o["steps"].item()) for o in outs)
+    t = torch.tensor([elapsed_ms, float(steps_done)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        elapsed_ms, steps_done = float(tmax[0]), float(tsum[1])
+    value = steps_done / (elapsed_ms * 1e-3)
+
+    # ---- rollout kernel alone (CUDA events on the launching stream) for the roofline --------------
+    n, ns, c, cs, P_, T_, N_ = eng._split(pop_d)
+    bc, arrs = eng.encode(pop_d, table)
+    import ctypes as C
+    desc = data_d.desc()
+    ws = eng._workspace(eng.lib.mtgp_workspace_bytes(P, T_, N_, C.byref(desc)))
+    fit = torch.empty((P,), dtype=torch.float32, device=dev)
+    from multitreegp_b200._lib import check
+    roll_ms = []
+    for i in range(2 + min(K, 5)):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # mtgp_rollout = lower + rollout; lower is timed separately below and subtracted
+        a.record()
+        check(eng.lib.mtgp_rollout(bc, P, T_, N_, C.byref(table), C.byref(desc), fit.data_ptr(), None, None,
+                                   ws.data_ptr(), ws.numel(), eng._stream()))
+        b.record(); torch.cuda.synchronize(dev)
+        if i >= 2:
+            roll_ms.append(a.elapsed_time(b))
+    low_ms = []
+    n_data = desc.n_obs + desc.n_targets + (w["S"] + 1 if w["kind"] == abi.EVAL_DYNAMIC else 0)
+    tmp_base = n_data + 2 * w["S"]
+    for i in range(4):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); eng.lower(bc, P, T_, N_, table, tmp_base=tmp_base); b.record()
+        torch.cuda.synchronize(dev)
+        if i >= 1:
+            low_ms.append(a.elapsed_time(b))
+    kernel_ms = float(np.mean(roll_ms)) - float(np.mean(low_ms))
+    flops, int_ops, tree_ops = algorithmic_ops_per_step(w)
+    per_launch_steps = steps_done / (K * world)
+    peaks, peak_src = measured_peaks()
+    sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+    fp32_peak = N_SM * FP32_LANES_PER_SM * 2 * sm_mhz * 1e6 / 1e12
+    achieved = per_launch_steps * (flops + int_ops) / (kernel_ms * 1e-3) / 1e12
+    roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": achieved / fp32_peak, "traffic": None, "kernel": "k_rollout<DYNAMIC,ACROBOT,noise>",
+                "kernel_ms": kernel_ms, "ops_per_rollout_step": {"fp": flops, "int_prng": int_ops, "tree_ops": tree_ops},
+                "peak_note": f"non-tensor FP32: 148 SM x 128 lanes x 2 (FMA) x {sm_mhz:.0f} MHz ({peak_src} clock); "
+                             "the path runs un-fused IEEE ops by contract, whose ceiling is half of this"}
+
+    # ---- end to end: HOST buffers through the evaluator class (H2D + kernels + D2H every step) ------
+    from multitreegp_b200.evaluators import dynamic_evaluate, feedforward_evaluate
+    if w["kind"] == abi.EVAL_DYNAMIC:
+        ev = dynamic_evaluate.Evaluator(w["env"], w["S"], w["data"].dt0, library=w["lib"])
+    else:
+        ev = feedforward_evaluate.Evaluator(w["env"], w["data"].dt0, library=w["lib"])
+    pop_host = pop_pinned.numpy()
+    for _ in range(2):
+        ev.evaluate_population(pop_host, w["data"])
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        fit_host = ev.evaluate_population(pop_host, w["data"])
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = steps_done / float(te[0])
+    h2d = pop_host.nbytes + sum(a.nbytes for a in (w["data"].x0, w["data"].ts, w["data"].obs_keys, w["data"].params))
+    e2e = {"value": e2e_value, "unit": "rollout-steps/s", "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(fit_host.nbytes)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    line = {"metric": "rollout_steps_per_s", "value": value, "unit": "rollout-steps/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "population_per_gpu": P, "trees": int(w["pop"].shape[1]),
+                       "max_nodes": w["N"], "trajectories": w["B"], "euler_steps": w["n_sched"],
+                       "obs_noise": args.obs_noise, "env": "Acrobot",
+                       "nominal_rollout_steps_per_step": P * w["B"] * w["n_sched"] * world,
+                       "executed_rollout_steps_per_step": steps_done / K,
+                       "l2": "inputs larger than L2 (population 198 MB per GPU re-read from HBM every step)",
+                       "step": "encode + lower + fused rollout" + (" + NCCL all-gather" if world > 1 else "")},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": 3 * K, "roofline": roofline}
+
+    # ---- secondary metric of BASELINE.json: tree-node evals/s on the pointwise scale-up (configs[3]) ----
+    if not args.no_secondary and world == 1:
+        line["secondary"] = bench_pointwise(eng, dev, K, peaks, peak_src, not args.no_cpu)
+    if not args.no_cpu and world == 1:
+        rate, n, steps, dt, cores = cpu_time_rollout(w, target_s=12.0)
+        line["cpu_baseline"] = {"value": rate, "unit": "rollout-steps/s", "cores": cores, "kind": "port",
+                                "sample": f"{n} of {P} individuals x {w['B']} trajectories x {w['n_sched']} steps "
+                                          f"({steps} rollout-steps in {dt:.1f} s, oracle/mtgp_oracle.c, OpenMP)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_pointwise(eng, dev, K, peaks, peak_src, with_cpu):
+    import torch
+    rng = np.random.default_rng(7)
+    lib = NodeLibrary(OPS_SR + [("sin", 1, 0.1), ("cos", 1, 0.1)], [[f"x{i}" for i in range(C4["n_vars"])]], [1])
+    pop = sample_population(rng, C4["P"], lib, C4["depth"], C4["N"])
+    X, Y = pointwise_data(rng, C4["n_points"], C4["n_vars"])
+    pop_d, Xd, Yd = (torch.from_numpy(a).to(dev) for a in (pop, X, Y))
+    table = lib.table()
+    for _ in range(3):
+        eng.pointwise_fitness(pop_d, table, Xd, Yd)
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(K):
+        eng.pointwise_fitness(pop_d, table, Xd, Yd)
+    b.record(); torch.cuda.synchronize(dev)
+    ms = a.elapsed_time(b) / K
+    live = float((pop[..., 0] != 0).sum())
+    node_evals = live * C4["n_points"]
+    logical_bytes = C4["P"] * C4["n_points"] * (C4["n_vars"] + 1) * 4.0
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    out = {"metric": "tree_node_evals_per_s", "value": node_evals / (ms * 1e-3), "unit": "live node-evals/s",
+           "padded_node_evals_per_s": C4["P"] * C4["N"] * C4["n_points"] / (ms * 1e-3), "ms_per_step": ms,
+           "config": {"workload": "symbolic regression scale-up: pop 100k x 100k points, depth<=8 (BASELINE configs[3])",
+                      "n_vars": C4["n_vars"], "mean_live_nodes": live / C4["P"]},
+           "roofline": {"bound": "hbm", "achieved": logical_bytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                        "frac": logical_bytes / (ms * 1e-3) / 1e9 / hbm, "traffic": None,
+                        "note": f"LOGICAL streaming bytes P*n_points*(n_vars+1)*4 against the {peak_src} HBM copy peak; "
+                                "the 1.2 MB data set is L2-resident, so real DRAM traffic is the population "
+                                "(408 MB) + bytecode/programs, and a fraction above 1 only says the data is reused on chip"}}
+    if with_cpu:
+        from oracle import pyoracle as po
+        n, npts = 256, 4096
+        t = time.perf_counter(); po.pointwise_population(pop[:n], table, X[:npts], Y[:npts]); dt = time.perf_counter() - t
+        live_s = float((pop[:n, ..., 0] != 0).sum())
+        out["cpu_baseline"] = {"value": live_s * npts / dt, "unit": "live node-evals/s", "cores": po.num_threads(),
+                               "kind": "port", "sample": f"{n} individuals x {npts} points ({dt:.1f} s)"}
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -53,11 +53,12 @@ struct Workspace {
   uint32_t* meta;
   float* Xt;
   float* Yt;
+  void* noise;
   size_t bytes;
 };
 
 // layout shared by mtgp_workspace_bytes and every entry point
-Workspace carve(void* ws, int P, int T, int N, int n_points_padded, int n_vars) {
+Workspace carve(void* ws, int P, int T, int N, int n_points_padded, int n_vars, size_t noise_bytes = 0) {
   Carver c(ws);
   Workspace w{};
   const size_t rows = (size_t)P * T * N, trees = (size_t)P * T;
@@ -71,6 +72,7 @@ Workspace carve(void* ws, int P, int T, int N, int n_points_padded, int n_vars) 
   w.meta = c.take<uint32_t>(trees);
   w.Xt = c.take<float>((size_t)n_points_padded * (n_vars > 0 ? n_vars : 0));
   w.Yt = c.take<float>((size_t)n_points_padded * T);
+  w.noise = noise_bytes ? c.take<unsigned char>(noise_bytes) : nullptr;
   w.bytes = align_up(c.off, 256);
   return w;
 }
@@ -191,8 +193,7 @@ const char* mtgp_last_error(void) { return g_err; }
 static int padded_points(int n_points) { return (int)align_up((size_t)(n_points > 0 ? n_points : 0), 256); }
 
 size_t mtgp_workspace_bytes(int P, int T, int N, const mtgp_rollout_desc* rollout) {
-  (void)rollout;
-  return carve(nullptr, P, T, N, 0, 0).bytes;
+  return carve(nullptr, P, T, N, 0, 0, rollout ? mtgp_noise_workspace_bytes(*rollout) : 0).bytes;
 }
 
 size_t mtgp_workspace_bytes_pointwise(int P, int T, int N, int n_points, int n_vars) {
@@ -250,7 +251,7 @@ int mtgp_rollout(mtgp_bytecode bc, int P, int T, int N, const mtgp_node_table* t
   int tmp_base = 0;
   if ((rc = validate_rollout(desc, T, N, table, &tmp_base))) return rc;
   if (!fitness) { mtgp_set_error("fitness is NULL"); return MTGP_ERR_INVALID_ARGUMENT; }
-  Workspace w = carve(workspace, P, T, N, 0, 0);
+  Workspace w = carve(workspace, P, T, N, 0, 0, mtgp_noise_workspace_bytes(*desc));
   if (!workspace || workspace_bytes < w.bytes) {
     mtgp_set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
     return MTGP_ERR_WORKSPACE;
@@ -258,7 +259,7 @@ int mtgp_rollout(mtgp_bytecode bc, int P, int T, int N, const mtgp_node_table* t
   cudaStream_t s = (cudaStream_t)stream;
   if ((rc = mtgp_launch_lower(bc, P, T, N, table, tmp_base, mtgp_lstride(N), w.prog, w.meta, s))) return rc;
   mtgp_programs progs{w.prog, w.meta, mtgp_lstride(N), tmp_base, mtgp_tmp_bound(N)};
-  return mtgp_launch_rollout(progs, nullptr, P, T, N, *desc, 0.0f, fitness, traj, steps_done, s);
+  return mtgp_launch_rollout(progs, nullptr, P, T, N, *desc, 0.0f, fitness, traj, steps_done, w.noise, s);
 }
 
 int mtgp_population_fitness_ex(const float* nodes, int nodes_stride, const float* coef, int coef_stride, int P,
@@ -272,7 +273,7 @@ int mtgp_population_fitness_ex(const float* nodes, int nodes_stride, const float
   int tmp_base = 0;
   if ((rc = validate_rollout(desc, T, N, table, &tmp_base))) return rc;
   if (!fitness || !nodes || !coef) { mtgp_set_error("NULL population / fitness buffer"); return MTGP_ERR_INVALID_ARGUMENT; }
-  Workspace w = carve(workspace, P, T, N, 0, 0);
+  Workspace w = carve(workspace, P, T, N, 0, 0, mtgp_noise_workspace_bytes(*desc));
   if (!workspace || workspace_bytes < w.bytes) {
     mtgp_set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
     return MTGP_ERR_WORKSPACE;
@@ -281,7 +282,7 @@ int mtgp_population_fitness_ex(const float* nodes, int nodes_stride, const float
   if ((rc = mtgp_launch_encode(nodes, nodes_stride, coef, coef_stride, P, T, N, table, w.bc, s))) return rc;
   if ((rc = mtgp_launch_lower(w.bc, P, T, N, table, tmp_base, mtgp_lstride(N), w.prog, w.meta, s))) return rc;
   mtgp_programs progs{w.prog, w.meta, mtgp_lstride(N), tmp_base, mtgp_tmp_bound(N)};
-  return mtgp_launch_rollout(progs, w.bc.live, P, T, N, *desc, size_parsimony, fitness, traj, steps_done, s);
+  return mtgp_launch_rollout(progs, w.bc.live, P, T, N, *desc, size_parsimony, fitness, traj, steps_done, w.noise, s);
 }
 
 int mtgp_population_fitness(const float* nodes, int nodes_stride, const float* coef, int coef_stride, int P, int T,

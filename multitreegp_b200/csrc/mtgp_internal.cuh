@@ -36,8 +36,9 @@ struct mtgp_programs {
 
 int mtgp_launch_rollout(const mtgp_programs& progs, const int32_t* live, int P, int T, int N,
                         const mtgp_rollout_desc& desc, float size_parsimony, float* fitness,
-                        const mtgp_trajectory_out* traj, unsigned long long* steps_done,
+                        const mtgp_trajectory_out* traj, unsigned long long* steps_done, void* noise_ws,
                         cudaStream_t stream);
+size_t mtgp_noise_workspace_bytes(const mtgp_rollout_desc& d);  // 0: noise generated inline
 
 int mtgp_launch_pointwise(const mtgp_programs& progs, const int32_t* live, int P, int T, int N,
                           const float* Xt, const float* Yt, int n_points, int n_points_padded,

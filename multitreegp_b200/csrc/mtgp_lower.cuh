@@ -169,55 +169,47 @@ MTGP_LHD uint32_t mtgp_lower_tree(const uint8_t* op, const int16_t* ra, const in
     if (rx >= 0 && ref[rx] != 255 && --ref[rx] == 0 && kind[rx] == DK_TMP) slots.release((int)payload[rx] - tmp_base);
     if (ry >= 0 && ref[ry] != 255 && --ref[ry] == 0 && kind[ry] == DK_TMP) slots.release((int)payload[ry] - tmp_base);
 
-    uint32_t h, xs = 0, ys = 0;
-    float imm = 0.0f;
-    const bool xm = (xk == DK_VAR || xk == DK_TMP), ym = (yk == DK_VAR || yk == DK_TMP);
-    if (ar == 1) {
-      h = (xk == DK_ACC ? H_UA_BASE : H_UM_BASE) + (uint32_t)(opcode - MTGP_OP_SIN);
-      xs = xp;
-    } else {
-      const bool commutative = (opcode == MTGP_OP_ADD || opcode == MTGP_OP_MUL || opcode == MTGP_OP_MAX ||
-                                opcode == MTGP_OP_MIN);
-      if (commutative) {
-        const uint32_t base = opcode == MTGP_OP_ADD ? H_ADD_BASE : opcode == MTGP_OP_MUL ? H_MUL_BASE
-                            : opcode == MTGP_OP_MAX ? H_MAX_BASE : H_MIN_BASE;
-        // canonical operand order: accumulator first, immediate last
-        if (yk == DK_ACC || (xk == DK_IMM)) {
-          int tk = xk; xk = yk; yk = tk;
-          uint32_t tp = xp; xp = yp; yp = tp;
-        }
-        const bool xm2 = (xk == DK_VAR || xk == DK_TMP), ym2 = (yk == DK_VAR || yk == DK_TMP);
-        if (xk == DK_ACC && ym2) { h = base + K_AM; ys = yp; }
-        else if (xk == DK_ACC) { h = base + K_AI; imm = mtgp_u2f(yp); }
-        else if (xm2 && ym2) { h = base + K_MM; xs = xp; ys = yp; }
-        else { h = base + K_MI; xs = xp; imm = mtgp_u2f(yp); }
-      } else {
-        const uint32_t base = opcode == MTGP_OP_SUB ? H_SUB_BASE : H_DIV_BASE;
-        if (xk == DK_ACC && ym) { h = base + N_AM; ys = yp; }
-        else if (xk == DK_ACC) { h = base + N_AI; imm = mtgp_u2f(yp); }
-        else if (xm && yk == DK_ACC) { h = base + N_MA; xs = xp; }
-        else if (xk == DK_IMM && yk == DK_ACC) { h = base + N_IA; imm = mtgp_u2f(xp); }
-        else if (xm && ym) { h = base + N_MM; xs = xp; ys = yp; }
-        else if (xm) { h = base + N_MI; xs = xp; imm = mtgp_u2f(yp); }
-        else { h = base + N_IM; ys = yp; imm = mtgp_u2f(xp); }
-      }
+    // one instruction: opcode + operand kinds; the (single) immediate rides in the instruction
+    uint32_t xop;
+    switch (opcode) {
+      case MTGP_OP_ADD: xop = X_ADD; break;
+      case MTGP_OP_SUB: xop = X_SUB; break;
+      case MTGP_OP_MUL: xop = X_MUL; break;
+      case MTGP_OP_DIV: xop = X_DIV; break;
+      case MTGP_OP_MAX: xop = X_MAX; break;
+      case MTGP_OP_MIN: xop = X_MIN; break;
+      case MTGP_OP_SIN: xop = X_SIN; break;
+      case MTGP_OP_COS: xop = X_COS; break;
+      case MTGP_OP_EXP: xop = X_EXP; break;
+      case MTGP_OP_LOG: xop = X_LOG; break;
+      case MTGP_OP_SQRT: xop = X_SQRT; break;
+      case MTGP_OP_TANH: xop = X_TANH; break;
+      case MTGP_OP_NEG: xop = X_NEG; break;
+      case MTGP_OP_ABS: xop = X_ABS; break;
+      default: xop = X_MUL; break;  // MTGP_OP_SQUARE = x * x
     }
-    out[n] = mtgp_make_instr(h, MTGP_NO_SLOT, xs, ys, imm);
+    if (opcode == MTGP_OP_SQUARE) { yk = xk; yp = xp; }
+    const uint32_t xkind = (xk == DK_ACC) ? OK_ACC : (xk == DK_IMM ? OK_IMM : OK_MEM);
+    const uint32_t ykind = (ar == 1 && opcode != MTGP_OP_SQUARE) ? OK_ACC
+                         : ((yk == DK_ACC) ? OK_ACC : (yk == DK_IMM ? OK_IMM : OK_MEM));
+    const uint32_t xs = (xkind == OK_MEM) ? xp : 0u, ys = (ykind == OK_MEM) ? yp : 0u;
+    const float imm = (xkind == OK_IMM) ? mtgp_u2f(xp) : ((ykind == OK_IMM) ? mtgp_u2f(yp) : 0.0f);
+    out[n] = mtgp_make_instr(xop, xkind, ykind, MTGP_NO_SLOT, xs, ys, imm);
     last = n++;
     acc_row = i;
     kind[i] = DK_ACC;
   }
   if (!overflow) {
     const int r = N - 1;
-    if (kind[r] == DK_IMM) out[n++] = mtgp_make_instr(H_LOADI, MTGP_NO_SLOT, 0, 0, mtgp_u2f(payload[r]));
-    else if (kind[r] != DK_ACC) out[n++] = mtgp_make_instr(H_LOADM, MTGP_NO_SLOT, payload[r], 0, 0.0f);
+    if (kind[r] == DK_IMM) out[n++] = mtgp_make_instr(X_LOAD, OK_IMM, OK_ACC, MTGP_NO_SLOT, 0, 0, mtgp_u2f(payload[r]));
+    else if (kind[r] != DK_ACC) out[n++] = mtgp_make_instr(X_LOAD, OK_MEM, OK_ACC, MTGP_NO_SLOT, payload[r], 0, 0.0f);
   } else {
     // cannot happen for N within the limits checked on the host; produce NaN rather than garbage
     n = 0;
-    out[n++] = mtgp_make_instr(H_LOADI, MTGP_NO_SLOT, 0, 0, mtgp_nanf());
+    out[n++] = mtgp_make_instr(X_LOAD, OK_IMM, OK_ACC, MTGP_NO_SLOT, 0, 0, mtgp_nanf());
   }
-  out[n] = mtgp_make_instr(H_END, MTGP_NO_SLOT, 0, 0, 0.0f);
-  if (((n + 1) & 1) != 0) out[n + 1] = mtgp_make_instr(H_END, MTGP_NO_SLOT, 0, 0, 0.0f);  // 16-byte granules
+  out[n] = mtgp_make_instr(X_END, 0, 0, MTGP_NO_SLOT, 0, 0, 0.0f);
+  if (((n + 1) & 1) != 0) out[n + 1] = mtgp_make_instr(X_END, 0, 0, MTGP_NO_SLOT, 0, 0, 0.0f);  // 16-byte granules
   return (uint32_t)n | ((uint32_t)slots.high << 16);
 }
 

@@ -17,8 +17,8 @@
 // functions (genetic_programming.py:356-388); this executes only live operator nodes, with the
 // same float32 result for every tree.
 //
-// Instruction = 8 bytes:  .x = handler | store_slot << 8 | x_slot << 16 | y_slot << 24
-//                         .y = immediate (float bits)
+// Instruction = 8 bytes:  .x = opcode | x kind << 4 | y kind << 6 | store_slot << 8 | x_slot << 16 | y_slot << 24
+//                         .y = immediate (float bits)          kinds: accumulator / memory slot / immediate
 // Slot s of a warp's value file is the 32*R floats at  base + s*32*R ; lane l owns elements
 // [l*R, l*R+R) -- conflict-free for R = 1 (4-byte) and R = 4 (16-byte) accesses.
 #pragma once
@@ -32,31 +32,35 @@
 #define MTGP_NO_SLOT 0xFFu
 #define MTGP_MAX_SLOTS 254
 
-enum mtgp_handler : uint32_t {
-  H_END = 0,
-  H_LOADI = 1,  // acc = imm
-  H_LOADM = 2,  // acc = M[x]
-  // unary, operand in A (9) then operand in M (9); order follows mtgp_opcode SIN..SQUARE
-  H_UA_BASE = 3,
-  H_UM_BASE = 12,
-  // commutative binary: ADD, MUL, MAX, MIN x {AM, AI, MM, MI}
-  H_ADD_BASE = 21,
-  H_MUL_BASE = 25,
-  H_MAX_BASE = 29,
-  H_MIN_BASE = 33,
-  // non-commutative: SUB, DIV x {AM, AI, MA, IA, MM, MI, IM}
-  H_SUB_BASE = 37,
-  H_DIV_BASE = 44,
-  H_COUNT = 51
+// Instruction word .x = opcode (bits 0-3) | x kind (bits 4-5) | y kind (bits 6-7) | store slot << 8
+//                       | x slot << 16 | y slot << 24;   .y = immediate (float bits).
+// The opcode set is closed and small on purpose: dispatch is one short compare chain and the three
+// most frequent operators (+ - *) share one branch-free data path.
+enum mtgp_xop : uint32_t {
+  X_END = 0,
+  X_LOAD = 1,  // acc = x
+  X_ADD = 2,
+  X_SUB = 3,
+  X_MUL = 4,   // MTGP_OP_SQUARE is lowered to x * x
+  X_DIV = 5,
+  X_MAX = 6,
+  X_MIN = 7,
+  X_SIN = 8,
+  X_COS = 9,
+  X_EXP = 10,
+  X_LOG = 11,
+  X_SQRT = 12,
+  X_TANH = 13,
+  X_NEG = 14,
+  X_ABS = 15
 };
-// kind offsets inside a binary group
-enum { K_AM = 0, K_AI = 1, K_MM = 2, K_MI = 3 };                                       // commutative
-enum { N_AM = 0, N_AI = 1, N_MA = 2, N_IA = 3, N_MM = 4, N_MI = 5, N_IM = 6 };           // non-commutative
+enum { OK_ACC = 0, OK_MEM = 1, OK_IMM = 2 };  // operand kinds
 
-__host__ __device__ __forceinline__ uint2 mtgp_make_instr(uint32_t h, uint32_t st, uint32_t xs,
-                                                          uint32_t ys, float imm) {
+__host__ __device__ __forceinline__ uint2 mtgp_make_instr(uint32_t op, uint32_t xk, uint32_t yk, uint32_t st,
+                                                          uint32_t xs, uint32_t ys, float imm) {
   uint2 w;
-  w.x = (h & 0xFFu) | ((st & 0xFFu) << 8) | ((xs & 0xFFu) << 16) | ((ys & 0xFFu) << 24);
+  w.x = (op & 15u) | ((xk & 3u) << 4) | ((yk & 3u) << 6) | ((st & 0xFFu) << 8) | ((xs & 0xFFu) << 16) |
+        ((ys & 0xFFu) << 24);
   w.y = mtgp_f2u(imm);
   return w;
 }
@@ -124,90 +128,54 @@ __host__ __device__ __forceinline__ void vf_store(float* lane_base, uint32_t slo
 #define MTGP_FOR_R _Pragma("unroll") for (int r = 0; r < R; r++)
 
 // ---- the interpreter ------------------------------------------------------------------------
-// prog: shared-memory program (terminated by H_END), identical for all lanes of the warp, so
-// every branch below is warp-uniform.  lane_base = value file + lane*R.
+// prog: shared-memory program (terminated by X_END), identical for all lanes of the warp, so every
+// branch below is warp-uniform.  lane_base = value file + lane*R.
 // Returns the value of the tree's root for the R points / trajectories this lane owns.
 template <int R>
-__host__ __device__ __noinline__ Vec<R> mtgp_interpret(const uint2* __restrict__ prog, float* lane_base) {
+__host__ __device__ __forceinline__ Vec<R> mtgp_interpret_inline(const uint2* __restrict__ prog, float* lane_base) {
   Vec<R> acc;
   MTGP_FOR_R acc.v[r] = 0.0f;
   uint2 w = prog[0];
   int pc = 0;
-  while (true) {
-    const uint32_t h = w.x & 0xFFu;
-    if (h == H_END) break;
-    const uint32_t st = (w.x >> 8) & 0xFFu, xs = (w.x >> 16) & 0xFFu, ys = w.x >> 24;
+  while ((w.x & 15u) != X_END) {
+    const uint32_t c = w.x;
     const float imm = mtgp_u2f(w.y);
     w = prog[++pc];  // prefetch the next instruction under this one's arithmetic
-    switch (h) {
-      case H_LOADI: MTGP_FOR_R acc.v[r] = imm; break;
-      case H_LOADM: acc = vf_load<R>(lane_base, xs); break;
-#define U_CASES(OFF, OPC)                                                                        \
-  case H_UA_BASE + OFF: MTGP_FOR_R acc.v[r] = mtgp_apply_unary(OPC, acc.v[r]); break;            \
-  case H_UM_BASE + OFF: {                                                                        \
-    Vec<R> x = vf_load<R>(lane_base, xs);                                                        \
-    MTGP_FOR_R acc.v[r] = mtgp_apply_unary(OPC, x.v[r]);                                         \
-  } break;
-      U_CASES(0, MTGP_OP_SIN)
-      U_CASES(1, MTGP_OP_COS)
-      U_CASES(2, MTGP_OP_EXP)
-      U_CASES(3, MTGP_OP_LOG)
-      U_CASES(4, MTGP_OP_SQRT)
-      U_CASES(5, MTGP_OP_TANH)
-      U_CASES(6, MTGP_OP_NEG)
-      U_CASES(7, MTGP_OP_ABS)
-      U_CASES(8, MTGP_OP_SQUARE)
-#undef U_CASES
-#define C_CASES(BASE, OPC)                                                                       \
-  case BASE + K_AM: {                                                                            \
-    Vec<R> y = vf_load<R>(lane_base, ys);                                                        \
-    MTGP_FOR_R acc.v[r] = mtgp_apply_binary(OPC, acc.v[r], y.v[r]);                              \
-  } break;                                                                                       \
-  case BASE + K_AI: MTGP_FOR_R acc.v[r] = mtgp_apply_binary(OPC, acc.v[r], imm); break;          \
-  case BASE + K_MM: {                                                                            \
-    Vec<R> x = vf_load<R>(lane_base, xs);                                                        \
-    Vec<R> y = vf_load<R>(lane_base, ys);                                                        \
-    MTGP_FOR_R acc.v[r] = mtgp_apply_binary(OPC, x.v[r], y.v[r]);                                \
-  } break;                                                                                       \
-  case BASE + K_MI: {                                                                            \
-    Vec<R> x = vf_load<R>(lane_base, xs);                                                        \
-    MTGP_FOR_R acc.v[r] = mtgp_apply_binary(OPC, x.v[r], imm);                                   \
-  } break;
-      C_CASES(H_ADD_BASE, MTGP_OP_ADD)
-      C_CASES(H_MUL_BASE, MTGP_OP_MUL)
-      C_CASES(H_MAX_BASE, MTGP_OP_MAX)
-      C_CASES(H_MIN_BASE, MTGP_OP_MIN)
-#undef C_CASES
-#define N_CASES(BASE, OPC)                                                                       \
-  case BASE + N_AM: {                                                                            \
-    Vec<R> y = vf_load<R>(lane_base, ys);                                                        \
-    MTGP_FOR_R acc.v[r] = mtgp_apply_binary(OPC, acc.v[r], y.v[r]);                              \
-  } break;                                                                                       \
-  case BASE + N_AI: MTGP_FOR_R acc.v[r] = mtgp_apply_binary(OPC, acc.v[r], imm); break;          \
-  case BASE + N_MA: {                                                                            \
-    Vec<R> x = vf_load<R>(lane_base, xs);                                                        \
-    MTGP_FOR_R acc.v[r] = mtgp_apply_binary(OPC, x.v[r], acc.v[r]);                              \
-  } break;                                                                                       \
-  case BASE + N_IA: MTGP_FOR_R acc.v[r] = mtgp_apply_binary(OPC, imm, acc.v[r]); break;          \
-  case BASE + N_MM: {                                                                            \
-    Vec<R> x = vf_load<R>(lane_base, xs);                                                        \
-    Vec<R> y = vf_load<R>(lane_base, ys);                                                        \
-    MTGP_FOR_R acc.v[r] = mtgp_apply_binary(OPC, x.v[r], y.v[r]);                                \
-  } break;                                                                                       \
-  case BASE + N_MI: {                                                                            \
-    Vec<R> x = vf_load<R>(lane_base, xs);                                                        \
-    MTGP_FOR_R acc.v[r] = mtgp_apply_binary(OPC, x.v[r], imm);                                   \
-  } break;                                                                                       \
-  case BASE + N_IM: {                                                                            \
-    Vec<R> y = vf_load<R>(lane_base, ys);                                                        \
-    MTGP_FOR_R acc.v[r] = mtgp_apply_binary(OPC, imm, y.v[r]);                                   \
-  } break;
-      N_CASES(H_SUB_BASE, MTGP_OP_SUB)
-      N_CASES(H_DIV_BASE, MTGP_OP_DIV)
-#undef N_CASES
-      default: break;
+    const uint32_t op = c & 15u, xk = (c >> 4) & 3u, yk = (c >> 6) & 3u, st = (c >> 8) & 0xFFu;
+    Vec<R> x = acc, y = acc;
+    if (xk == OK_MEM) x = vf_load<R>(lane_base, (c >> 16) & 0xFFu);
+    if (yk == OK_MEM) y = vf_load<R>(lane_base, c >> 24);
+    if (xk == OK_IMM) { MTGP_FOR_R x.v[r] = imm; }
+    if (yk == OK_IMM) { MTGP_FOR_R y.v[r] = imm; }
+    if (op <= X_MUL) {
+      // LOAD / ADD / SUB / MUL: one straight-line path (x - y == x + (-y) exactly)
+      const uint32_t flip = (op == X_SUB) ? 0x80000000u : 0u;
+      MTGP_FOR_R {
+        const float s = x.v[r] + mtgp_u2f(mtgp_f2u(y.v[r]) ^ flip);
+        const float m = x.v[r] * y.v[r];
+        acc.v[r] = (op == X_MUL) ? m : ((op == X_LOAD) ? x.v[r] : s);
+      }
+    } else {
+      switch (op) {
+        case X_DIV: MTGP_FOR_R acc.v[r] = x.v[r] / y.v[r]; break;
+        case X_MAX: MTGP_FOR_R acc.v[r] = mtgp_maximumf(x.v[r], y.v[r]); break;
+        case X_MIN: MTGP_FOR_R acc.v[r] = mtgp_minimumf(x.v[r], y.v[r]); break;
+        case X_SIN: MTGP_FOR_R acc.v[r] = mtgp_sinf(x.v[r]); break;
+        case X_COS: MTGP_FOR_R acc.v[r] = mtgp_cosf(x.v[r]); break;
+        case X_EXP: MTGP_FOR_R acc.v[r] = mtgp_expf(x.v[r]); break;
+        case X_LOG: MTGP_FOR_R acc.v[r] = mtgp_logf(x.v[r]); break;
+        case X_SQRT: MTGP_FOR_R acc.v[r] = mtgp_sqrtf(x.v[r]); break;
+        case X_TANH: MTGP_FOR_R acc.v[r] = mtgp_tanhf(x.v[r]); break;
+        case X_NEG: MTGP_FOR_R acc.v[r] = -x.v[r]; break;
+        default: MTGP_FOR_R acc.v[r] = mtgp_absf(x.v[r]); break;  // X_ABS
+      }
     }
     if (st != MTGP_NO_SLOT) vf_store<R>(lane_base, st, acc);
   }
   return acc;
+}
+
+template <int R>
+__host__ __device__ __noinline__ Vec<R> mtgp_interpret(const uint2* __restrict__ prog, float* lane_base) {
+  return mtgp_interpret_inline<R>(prog, lane_base);
 }

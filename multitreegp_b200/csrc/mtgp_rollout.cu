@@ -17,6 +17,8 @@
 // Programs are staged into shared memory with cp.async.bulk (TMA 1-D bulk copy) + mbarrier.
 // Arithmetic order follows the reference source literally (see the oracle for the same
 // expressions); the file is compiled with -fmad=false so nothing is contracted.
+#include <stdlib.h>
+
 #include "mtgp_internal.cuh"
 
 namespace {
@@ -37,6 +39,9 @@ struct RolloutParams {
   float* fitness;
   float *xs_o, *ys_o, *us_o, *act_o, *tf_o;
   unsigned long long* steps_done;
+  const float* noise;  // [cap_steps + K, n_obs, B] precomputed observation noise (NOISE == 1), see k_noise_table
+  int cap_steps;       // rows of the step part of the noise table
+  int min_need, max_need;  // this launch handles individuals whose temporaries are in [min_need, max_need]
   int n_latent;        // state kept in the value file: SR -> T, DYNAMIC -> state_size, STATIC -> 0
   int slot_lat;        // data-vector slot of latent component 0
   int slot_u;          // data-vector slot of the control (control evaluators)
@@ -203,11 +208,41 @@ struct Env {
   }
 
   // EnvironmentBase.f_obs (control_environment_base.py:43-48) + Acrobot.f_obs (acrobot.py:29-32)
-  template <bool NOISE>
-  __device__ __forceinline__ void f_obs(float t, const float* x, float* y, int n_obs, float obs_noise,
-                                        int partitionable) const {
+  // normal(fold_in(key, bits(t)), (n_obs,)) @ W, W = obs_noise * eye (reactor.py:43 scales it)
+  __device__ __forceinline__ void noise_term(float t, int n_obs, float obs_noise, int partitionable,
+                                             float* out) const {
     float nrm[D];
-    if (NOISE) obs_normal<D>(key0, key1, t, n_obs, partitionable, nrm);
+    obs_normal<D>(key0, key1, t, n_obs, partitionable, nrm);
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      if (i < n_obs) {
+        float nacc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+          if (j < n_obs) {
+            float w = (i == j) ? obs_noise : 0.0f;
+            if (ENV == MTGP_ENV_REACTOR) w = w * (i == 2 ? 0.1f : 15.0f);
+            const float term = nrm[j] * w;
+            nacc = (j == 0) ? term : nacc + term;
+          }
+        }
+        out[i] = nacc;
+      }
+    }
+  }
+
+  // NOISE: 0 none, 1 = noise term read from the precomputed table row `nz` (element stride `nzs`),
+  //        2 = generated inline.  All three give the same bits.
+  template <int NOISE>
+  __device__ __forceinline__ void f_obs(float t, const float* x, float* y, int n_obs, float obs_noise,
+                                        int partitionable, const float* nz, int nzs) const {
+    float nt[D];
+    if (NOISE == 2) noise_term(t, n_obs, obs_noise, partitionable, nt);
+    if (NOISE == 1) {
+#pragma unroll
+      for (int i = 0; i < D; i++)
+        if (i < n_obs) nt[i] = __ldg(nz + (size_t)i * nzs);
+    }
 #pragma unroll
     for (int i = 0; i < D; i++) {
       if (i < n_obs) {
@@ -217,19 +252,7 @@ struct Env {
           const float term = ((i == j) ? 1.0f : 0.0f) * x[j];
           acc = (j == 0) ? term : acc + term;
         }
-        if (NOISE) {
-          float nacc = 0.0f;
-#pragma unroll
-          for (int j = 0; j < D; j++) {  // normal @ W
-            if (j < n_obs) {
-              float w = (i == j) ? obs_noise : 0.0f;
-              if (ENV == MTGP_ENV_REACTOR) w = w * (i == 2 ? 0.1f : 15.0f);
-              const float term = nrm[j] * w;
-              nacc = (j == 0) ? term : nacc + term;
-            }
-          }
-          acc = acc + nacc;
-        }
+        if (NOISE != 0) acc = acc + nt[i];
         y[i] = acc;
       }
     }
@@ -340,9 +363,59 @@ struct Env {
   }
 };
 
+// ---- observation-noise table -------------------------------------------------------------------------
+// The noise term of f_obs depends only on (trajectory key, time): it is the same for every individual
+// of the population.  Two tiny kernels compute it once per evaluation:
+//   k_schedule     walks the diffrax time loop (float32, same arithmetic as the rollout kernel) and
+//                  records tprev of every step;
+//   k_noise_table  evaluates normal(fold_in(key_b, bits(t))) @ W for every (step | save point, b).
+// Layout: row r = step s (r < cap) or save point k (r = cap + k); element [r][i][b].
+__global__ void k_schedule(const float* __restrict__ ts, int K, float dt0, int max_steps, int cap,
+                           float* __restrict__ tprev_out, int* __restrict__ n_steps_out) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const float t0 = ts[0], t1 = ts[K - 1];
+  float tprev = t0, tnext = t0 + dt0;
+  tnext = tnext < t1 ? tnext : t1;
+  int n = 0;
+  while (tprev < t1 && n < max_steps && n < cap) {
+    tprev_out[n] = tprev;
+    const float new_tprev = tnext < t1 ? tnext : t1;
+    float new_tnext = tnext + dt0;
+    new_tnext = (new_tnext > t1 - 1e-6f) ? t1 : new_tnext;
+    tprev = new_tprev;
+    tnext = new_tnext;
+    n++;
+  }
+  *n_steps_out = n;
+}
+
+template <int ENV>
+__global__ void __launch_bounds__(256) k_noise_table(const RolloutParams P, const float* __restrict__ tprev,
+                                                    const int* __restrict__ n_steps, float* __restrict__ table) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int rows = P.cap_steps + P.K;
+  if (idx >= (long long)rows * P.B) return;
+  const int r = (int)(idx / P.B), b = (int)(idx % P.B);
+  float t;
+  if (r < P.cap_steps) {
+    if (r >= *n_steps) return;
+    t = tprev[r];
+  } else {
+    t = P.ts[r - P.cap_steps];
+  }
+  Env<ENV> env;
+  env.key0 = P.obs_keys[2 * b];
+  env.key1 = P.obs_keys[2 * b + 1];
+  float nt[Env<ENV>::D];
+  env.noise_term(t, P.n_obs, P.obs_noise, P.partitionable, nt);
+#pragma unroll
+  for (int i = 0; i < Env<ENV>::D; i++)
+    if (i < P.n_obs) table[((size_t)r * P.n_obs + i) * P.B + b] = nt[i];
+}
+
 // ---- the kernel ----------------------------------------------------------------------------------
-template <int KIND, int ENV, bool NOISE>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) k_rollout(const RolloutParams P) {
+template <int KIND, int ENV, int NOISE>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_rollout(const RolloutParams P) {
   constexpr int D = (KIND == MTGP_EVAL_SR) ? 0 : EnvDim<ENV>::D;
   constexpr int DR = D > 0 ? D : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -355,6 +428,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_rollout(const RolloutPara
                                        (size_t)kWarpsPerCta * P.prog_words_per_warp * sizeof(uint2)) +
               (size_t)wic * P.slots_per_warp * 32;
   if (ind >= P.P) return;  // whole warp leaves together (no block-wide barrier below)
+
+  // which launch owns this individual: by the temporaries its programs need (warp-uniform)
+  {
+    int need = 0;
+    for (int t = 0; t < P.T; t++) need = max(need, (int)(P.meta[(size_t)ind * P.T + t] >> 16));
+    if (need < P.min_need || need > P.max_need) return;
+  }
 
   // ---- stage this individual's programs: cp.async.bulk -> shared, completion on an mbarrier ----
   uint64_t* bar = bars + 2 * wic;
@@ -381,6 +461,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_rollout(const RolloutPara
   const int K = P.K, NL = P.n_latent;
   const float t0 = ts[0], t1 = ts[K - 1];
   const float dts = (K > 1) ? ts[1] - ts[0] : 0.0f;  // ts[1]-ts[0], acrobot.py:82
+  const uint2* prog_readout = prog_s + (size_t)((KIND == MTGP_EVAL_DYNAMIC) ? P.state_size : 0) * P.lstride;
   float fit_sum = 0.0f;
   unsigned long long my_steps = 0;
 
@@ -392,6 +473,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_rollout(const RolloutPara
     if (KIND != MTGP_EVAL_SR) env.init(P, bb);
     if (KIND != MTGP_EVAL_SR)
       for (int i = 0; i < P.n_targets; i++) lb[(P.slot_target + i) * 32] = P.targets[bb * P.n_targets + i];
+    const float* nz_base = (NOISE == 1) ? P.noise + bb : nullptr;
+    const int nzs = P.B;
 
     int fs_known = -1;
     bool viol = false;
@@ -401,12 +484,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_rollout(const RolloutPara
       float x[DR], x1[DR];
       if (KIND != MTGP_EVAL_SR) {
 #pragma unroll
-        for (int i = 0; i < D; i++) x[i] = P.x0[bb * D + i];
+        for (int i = 0; i < D; i++) { x[i] = P.x0[bb * D + i]; x1[i] = x[i]; }
       }
       for (int j = 0; j < NL; j++) {
         const float v = (KIND == MTGP_EVAL_SR) ? P.x0[bb * NL + j] : 0.0f;  // a0 = 0 (dynamic_evaluate.py:89)
         lb[(P.slot_state + j) * 32] = v;
         lb[(P.slot_lat + j) * 32] = v;
+        lb[(P.slot_out + j) * 32] = v;
       }
       if (KIND != MTGP_EVAL_SR) { env.sum = 0.0f; env.sum0 = 0.0f; env.fs = -1; }
       float sr_total = 0.0f;
@@ -421,56 +505,65 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_rollout(const RolloutPara
       float tprev = t0, tnext = t0 + P.dt0;
       tnext = tnext < t1 ? tnext : t1;
       int steps = 0, k = 0;
-      while (tprev < t1 && steps < P.max_steps) {
-        if (__ballot_sync(0xFFFFFFFFu, alive && lane_valid) == 0u) break;
-        const float dt = tnext - tprev;
-        float u = 0.0f;
-        float y[DR];
-        if (KIND != MTGP_EVAL_SR) {
-          env.template f_obs<NOISE>(tprev, x, y, P.n_obs, P.obs_noise, P.partitionable);
-          if (KIND == MTGP_EVAL_STATIC) {
+      // One iteration = one Euler step while any lane is still integrating, then the save points that
+      // step covers.  Once the solve is over (t1 reached, max_steps, or every lane's event fired) the
+      // remaining save points are emitted from the inf pre-fill of SaveAt -- by the same code.
+      while (k < K) {
+        const bool stepping = (tprev < t1) && (steps < P.max_steps) &&
+                              (__ballot_sync(0xFFFFFFFFu, alive && lane_valid) != 0u);
+        float save_until = mtgp_inff(), new_tprev = tprev, new_tnext = tnext;
+        if (stepping) {
+          const float dt = tnext - tprev;
+          float u = 0.0f;
+          if (KIND != MTGP_EVAL_SR) {
+            float y[DR];
+            env.template f_obs<NOISE>(tprev, x, y, P.n_obs, P.obs_noise, P.partitionable,
+                                      nz_base + (size_t)steps * P.n_obs * nzs, nzs);
+            if (KIND == MTGP_EVAL_STATIC) {
 #pragma unroll
-            for (int i = 0; i < D; i++)
-              if (i < P.n_obs) lb[i * 32] = y[i];
-            u = mtgp_interpret<1>(prog_s, lb).v[0];
-          } else {
+              for (int i = 0; i < D; i++)
+                if (i < P.n_obs) lb[i * 32] = y[i];
+            } else {
 #pragma unroll
-            for (int i = 0; i < D; i++)
-              if (i < P.n_obs) lb[i * 32] = 0.0f;
-            lb[P.slot_u * 32] = 0.0f;
-            u = mtgp_interpret<1>(prog_s + (size_t)P.state_size * P.lstride, lb).v[0];  // readout (:113)
+              for (int i = 0; i < D; i++)
+                if (i < P.n_obs) lb[i * 32] = 0.0f;
+              lb[P.slot_u * 32] = 0.0f;
+            }
+            u = mtgp_interpret<1>(prog_readout, lb).v[0];  // feedforward :107 / dynamic readout :113
+            float dx[DR];
+            env.drift(x, u, dx);
+#pragma unroll
+            for (int i = 0; i < D; i++) x1[i] = x[i] + dt * dx[i];
+            if (KIND == MTGP_EVAL_DYNAMIC) {
+#pragma unroll
+              for (int i = 0; i < D; i++)
+                if (i < P.n_obs) lb[i * 32] = y[i];
+              lb[P.slot_u * 32] = u;
+            }
           }
-          float dx[DR];
-          env.drift(x, u, dx);
-#pragma unroll
-          for (int i = 0; i < D; i++) x1[i] = x[i] + dt * dx[i];
-          if (KIND == MTGP_EVAL_DYNAMIC) {
-#pragma unroll
-            for (int i = 0; i < D; i++)
-              if (i < P.n_obs) lb[i * 32] = y[i];
-            lb[P.slot_u * 32] = u;
+          for (int j = 0; j < NL; j++) {  // latent trees: state equation (:116) / SR vector field
+            const float f = mtgp_interpret<1>(prog_s + (size_t)j * P.lstride, lb).v[0];
+            lb[(P.slot_out + j) * 32] = lb[(P.slot_state + j) * 32] + dt * f;
           }
+          new_tprev = tnext < t1 ? tnext : t1;
+          new_tnext = tnext + P.dt0;
+          new_tnext = (new_tnext > t1 - 1e-6f) ? t1 : new_tnext;  // _clip_to_end
+          save_until = tnext;
         }
-        for (int j = 0; j < NL; j++) {  // latent trees: state equation (:116) / SR vector field
-          const float f = mtgp_interpret<1>(prog_s + (size_t)j * P.lstride, lb).v[0];
-          lb[(P.slot_out + j) * 32] = lb[(P.slot_state + j) * 32] + dt * f;
-        }
-        const float new_tprev = tnext < t1 ? tnext : t1;
-        float new_tnext = tnext + P.dt0;
-        new_tnext = (new_tnext > t1 - 1e-6f) ? t1 : new_tnext;  // _clip_to_end
+        const bool live_save = stepping && alive;
         // ---- SaveAt(ts): dense (linear) output for every ts[k] <= tnext ----
-        while (k < K && ts[k] <= tnext) {
+        while (k < K && ts[k] <= save_until) {
           const float tk = ts[k];
           const float coeff = (tprev == tnext) ? 0.0f : (tk - tprev) / (tnext - tprev);
           float xs[DR];
           if (KIND != MTGP_EVAL_SR) {
 #pragma unroll
-            for (int i = 0; i < D; i++) xs[i] = alive ? x[i] + coeff * (x1[i] - x[i]) : mtgp_inff();
+            for (int i = 0; i < D; i++) xs[i] = live_save ? x[i] + coeff * (x1[i] - x[i]) : mtgp_inff();
           }
           float row = 0.0f;
           for (int j = 0; j < NL; j++) {
             const float a0 = lb[(P.slot_state + j) * 32], a1 = lb[(P.slot_out + j) * 32];
-            const float lat = alive ? a0 + coeff * (a1 - a0) : mtgp_inff();
+            const float lat = live_save ? a0 + coeff * (a1 - a0) : mtgp_inff();
             if (KIND == MTGP_EVAL_SR) {
               const float e = lat - P.ys_true[((size_t)bb * K + k) * NL + j];
               row = row + e * e;
@@ -484,21 +577,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_rollout(const RolloutPara
             sr_total = sr_total + row;
           } else {
             float ys[DR];
-            env.template f_obs<NOISE>(tk, xs, ys, P.n_obs, P.obs_noise, P.partitionable);
+            env.template f_obs<NOISE>(tk, xs, ys, P.n_obs, P.obs_noise, P.partitionable,
+                                      nz_base + (size_t)(P.cap_steps + k) * P.n_obs * nzs, nzs);
 #pragma unroll
             for (int i = 0; i < D; i++)
               if (i < P.n_obs) lb[i * 32] = ys[i];
-            float uk;
-            if (KIND == MTGP_EVAL_STATIC) {
-              uk = mtgp_interpret<1>(prog_s, lb).v[0];
-            } else {
-              lb[P.slot_u * 32] = 0.0f;  // zeros(control_size) (dynamic_evaluate.py:101)
-              uk = mtgp_interpret<1>(prog_s + (size_t)P.state_size * P.lstride, lb).v[0];
-            }
+            if (KIND == MTGP_EVAL_DYNAMIC) lb[P.slot_u * 32] = 0.0f;  // zeros(control_size) (dynamic_evaluate.py:101)
+            const float uk = mtgp_interpret<1>(prog_readout, lb).v[0];
             const float qk = (ENV == MTGP_ENV_ACROBOT) ? tk / dts : 0.0f;
             if (ENV == MTGP_ENV_ACROBOT && qk > (float)(k + 1)) viol = true;
             env.cost_add(k, qk, xs, uk, fs_known);
-            if (lane_valid && pass == 0) {
+            if (lane_valid && pass == 0 && (P.xs_o || P.ys_o || P.us_o)) {
               const size_t o = ((size_t)ind * P.B + b) * K + k;
               if (P.xs_o)
 #pragma unroll
@@ -512,78 +601,32 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_rollout(const RolloutPara
           }
           k++;
         }
-        // ---- Event(cond_fn): sign change of cond_fn evaluated at (tnext, y1) ----
-        bool bad = false;
-        if (KIND != MTGP_EVAL_SR) bad = env.bad_state(x1);
-        for (int j = 0; j < NL; j++) bad |= !mtgp_isfinitef(lb[(P.slot_out + j) * 32]);
-        const bool fired = (bad != ev_old_bad);
-        // ---- commit ----
-        if (alive) {
-          ev_old_bad = bad;
-          my_steps += lane_valid ? 1ull : 0ull;
-          if (KIND != MTGP_EVAL_SR) {
+        if (stepping) {
+          // ---- Event(cond_fn): sign change of cond_fn evaluated at (tnext, y1) ----
+          bool bad = false;
+          if (KIND != MTGP_EVAL_SR) bad = env.bad_state(x1);
+          for (int j = 0; j < NL; j++) bad |= !mtgp_isfinitef(lb[(P.slot_out + j) * 32]);
+          const bool fired = (bad != ev_old_bad);
+          // ---- commit ----
+          if (alive) {
+            ev_old_bad = bad;
+            if (pass == 0 && lane_valid) my_steps++;
+            if (KIND != MTGP_EVAL_SR) {
 #pragma unroll
-            for (int i = 0; i < D; i++) x[i] = x1[i];
+              for (int i = 0; i < D; i++) x[i] = x1[i];
+            }
           }
-        }
-        for (int j = 0; j < NL; j++) {
-          const float cur = lb[(P.slot_state + j) * 32];
-          const float nv = alive ? lb[(P.slot_out + j) * 32] : cur;
-          lb[(P.slot_state + j) * 32] = nv;
-          lb[(P.slot_lat + j) * 32] = nv;
-        }
-        if (alive && fired) alive = false;
-        tprev = new_tprev;
-        tnext = new_tnext;
-        steps++;
-      }
-      // ---- save points the solve never reached stay inf (SaveAt pre-fill) ----
-      alive = false;
-      while (k < K) {
-        const float tk = ts[k];
-        if (KIND == MTGP_EVAL_SR) {
-          float row = 0.0f;
           for (int j = 0; j < NL; j++) {
-            const float e = mtgp_inff() - P.ys_true[((size_t)bb * K + k) * NL + j];
-            row = row + e * e;
-            if (P.xs_o && lane_valid && pass == 0) P.xs_o[(((size_t)ind * P.B + b) * K + k) * NL + j] = mtgp_inff();
+            const float cur = lb[(P.slot_state + j) * 32];
+            const float nv = alive ? lb[(P.slot_out + j) * 32] : cur;
+            lb[(P.slot_state + j) * 32] = nv;
+            lb[(P.slot_lat + j) * 32] = nv;
           }
-          sr_total = sr_total + row;
-        } else {
-          float xs[DR], ys[DR];
-#pragma unroll
-          for (int i = 0; i < D; i++) xs[i] = mtgp_inff();
-          for (int j = 0; j < NL; j++) {
-            lb[(P.slot_lat + j) * 32] = mtgp_inff();
-            if (P.act_o && lane_valid && pass == 0) P.act_o[(((size_t)ind * P.B + b) * K + k) * NL + j] = mtgp_inff();
-          }
-          env.template f_obs<NOISE>(tk, xs, ys, P.n_obs, P.obs_noise, P.partitionable);
-#pragma unroll
-          for (int i = 0; i < D; i++)
-            if (i < P.n_obs) lb[i * 32] = ys[i];
-          float uk;
-          if (KIND == MTGP_EVAL_STATIC) {
-            uk = mtgp_interpret<1>(prog_s, lb).v[0];
-          } else {
-            lb[P.slot_u * 32] = 0.0f;
-            uk = mtgp_interpret<1>(prog_s + (size_t)P.state_size * P.lstride, lb).v[0];
-          }
-          const float qk = (ENV == MTGP_ENV_ACROBOT) ? tk / dts : 0.0f;
-          if (ENV == MTGP_ENV_ACROBOT && qk > (float)(k + 1)) viol = true;
-          env.cost_add(k, qk, xs, uk, fs_known);
-          if (lane_valid && pass == 0) {
-            const size_t o = ((size_t)ind * P.B + b) * K + k;
-            if (P.xs_o)
-#pragma unroll
-              for (int i = 0; i < D; i++) P.xs_o[o * D + i] = xs[i];
-            if (P.ys_o)
-#pragma unroll
-              for (int i = 0; i < D; i++)
-                if (i < P.n_obs) P.ys_o[o * P.n_obs + i] = ys[i];
-            if (P.us_o) P.us_o[o] = uk;
-          }
+          if (alive && fired) alive = false;
+          tprev = new_tprev;
+          tnext = new_tnext;
+          steps++;
         }
-        k++;
       }
       traj_fitness = (KIND == MTGP_EVAL_SR) ? sr_total / (float)K : env.cost_finish(K, fs_known);
       // Acrobot with a ts grid for which the running-prefix cost is not exact (ts[k]/dts > k+1
@@ -613,19 +656,58 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_rollout(const RolloutPara
   }
 }
 
-template <int KIND, int ENV>
-int launch_kind_env(const RolloutParams& rp, size_t smem, cudaStream_t stream) {
-  const unsigned blocks = (unsigned)((rp.P + kWarpsPerCta - 1) / kWarpsPerCta);
-  if (rp.obs_noise != 0.0f && KIND != MTGP_EVAL_SR) {
-    auto kern = k_rollout<KIND, ENV, true>;
-    MTGP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<blocks, kWarpsPerCta * 32, smem, stream>>>(rp);
-  } else {
-    auto kern = k_rollout<KIND, ENV, false>;
-    MTGP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<blocks, kWarpsPerCta * 32, smem, stream>>>(rp);
+size_t rollout_smem(const RolloutParams& rp) {
+  return 16 * kWarpsPerCta + (size_t)kWarpsPerCta * rp.prog_words_per_warp * sizeof(uint2) +
+         (size_t)kWarpsPerCta * rp.slots_per_warp * 32 * sizeof(float);
+}
+
+template <int KIND, int ENV, int NOISE>
+int launch_one(RolloutParams rp, int tmp_base, int n_tmp, int min_need, int max_need, cudaStream_t stream) {
+  rp.slots_per_warp = tmp_base + n_tmp;
+  rp.min_need = min_need;
+  rp.max_need = max_need;
+  const size_t smem = rollout_smem(rp);
+  if (smem > 227 * 1024) {
+    mtgp_set_error("rollout needs %zu bytes of shared memory per CTA: over the 227 KB limit", smem);
+    return MTGP_ERR_UNSUPPORTED;
   }
+  auto kern = k_rollout<KIND, ENV, NOISE>;
+  MTGP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned blocks = (unsigned)((rp.P + kWarpsPerCta - 1) / kWarpsPerCta);
+  kern<<<blocks, kWarpsPerCta * 32, smem, stream>>>(rp);
   return mtgp_check_launch("k_rollout");
+}
+
+// Individuals whose programs need at most kFastTmp temporaries (every tree of ordinary depth) run
+// with a small value file and high occupancy; the rest (long combs grown by mutation) run in a
+// second launch provisioned with the worst-case bound.  Each launch skips the other's individuals.
+constexpr int kFastTmp = 8;
+
+template <int KIND, int ENV>
+int launch_kind_env(RolloutParams rp, int tmp_base, int bound, void* noise_ws, cudaStream_t stream) {
+  int noise = 0;
+  if (rp.obs_noise != 0.0f && KIND != MTGP_EVAL_SR) {
+    noise = noise_ws ? 1 : 2;
+    if (noise == 1) {
+      float* tprev = static_cast<float*>(noise_ws);
+      int* n_steps = reinterpret_cast<int*>(tprev + rp.cap_steps);
+      float* table = tprev + rp.cap_steps + 64;
+      k_schedule<<<1, 32, 0, stream>>>(rp.ts, rp.K, rp.dt0, rp.max_steps, rp.cap_steps, tprev, n_steps);
+      const long long n = (long long)(rp.cap_steps + rp.K) * rp.B;
+      k_noise_table<ENV><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(rp, tprev, n_steps, table);
+      int rc = mtgp_check_launch("k_noise_table");
+      if (rc) return rc;
+      rp.noise = table;
+    }
+  }
+  const int fast = bound < kFastTmp ? bound : kFastTmp;
+  int rc;
+#define LAUNCH2(NZ)                                                                         \
+  rc = launch_one<KIND, ENV, NZ>(rp, tmp_base, fast, 0, fast, stream);                      \
+  if (rc == MTGP_OK && bound > fast) rc = launch_one<KIND, ENV, NZ>(rp, tmp_base, bound, fast + 1, bound, stream);
+  if (noise == 0) { LAUNCH2(0) } else if (noise == 1) { LAUNCH2(1) } else { LAUNCH2(2) }
+#undef LAUNCH2
+  return rc;
 }
 
 }  // namespace
@@ -649,11 +731,22 @@ int mtgp_rollout_slot_map(const mtgp_rollout_desc& d, int T, int* n_data, int* n
   return *n_data + 2 * (*n_latent);
 }
 
+// Rows of the step part of the noise table, and its size in bytes (0 = generate the noise inline).
+static const size_t kNoiseTableMaxBytes = (size_t)512 << 20;
+int mtgp_noise_cap_steps(const mtgp_rollout_desc& d) { return d.max_steps < (1 << 22) ? d.max_steps : (1 << 22); }
+size_t mtgp_noise_workspace_bytes(const mtgp_rollout_desc& d) {
+  if (d.kind == MTGP_EVAL_SR || d.obs_noise == 0.0f) return 0;
+  const char* force_inline = getenv("MTGP_NOISE_INLINE");  // test hook: exercise the in-kernel generator
+  if (force_inline && force_inline[0] == '1') return 0;
+  const size_t cap = (size_t)mtgp_noise_cap_steps(d);
+  const size_t bytes = (cap + 64) * sizeof(float) + (cap + d.K) * (size_t)d.n_obs * d.B * sizeof(float);
+  return bytes <= kNoiseTableMaxBytes ? bytes : 0;
+}
+
 int mtgp_launch_rollout(const mtgp_programs& progs, const int32_t* live, int P, int T, int N,
                         const mtgp_rollout_desc& d, float size_parsimony, float* fitness,
-                        const mtgp_trajectory_out* traj, unsigned long long* steps_done,
+                        const mtgp_trajectory_out* traj, unsigned long long* steps_done, void* noise_ws,
                         cudaStream_t stream) {
-  (void)N;
   if (P == 0) return MTGP_OK;
   RolloutParams rp{};
   rp.prog = progs.prog; rp.meta = progs.meta; rp.live = live; rp.lstride = progs.lstride;
@@ -670,6 +763,8 @@ int mtgp_launch_rollout(const mtgp_programs& progs, const int32_t* live, int P, 
     rp.tf_o = traj->traj_fitness;
   }
   rp.steps_done = steps_done;
+  rp.cap_steps = mtgp_noise_cap_steps(d);
+  if (mtgp_noise_workspace_bytes(d) == 0) noise_ws = nullptr;
   int n_data, n_latent;
   const int reserved = mtgp_rollout_slot_map(d, T, &n_data, &n_latent);
   rp.n_latent = n_latent;
@@ -688,15 +783,9 @@ int mtgp_launch_rollout(const mtgp_programs& progs, const int32_t* live, int P, 
     mtgp_set_error("internal: slot map mismatch (%d vs %d)", reserved, progs.tmp_base);
     return MTGP_ERR_INVALID_ARGUMENT;
   }
-  rp.slots_per_warp = progs.tmp_base + progs.n_tmp;
   rp.prog_words_per_warp = T * progs.lstride;
-  const size_t smem = 16 * kWarpsPerCta + (size_t)kWarpsPerCta * rp.prog_words_per_warp * sizeof(uint2) +
-                      (size_t)kWarpsPerCta * rp.slots_per_warp * 32 * sizeof(float);
-  if (smem > 227 * 1024) {
-    mtgp_set_error("rollout needs %zu bytes of shared memory per CTA (T=%d, N=%d): over the 227 KB limit", smem, T, N);
-    return MTGP_ERR_UNSUPPORTED;
-  }
-#define DISPATCH(KIND, ENV) return launch_kind_env<KIND, ENV>(rp, smem, stream)
+  const int bound = progs.n_tmp;
+#define DISPATCH(KIND, ENV) return launch_kind_env<KIND, ENV>(rp, progs.tmp_base, bound, noise_ws, stream)
   if (d.kind == MTGP_EVAL_SR) DISPATCH(MTGP_EVAL_SR, MTGP_ENV_NONE);
   if (d.kind == MTGP_EVAL_STATIC) {
     if (d.env_id == MTGP_ENV_ACROBOT) DISPATCH(MTGP_EVAL_STATIC, MTGP_ENV_ACROBOT);

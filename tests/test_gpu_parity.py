@@ -111,6 +111,20 @@ def test_control_rollout_parity(engine, oracle, env_name, kind, obs_noise):
     assert int(gpu["steps"][0]) == ref["steps"]
 
 
+def test_inline_noise_generator_matches_the_table(engine, oracle, monkeypatch):
+    """The rollout kernel normally reads the observation noise from a table computed once per
+    evaluation; when the table would be too large it generates the noise in-kernel.  Same bits."""
+    rng = np.random.default_rng(4)
+    lib, pop, data = util.control_case("acrobot", abi.EVAL_DYNAMIC, rng, P=64, B=16, T_end=6.0, obs_noise=0.1)
+    ref = oracle.rollout_population(pop, lib.table(), data)
+    a = _gpu_rollout(engine, lib, pop, data, trajectories=True)
+    monkeypatch.setenv("MTGP_NOISE_INLINE", "1")
+    b = _gpu_rollout(engine, lib, pop, data, trajectories=True)
+    for g in (a, b):
+        assert util.same_or_both_nan(g["traj_fitness"], ref["traj_fitness"]).all()
+        assert util.same_or_both_nan(g["ys"], a["ys"]).all()
+
+
 def test_threefry_original_mode(engine, oracle):
     rng = np.random.default_rng(5)
     for env_name in ("acrobot", "reactor", "harmonic"):  # n_obs = 4, 3 (odd: zero pad), 2
@@ -194,8 +208,8 @@ def test_deep_comb_trees_take_the_slow_pointwise_path(engine, oracle):
     N = 63
     tree = np.zeros((N, 4), dtype=np.float32)
     tree[:, 1:3] = -1
-    # right-nested chain: every operator's left child is an operator applied to two leaves
-    # rows (ascending): build  f_k = (x0 * x1) + f_{k-1}  so that many right operands stay live
+    # f_k = f_{k-1} + (c_k * x1): in postfix order the right operand is computed first and stays live
+    # while the left sub-tree is evaluated, so depth 12 needs 12 temporaries (> the fast kernel's 8)
     rows = []
 
     def emit(idv, a=-1, b=-1, c=0.0):
@@ -206,10 +220,10 @@ def test_deep_comb_trees_take_the_slow_pointwise_path(engine, oracle):
     def build(depth):
         if depth == 0:
             return emit(ids["x0"])
-        r = build(depth - 1)                      # right subtree first (postfix order)
         l1 = emit(ids["x1"]); l0 = emit(1, c=0.5 + depth)
-        left = emit(ids["*"], l0, l1)             # a = i-1, b = i-2
-        return emit(ids["+"], left, r)
+        right = emit(ids["*"], l0, l1)            # right operand first (postfix), stays live ...
+        left = build(depth - 1)                   # ... while the whole left sub-tree is evaluated
+        return emit(ids["+"], left, right)
     build(12)
     tree[N - len(rows):] = np.array(rows, dtype=np.float32)
     off = N - len(rows)
