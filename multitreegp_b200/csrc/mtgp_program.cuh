@@ -127,12 +127,12 @@ __host__ __device__ __forceinline__ void vf_store(float* lane_base, uint32_t slo
 
 #define MTGP_FOR_R _Pragma("unroll") for (int r = 0; r < R; r++)
 
-// ---- the interpreter ------------------------------------------------------------------------
+// ---- compact-format interpreter (R values per lane; used by the pointwise kernel) ---------------
 // prog: shared-memory program (terminated by X_END), identical for all lanes of the warp, so every
-// branch below is warp-uniform.  lane_base = value file + lane*R.
-// Returns the value of the tree's root for the R points / trajectories this lane owns.
+// branch below is warp-uniform and its cost is amortised over the 32*R values a warp evaluates per
+// dispatched instruction.  lane_base = value file + lane*R.
 template <int R>
-__host__ __device__ __forceinline__ Vec<R> mtgp_interpret_inline(const uint2* __restrict__ prog, float* lane_base) {
+__host__ __device__ __noinline__ Vec<R> mtgp_interpret(const uint2* __restrict__ prog, float* lane_base) {
   Vec<R> acc;
   MTGP_FOR_R acc.v[r] = 0.0f;
   uint2 w = prog[0];
@@ -147,35 +147,146 @@ __host__ __device__ __forceinline__ Vec<R> mtgp_interpret_inline(const uint2* __
     if (yk == OK_MEM) y = vf_load<R>(lane_base, c >> 24);
     if (xk == OK_IMM) { MTGP_FOR_R x.v[r] = imm; }
     if (yk == OK_IMM) { MTGP_FOR_R y.v[r] = imm; }
-    if (op <= X_MUL) {
-      // LOAD / ADD / SUB / MUL: one straight-line path (x - y == x + (-y) exactly)
-      const uint32_t flip = (op == X_SUB) ? 0x80000000u : 0u;
-      MTGP_FOR_R {
-        const float s = x.v[r] + mtgp_u2f(mtgp_f2u(y.v[r]) ^ flip);
-        const float m = x.v[r] * y.v[r];
-        acc.v[r] = (op == X_MUL) ? m : ((op == X_LOAD) ? x.v[r] : s);
-      }
-    } else {
-      switch (op) {
-        case X_DIV: MTGP_FOR_R acc.v[r] = x.v[r] / y.v[r]; break;
-        case X_MAX: MTGP_FOR_R acc.v[r] = mtgp_maximumf(x.v[r], y.v[r]); break;
-        case X_MIN: MTGP_FOR_R acc.v[r] = mtgp_minimumf(x.v[r], y.v[r]); break;
-        case X_SIN: MTGP_FOR_R acc.v[r] = mtgp_sinf(x.v[r]); break;
-        case X_COS: MTGP_FOR_R acc.v[r] = mtgp_cosf(x.v[r]); break;
-        case X_EXP: MTGP_FOR_R acc.v[r] = mtgp_expf(x.v[r]); break;
-        case X_LOG: MTGP_FOR_R acc.v[r] = mtgp_logf(x.v[r]); break;
-        case X_SQRT: MTGP_FOR_R acc.v[r] = mtgp_sqrtf(x.v[r]); break;
-        case X_TANH: MTGP_FOR_R acc.v[r] = mtgp_tanhf(x.v[r]); break;
-        case X_NEG: MTGP_FOR_R acc.v[r] = -x.v[r]; break;
-        default: MTGP_FOR_R acc.v[r] = mtgp_absf(x.v[r]); break;  // X_ABS
-      }
+    switch (op) {
+      case X_LOAD: acc = x; break;
+      case X_ADD: MTGP_FOR_R acc.v[r] = x.v[r] + y.v[r]; break;
+      case X_SUB: MTGP_FOR_R acc.v[r] = x.v[r] - y.v[r]; break;
+      case X_MUL: MTGP_FOR_R acc.v[r] = x.v[r] * y.v[r]; break;
+      case X_DIV: MTGP_FOR_R acc.v[r] = x.v[r] / y.v[r]; break;
+      case X_MAX: MTGP_FOR_R acc.v[r] = mtgp_maximumf(x.v[r], y.v[r]); break;
+      case X_MIN: MTGP_FOR_R acc.v[r] = mtgp_minimumf(x.v[r], y.v[r]); break;
+      case X_SIN: MTGP_FOR_R acc.v[r] = mtgp_sinf(x.v[r]); break;
+      case X_COS: MTGP_FOR_R acc.v[r] = mtgp_cosf(x.v[r]); break;
+      case X_EXP: MTGP_FOR_R acc.v[r] = mtgp_expf(x.v[r]); break;
+      case X_LOG: MTGP_FOR_R acc.v[r] = mtgp_logf(x.v[r]); break;
+      case X_SQRT: MTGP_FOR_R acc.v[r] = mtgp_sqrtf(x.v[r]); break;
+      case X_TANH: MTGP_FOR_R acc.v[r] = mtgp_tanhf(x.v[r]); break;
+      case X_NEG: MTGP_FOR_R acc.v[r] = -x.v[r]; break;
+      default: MTGP_FOR_R acc.v[r] = mtgp_absf(x.v[r]); break;  // X_ABS
     }
     if (st != MTGP_NO_SLOT) vf_store<R>(lane_base, st, acc);
   }
   return acc;
 }
 
-template <int R>
-__host__ __device__ __noinline__ Vec<R> mtgp_interpret(const uint2* __restrict__ prog, float* lane_base) {
-  return mtgp_interpret_inline<R>(prog, lane_base);
+// ---- pre-decoded ("wide") format for the rollout kernel (R = 1) --------------------------------
+// In the rollout the same program runs thousands of times per trajectory with ONE value per lane,
+// so per-dispatch decode (field extraction, kind tests, compare chains) is the dominant cost.  Each
+// warp therefore expands its compact programs once into 32-byte instructions whose fields are ready
+// to use: byte offsets into the value file and full-width select masks.  The common operators run
+// through ONE branch-free data path:
+//     x = MX ? M[xoff] : acc              y = MY ? M[yoff] : imm
+//     r = fma(x, P, Q)   with  P = MP ? y : c1,   Q = MP ? -0.0 : (y ^ fy)
+//   ADD: c1 = 1, fy = 0         x*1 + y          SUB : c1 = 1, fy = sign   x*1 + (-y)
+//   RSUB: c1 = -1, fy = 0       x*(-1) + y       MUL : MP = ~0             x*y + (-0.0)
+//   LOAD: ADD with y = imm = -0.0                (all exact: one rounding, same bits as the plain op)
+// and the result is ALWAYS stored (to a scratch slot when nobody needs it), so there is no
+// predicate for it.  Everything else (div, max, min, transcendental, ...) takes a switch.
+struct __align__(16) mtgp_wide_instr {
+  uint4 a;  // .x = x byte offset | y byte offset << 16 (slot * 128)
+            // .y = store byte offset | op << 16  (op: W_END, W_FAST, or a slow opcode)
+            // .z = immediate (float bits)      .w = MX: ~0 -> x from memory, 0 -> x = accumulator
+  uint4 b;  // .x = MY: ~0 -> y from memory, 0 -> y = immediate      .y = c1: float bits of +1 / -1
+            // .z = MP: ~0 -> multiply          .w = fy: 0 or 0x80000000
+};
+enum mtgp_wop : uint32_t {
+  W_END = 0, W_FAST = 1, W_DIV = 2, W_RDIV = 3, W_MAX = 4, W_MIN = 5, W_SIN = 6, W_COS = 7, W_EXP = 8, W_LOG = 9,
+  W_SQRT = 10, W_TANH = 11, W_NEG = 12, W_ABS = 13, W_SQUARE = 14, W_LOADI = 15
+};
+
+// compact -> wide.  `scratch_slot` receives the results nobody reads.
+__host__ __device__ __forceinline__ mtgp_wide_instr mtgp_expand_instr(uint2 c, uint32_t scratch_slot) {
+  const uint32_t op = c.x & 15u, st = (c.x >> 8) & 0xFFu;
+  uint32_t xk = (c.x >> 4) & 3u, yk = (c.x >> 6) & 3u, xs = (c.x >> 16) & 0xFFu, ys = c.x >> 24;
+  mtgp_wide_instr w;
+  uint32_t wop = W_FAST, imm = c.y, c1 = 0x3F800000u, mp = 0u, fy = 0u;
+  bool swap = false;
+  switch (op) {
+    case X_END: wop = W_END; break;
+    case X_LOAD:
+      if (xk == OK_IMM) wop = W_LOADI;
+      else { yk = OK_IMM; imm = 0x80000000u; }  // x + (-0.0) == x
+      break;
+    case X_ADD: swap = (xk == OK_IMM) || (yk == OK_ACC); break;
+    case X_MUL:
+      swap = (xk == OK_IMM) || (yk == OK_ACC && xk != OK_ACC);
+      mp = 0xFFFFFFFFu;
+      if (xk == OK_ACC && yk == OK_ACC) wop = W_SQUARE;
+      break;
+    case X_SUB:
+      if (xk == OK_IMM || yk == OK_ACC) { swap = true; c1 = 0xBF800000u; }  // y - x
+      else fy = 0x80000000u;
+      break;
+    case X_DIV:
+      wop = W_DIV;
+      if (xk == OK_IMM || yk == OK_ACC) { swap = true; wop = W_RDIV; }
+      break;
+    case X_MAX: wop = W_MAX; swap = (xk == OK_IMM) || (yk == OK_ACC); break;
+    case X_MIN: wop = W_MIN; swap = (xk == OK_IMM) || (yk == OK_ACC); break;
+    default: wop = W_SIN + (op - X_SIN); break;  // unary: SIN COS EXP LOG SQRT TANH NEG ABS
+  }
+  if (swap) {
+    uint32_t t = xk; xk = yk; yk = t;
+    t = xs; xs = ys; ys = t;
+  }
+  // after canonicalisation x is the accumulator or memory, y is memory or the immediate
+  w.a.x = ((xk == OK_MEM ? xs : 0u) * 128u) | (((yk == OK_MEM ? ys : 0u) * 128u) << 16);
+  w.a.y = ((st != MTGP_NO_SLOT ? st : scratch_slot) * 128u) | (wop << 16);
+  w.a.z = imm;
+  w.a.w = (xk == OK_MEM) ? 0xFFFFFFFFu : 0u;
+  w.b.x = (yk == OK_MEM) ? 0xFFFFFFFFu : 0u;
+  w.b.y = c1;
+  w.b.z = mp;
+  w.b.w = fy;
+  return w;
+}
+
+__host__ __device__ __forceinline__ uint32_t mtgp_bitsel(uint32_t mask, uint32_t a, uint32_t b) {
+  return (a & mask) | (b & ~mask);  // one LOP3
+}
+
+// prog: wide program in shared memory; lane_bytes: the lane's base of the value file as a byte
+// pointer (value file + lane*4).  Warp-uniform control flow throughout.
+__host__ __device__ __forceinline__ float mtgp_interpret_wide(const mtgp_wide_instr* __restrict__ prog,
+                                                              unsigned char* lane_bytes) {
+  float acc = 0.0f;
+  uint4 a = prog->a, b = prog->b;
+  while (true) {
+    const uint32_t wop = a.y >> 16;
+    if (wop == W_END) break;
+    float* lane_f = reinterpret_cast<float*>(lane_bytes);  // offsets are multiples of 128 bytes
+    const float xm = lane_f[(a.x & 0xFFFFu) >> 2];
+    const float ym = lane_f[a.x >> 18];
+    float* st = lane_f + ((a.y & 0xFFFFu) >> 2);
+    const uint32_t xb = mtgp_bitsel(a.w, mtgp_f2u(xm), mtgp_f2u(acc));
+    const uint32_t yb = mtgp_bitsel(b.x, mtgp_f2u(ym), a.z);
+    const float x = mtgp_u2f(xb), y = mtgp_u2f(yb);
+    const uint32_t pb = mtgp_bitsel(b.z, yb, b.y);
+    const uint32_t qb = mtgp_bitsel(b.z, 0x80000000u, yb ^ b.w);
+    ++prog;
+    a = prog->a;
+    b = prog->b;
+    if (wop == W_FAST) {
+      acc = fmaf(x, mtgp_u2f(pb), mtgp_u2f(qb));
+    } else {
+      switch (wop) {
+        case W_DIV: acc = x / y; break;
+        case W_RDIV: acc = y / x; break;
+        case W_MAX: acc = mtgp_maximumf(x, y); break;
+        case W_MIN: acc = mtgp_minimumf(x, y); break;
+        case W_SIN: acc = mtgp_sinf(x); break;
+        case W_COS: acc = mtgp_cosf(x); break;
+        case W_EXP: acc = mtgp_expf(x); break;
+        case W_LOG: acc = mtgp_logf(x); break;
+        case W_SQRT: acc = mtgp_sqrtf(x); break;
+        case W_TANH: acc = mtgp_tanhf(x); break;
+        case W_NEG: acc = -x; break;
+        case W_ABS: acc = mtgp_absf(x); break;
+        case W_SQUARE: acc = x * x; break;
+        default: acc = y; break;  // W_LOADI
+      }
+    }
+    *st = acc;
+  }
+  return acc;
 }

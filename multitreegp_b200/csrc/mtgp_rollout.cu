@@ -41,16 +41,18 @@ struct RolloutParams {
   unsigned long long* steps_done;
   const float* noise;  // [cap_steps + K, n_obs, B] precomputed observation noise (NOISE == 1), see k_noise_table
   int cap_steps;       // rows of the step part of the noise table
-  int min_need, max_need;  // this launch handles individuals whose temporaries are in [min_need, max_need]
+  int fast_tmp, fast_instr, want_fast;  // launch class: programs within / beyond the fast provisioning
   int n_latent;        // state kept in the value file: SR -> T, DYNAMIC -> state_size, STATIC -> 0
   int slot_lat;        // data-vector slot of latent component 0
   int slot_u;          // data-vector slot of the control (control evaluators)
   int slot_target;     // data-vector slot of target 0
   int slot_out;        // n_latent slots: y1 of the latent state
   int slot_state;      // n_latent slots: master copy of the latent state
-  int slots_per_warp;
-  int prog_words_per_warp;
+  int slots_per_warp;      // data + latent copies + temporaries + 1 scratch slot
+  int prog_words_per_warp; // compact staging area (uint2)
+  int wide_cap;            // pre-decoded instructions provisioned per warp
 };
+constexpr int kMaxTrees = 32;
 
 // ---- PTX helpers: mbarrier + 1-D bulk async copy (TMA) ------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -422,18 +424,29 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_rollout(const RolloutP
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const int ind = blockIdx.x * kWarpsPerCta + wic;
 
+  // shared memory: [mbarriers][per warp: compact programs | tree offsets | wide programs | value file]
+  const size_t per_warp = (size_t)P.prog_words_per_warp * sizeof(uint2) + kMaxTrees * sizeof(int) +
+                          (size_t)P.wide_cap * sizeof(mtgp_wide_instr) + (size_t)P.slots_per_warp * 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  uint2* prog_s = reinterpret_cast<uint2*>(smem_raw + 16 * kWarpsPerCta) + (size_t)wic * P.prog_words_per_warp;
-  float* vf = reinterpret_cast<float*>(smem_raw + 16 * kWarpsPerCta +
-                                       (size_t)kWarpsPerCta * P.prog_words_per_warp * sizeof(uint2)) +
-              (size_t)wic * P.slots_per_warp * 32;
+  unsigned char* wbase = smem_raw + 16 * kWarpsPerCta + (size_t)wic * per_warp;
+  uint2* prog_s = reinterpret_cast<uint2*>(wbase);
+  int* woff = reinterpret_cast<int*>(wbase + (size_t)P.prog_words_per_warp * sizeof(uint2));
+  mtgp_wide_instr* wide = reinterpret_cast<mtgp_wide_instr*>(woff + kMaxTrees);
+  float* vf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(wide) +
+                                       (size_t)P.wide_cap * sizeof(mtgp_wide_instr));
   if (ind >= P.P) return;  // whole warp leaves together (no block-wide barrier below)
 
-  // which launch owns this individual: by the temporaries its programs need (warp-uniform)
+  // which launch owns this individual: by the temporaries and instructions its programs need
+  int total_instr = 0;
   {
     int need = 0;
-    for (int t = 0; t < P.T; t++) need = max(need, (int)(P.meta[(size_t)ind * P.T + t] >> 16));
-    if (need < P.min_need || need > P.max_need) return;
+    for (int t = 0; t < P.T; t++) {
+      const uint32_t m = P.meta[(size_t)ind * P.T + t];
+      need = max(need, (int)(m >> 16));
+      total_instr += (int)(m & 0xFFFFu) + 1;
+    }
+    const bool fast = (need <= P.fast_tmp) && (total_instr <= P.fast_instr);
+    if (fast != (P.want_fast != 0)) return;
   }
 
   // ---- stage this individual's programs: cp.async.bulk -> shared, completion on an mbarrier ----
@@ -446,22 +459,36 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_rollout(const RolloutP
       total += ((n + 2u) & ~1u) * 8u;
     }
     mbar_expect_tx(bar, total);
+    int off = 0;
     for (int t = 0; t < P.T; t++) {
       const uint32_t n = P.meta[(size_t)ind * P.T + t] & 0xFFFFu;
       bulk_g2s(prog_s + (size_t)t * P.lstride, P.prog + ((size_t)ind * P.T + t) * P.lstride,
                ((n + 2u) & ~1u) * 8u, bar);
+      woff[t] = off;
+      off += (int)n + 1;
     }
   }
   __syncwarp();
   float* lb = vf + lane;  // lane base of the value file (R = 1)
+  unsigned char* lbytes = reinterpret_cast<unsigned char*>(lb);
   for (int s = 0; s < P.slots_per_warp; s++) lb[s * 32] = 0.0f;
   mbar_wait(bar, 0);
+  // ---- pre-decode: compact (8 B) -> wide (32 B) instructions, once per individual -------------
+  {
+    const uint32_t scratch = (uint32_t)P.slots_per_warp - 1u;
+    for (int t = 0; t < P.T; t++) {
+      const int n = (int)(P.meta[(size_t)ind * P.T + t] & 0xFFFFu) + 1;  // including X_END
+      mtgp_wide_instr* dst = wide + woff[t];
+      for (int i = lane; i < n; i += 32) dst[i] = mtgp_expand_instr(prog_s[(size_t)t * P.lstride + i], scratch);
+    }
+  }
+  __syncwarp();
 
   const float* ts = P.ts;
   const int K = P.K, NL = P.n_latent;
   const float t0 = ts[0], t1 = ts[K - 1];
   const float dts = (K > 1) ? ts[1] - ts[0] : 0.0f;  // ts[1]-ts[0], acrobot.py:82
-  const uint2* prog_readout = prog_s + (size_t)((KIND == MTGP_EVAL_DYNAMIC) ? P.state_size : 0) * P.lstride;
+  const mtgp_wide_instr* prog_readout = wide + woff[(KIND == MTGP_EVAL_DYNAMIC) ? P.state_size : 0];
   float fit_sum = 0.0f;
   unsigned long long my_steps = 0;
 
@@ -529,7 +556,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_rollout(const RolloutP
                 if (i < P.n_obs) lb[i * 32] = 0.0f;
               lb[P.slot_u * 32] = 0.0f;
             }
-            u = mtgp_interpret<1>(prog_readout, lb).v[0];  // feedforward :107 / dynamic readout :113
+            u = mtgp_interpret_wide(prog_readout, lbytes);  // feedforward :107 / dynamic readout :113
             float dx[DR];
             env.drift(x, u, dx);
 #pragma unroll
@@ -542,7 +569,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_rollout(const RolloutP
             }
           }
           for (int j = 0; j < NL; j++) {  // latent trees: state equation (:116) / SR vector field
-            const float f = mtgp_interpret<1>(prog_s + (size_t)j * P.lstride, lb).v[0];
+            const float f = mtgp_interpret_wide(wide + woff[j], lbytes);
             lb[(P.slot_out + j) * 32] = lb[(P.slot_state + j) * 32] + dt * f;
           }
           new_tprev = tnext < t1 ? tnext : t1;
@@ -583,7 +610,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_rollout(const RolloutP
             for (int i = 0; i < D; i++)
               if (i < P.n_obs) lb[i * 32] = ys[i];
             if (KIND == MTGP_EVAL_DYNAMIC) lb[P.slot_u * 32] = 0.0f;  // zeros(control_size) (dynamic_evaluate.py:101)
-            const float uk = mtgp_interpret<1>(prog_readout, lb).v[0];
+            const float uk = mtgp_interpret_wide(prog_readout, lbytes);
             const float qk = (ENV == MTGP_ENV_ACROBOT) ? tk / dts : 0.0f;
             if (ENV == MTGP_ENV_ACROBOT && qk > (float)(k + 1)) viol = true;
             env.cost_add(k, qk, xs, uk, fs_known);
@@ -657,15 +684,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_rollout(const RolloutP
 }
 
 size_t rollout_smem(const RolloutParams& rp) {
-  return 16 * kWarpsPerCta + (size_t)kWarpsPerCta * rp.prog_words_per_warp * sizeof(uint2) +
-         (size_t)kWarpsPerCta * rp.slots_per_warp * 32 * sizeof(float);
+  const size_t per_warp = (size_t)rp.prog_words_per_warp * sizeof(uint2) + kMaxTrees * sizeof(int) +
+                          (size_t)rp.wide_cap * sizeof(mtgp_wide_instr) + (size_t)rp.slots_per_warp * 128;
+  return 16 * kWarpsPerCta + (size_t)kWarpsPerCta * per_warp;
 }
 
 template <int KIND, int ENV, int NOISE>
-int launch_one(RolloutParams rp, int tmp_base, int n_tmp, int min_need, int max_need, cudaStream_t stream) {
-  rp.slots_per_warp = tmp_base + n_tmp;
-  rp.min_need = min_need;
-  rp.max_need = max_need;
+int launch_one(RolloutParams rp, int tmp_base, int n_tmp, int wide_cap, int want_fast, cudaStream_t stream) {
+  rp.slots_per_warp = tmp_base + n_tmp + 1;
+  rp.wide_cap = wide_cap;
+  rp.want_fast = want_fast;
   const size_t smem = rollout_smem(rp);
   if (smem > 227 * 1024) {
     mtgp_set_error("rollout needs %zu bytes of shared memory per CTA: over the 227 KB limit", smem);
@@ -678,10 +706,12 @@ int launch_one(RolloutParams rp, int tmp_base, int n_tmp, int min_need, int max_
   return mtgp_check_launch("k_rollout");
 }
 
-// Individuals whose programs need at most kFastTmp temporaries (every tree of ordinary depth) run
-// with a small value file and high occupancy; the rest (long combs grown by mutation) run in a
-// second launch provisioned with the worst-case bound.  Each launch skips the other's individuals.
+// Individuals whose programs need at most kFastTmp temporaries and kFastInstr instructions (every
+// tree of ordinary depth) run with a small shared-memory footprint and high occupancy; the rest
+// (long combs grown by mutation, very large trees) run in a second launch provisioned with the
+// worst-case bounds.  Each launch skips the other's individuals.
 constexpr int kFastTmp = 8;
+constexpr int kFastInstr = 64;
 
 template <int KIND, int ENV>
 int launch_kind_env(RolloutParams rp, int tmp_base, int bound, void* noise_ws, cudaStream_t stream) {
@@ -700,11 +730,14 @@ int launch_kind_env(RolloutParams rp, int tmp_base, int bound, void* noise_ws, c
       rp.noise = table;
     }
   }
-  const int fast = bound < kFastTmp ? bound : kFastTmp;
+  const int worst_instr = rp.T * rp.lstride;
+  const bool all_fast = (bound <= kFastTmp) && (worst_instr <= kFastInstr);
+  rp.fast_tmp = all_fast ? bound : kFastTmp;
+  rp.fast_instr = all_fast ? worst_instr : kFastInstr;
   int rc;
-#define LAUNCH2(NZ)                                                                         \
-  rc = launch_one<KIND, ENV, NZ>(rp, tmp_base, fast, 0, fast, stream);                      \
-  if (rc == MTGP_OK && bound > fast) rc = launch_one<KIND, ENV, NZ>(rp, tmp_base, bound, fast + 1, bound, stream);
+#define LAUNCH2(NZ)                                                                                  \
+  rc = launch_one<KIND, ENV, NZ>(rp, tmp_base, rp.fast_tmp, rp.fast_instr, 1, stream);                \
+  if (rc == MTGP_OK && !all_fast) rc = launch_one<KIND, ENV, NZ>(rp, tmp_base, bound, worst_instr, 0, stream);
   if (noise == 0) { LAUNCH2(0) } else if (noise == 1) { LAUNCH2(1) } else { LAUNCH2(2) }
 #undef LAUNCH2
   return rc;

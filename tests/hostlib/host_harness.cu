@@ -19,7 +19,8 @@ extern "C" __attribute__((visibility("default")))
 // Encodes (same rules as k_encode), lowers and interprets ONE tree on n_pts data vectors.
 // tree [N,4]; data [n_pts, n_data]; out [n_pts]; returns meta (n_instr | n_tmp << 16), flags in *flags_out.
 int hostlib_eval_tree(const float* tree, int N, const mtgp_node_table* tab, const float* data, int n_pts,
-                      int n_data, float* out, int* flags_out, unsigned long long* prog_out, int prog_cap) {
+                      int n_data, float* out, int* flags_out, unsigned long long* prog_out, int prog_cap,
+                      float* out_wide) {
   std::vector<uint8_t> op(N);
   std::vector<int16_t> a(N), b(N);
   std::vector<float> c(N);
@@ -44,10 +45,16 @@ int hostlib_eval_tree(const float* tree, int N, const mtgp_node_table* tab, cons
                                                   prog.data(), &canonical);
   *flags_out = (canonical ? 1 : 0) | (lossy ? 2 : 0);
   const int n_tmp = (int)(meta >> 16);
-  std::vector<float> vf((size_t)(tmp_base + n_tmp + 1) * 32, 0.0f);
+  std::vector<float> vf((size_t)(tmp_base + n_tmp + 2) * 32, 0.0f);
+  // the rollout kernel's pre-decoded form of the same program
+  const int n_instr = (int)(meta & 0xFFFFu) + 1;
+  std::vector<mtgp_wide_instr> wide(n_instr + 1);
+  for (int i = 0; i < n_instr; i++) wide[i] = mtgp_expand_instr(prog[i], (uint32_t)(tmp_base + n_tmp));
   for (int p = 0; p < n_pts; p++) {
     for (int j = 0; j < n_data; j++) vf[j * 32] = data[(size_t)p * n_data + j];
     out[p] = mtgp_interpret<1>(prog.data(), vf.data()).v[0];
+    if (out_wide)
+      out_wide[p] = mtgp_interpret_wide(wide.data(), reinterpret_cast<unsigned char*>(vf.data()));
   }
   if (prog_out)
     for (int i = 0; i < lstride && i < prog_cap; i++) memcpy(&prog_out[i], &prog[i], 8);

@@ -33,11 +33,15 @@ def host_eval(L, tree, tab, data):
     data = np.ascontiguousarray(data, np.float32)
     n_pts, n_data = data.shape
     out = np.empty(n_pts, np.float32)
+    out_wide = np.empty(n_pts, np.float32)
     fl = C.c_int(0)
     prog = np.zeros(tree.shape[0] + 4, np.uint64)
     meta = L.hostlib_eval_tree(C.c_void_p(tree.ctypes.data), C.c_int(tree.shape[0]), C.byref(tab),
                                C.c_void_p(data.ctypes.data), C.c_int(n_pts), C.c_int(n_data),
-                               C.c_void_p(out.ctypes.data), C.byref(fl), C.c_void_p(prog.ctypes.data), C.c_int(prog.size))
+                               C.c_void_p(out.ctypes.data), C.byref(fl), C.c_void_p(prog.ctypes.data), C.c_int(prog.size),
+                               C.c_void_p(out_wide.ctypes.data))
+    # the compact interpreter (pointwise kernel) and the pre-decoded one (rollout kernel) must agree bit for bit
+    assert util.same_or_both_nan(out, out_wide).all(), (out, out_wide)
     return out, meta & 0xFFFF, meta >> 16, fl.value, prog
 
 
