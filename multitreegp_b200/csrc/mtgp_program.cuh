@@ -245,37 +245,63 @@ __host__ __device__ __forceinline__ uint32_t mtgp_bitsel(uint32_t mask, uint32_t
   return (a & mask) | (b & ~mask);  // one LOP3
 }
 
-// prog: wide program in shared memory; lane_bytes: the lane's base of the value file as a byte
-// pointer (value file + lane*4).  Warp-uniform control flow throughout.
-__host__ __device__ __forceinline__ float mtgp_interpret_wide(const mtgp_wide_instr* __restrict__ prog,
-                                                              unsigned char* lane_bytes) {
+// Shared-memory accessors on 32-bit shared-space addresses (device) / plain pointers (host build of
+// the unit-test harness).  One IADD + LDS/STS per value-file access, one LDS.128 per half instruction.
+#if defined(__CUDA_ARCH__)
+typedef uint32_t mtgp_saddr;
+__device__ __forceinline__ mtgp_saddr mtgp_saddr_of(const void* p) { return (mtgp_saddr)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float mtgp_lds_f32(mtgp_saddr a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void mtgp_sts_f32(mtgp_saddr a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ uint4 mtgp_lds_v4(mtgp_saddr a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+#else
+typedef uintptr_t mtgp_saddr;
+static inline mtgp_saddr mtgp_saddr_of(const void* p) { return (mtgp_saddr)p; }
+static inline float mtgp_lds_f32(mtgp_saddr a) { float v; memcpy(&v, (const void*)a, 4); return v; }
+static inline void mtgp_sts_f32(mtgp_saddr a, float v) { memcpy((void*)a, &v, 4); }
+static inline uint4 mtgp_lds_v4(mtgp_saddr a) { uint4 v; memcpy(&v, (const void*)a, 16); return v; }
+#endif
+
+// prog: wide program in shared memory; lane: the lane's base of the value file (value file + lane*4).
+// Warp-uniform control flow throughout.
+__host__ __device__ __forceinline__ float mtgp_interpret_wide(mtgp_saddr prog, mtgp_saddr lane) {
   float acc = 0.0f;
-  uint4 a = prog->a, b = prog->b;
+  uint4 a = mtgp_lds_v4(prog), b = mtgp_lds_v4(prog + 16);
   while (true) {
     const uint32_t wop = a.y >> 16;
     if (wop == W_END) break;
-    float* lane_f = reinterpret_cast<float*>(lane_bytes);  // offsets are multiples of 128 bytes
-    const float xm = lane_f[(a.x & 0xFFFFu) >> 2];
-    const float ym = lane_f[a.x >> 18];
-    float* st = lane_f + ((a.y & 0xFFFFu) >> 2);
+    const float xm = mtgp_lds_f32(lane + (a.x & 0xFFFFu));
+    const float ym = mtgp_lds_f32(lane + (a.x >> 16));
+    const mtgp_saddr st = lane + (a.y & 0xFFFFu);
     const uint32_t xb = mtgp_bitsel(a.w, mtgp_f2u(xm), mtgp_f2u(acc));
     const uint32_t yb = mtgp_bitsel(b.x, mtgp_f2u(ym), a.z);
     const float x = mtgp_u2f(xb), y = mtgp_u2f(yb);
     const uint32_t pb = mtgp_bitsel(b.z, yb, b.y);
     const uint32_t qb = mtgp_bitsel(b.z, 0x80000000u, yb ^ b.w);
-    ++prog;
-    a = prog->a;
-    b = prog->b;
+    prog += 32;
+    a = mtgp_lds_v4(prog);
+    b = mtgp_lds_v4(prog + 16);
     if (wop == W_FAST) {
       acc = fmaf(x, mtgp_u2f(pb), mtgp_u2f(qb));
+    } else if (wop == W_SIN) {
+      acc = mtgp_sinf(x);
+    } else if (wop == W_COS) {
+      acc = mtgp_cosf(x);
     } else {
       switch (wop) {
         case W_DIV: acc = x / y; break;
         case W_RDIV: acc = y / x; break;
         case W_MAX: acc = mtgp_maximumf(x, y); break;
         case W_MIN: acc = mtgp_minimumf(x, y); break;
-        case W_SIN: acc = mtgp_sinf(x); break;
-        case W_COS: acc = mtgp_cosf(x); break;
         case W_EXP: acc = mtgp_expf(x); break;
         case W_LOG: acc = mtgp_logf(x); break;
         case W_SQRT: acc = mtgp_sqrtf(x); break;
@@ -286,7 +312,7 @@ __host__ __device__ __forceinline__ float mtgp_interpret_wide(const mtgp_wide_in
         default: acc = y; break;  // W_LOADI
       }
     }
-    *st = acc;
+    mtgp_sts_f32(st, acc);
   }
   return acc;
 }

@@ -240,10 +240,11 @@ struct Env {
                                         int partitionable, const float* nz, int nzs) const {
     float nt[D];
     if (NOISE == 2) noise_term(t, n_obs, obs_noise, partitionable, nt);
-    if (NOISE == 1) {
+    if (NOISE == 1) {  // table row: [b][4] floats, one 16-byte load per lane
+      const float4 v = __ldg(reinterpret_cast<const float4*>(nz));
+      const float t4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int i = 0; i < D; i++)
-        if (i < n_obs) nt[i] = __ldg(nz + (size_t)i * nzs);
+      for (int i = 0; i < D; i++) nt[i] = t4[i < 4 ? i : 3];
     }
 #pragma unroll
     for (int i = 0; i < D; i++) {
@@ -371,7 +372,7 @@ struct Env {
 //   k_schedule     walks the diffrax time loop (float32, same arithmetic as the rollout kernel) and
 //                  records tprev of every step;
 //   k_noise_table  evaluates normal(fold_in(key_b, bits(t))) @ W for every (step | save point, b).
-// Layout: row r = step s (r < cap) or save point k (r = cap + k); element [r][i][b].
+// Layout: row r = step s (r < cap) or save point k (r = cap + k); element [r][b][i], i padded to 4.
 __global__ void k_schedule(const float* __restrict__ ts, int K, float dt0, int max_steps, int cap,
                            float* __restrict__ tprev_out, int* __restrict__ n_steps_out) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(256) k_noise_table(const RolloutParams P, cons
   env.noise_term(t, P.n_obs, P.obs_noise, P.partitionable, nt);
 #pragma unroll
   for (int i = 0; i < Env<ENV>::D; i++)
-    if (i < P.n_obs) table[((size_t)r * P.n_obs + i) * P.B + b] = nt[i];
+    if (i < P.n_obs) table[((size_t)r * P.B + b) * 4 + i] = nt[i];
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
@@ -470,7 +471,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_rollout(const RolloutP
   }
   __syncwarp();
   float* lb = vf + lane;  // lane base of the value file (R = 1)
-  unsigned char* lbytes = reinterpret_cast<unsigned char*>(lb);
+  const mtgp_saddr lbytes = mtgp_saddr_of(lb);
   for (int s = 0; s < P.slots_per_warp; s++) lb[s * 32] = 0.0f;
   mbar_wait(bar, 0);
   // ---- pre-decode: compact (8 B) -> wide (32 B) instructions, once per individual -------------
@@ -488,7 +489,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_rollout(const RolloutP
   const int K = P.K, NL = P.n_latent;
   const float t0 = ts[0], t1 = ts[K - 1];
   const float dts = (K > 1) ? ts[1] - ts[0] : 0.0f;  // ts[1]-ts[0], acrobot.py:82
-  const mtgp_wide_instr* prog_readout = wide + woff[(KIND == MTGP_EVAL_DYNAMIC) ? P.state_size : 0];
+  const mtgp_saddr wide_s = mtgp_saddr_of(wide);
+  const mtgp_saddr prog_readout = wide_s + 32u * (uint32_t)woff[(KIND == MTGP_EVAL_DYNAMIC) ? P.state_size : 0];
   float fit_sum = 0.0f;
   unsigned long long my_steps = 0;
 
@@ -500,8 +502,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_rollout(const RolloutP
     if (KIND != MTGP_EVAL_SR) env.init(P, bb);
     if (KIND != MTGP_EVAL_SR)
       for (int i = 0; i < P.n_targets; i++) lb[(P.slot_target + i) * 32] = P.targets[bb * P.n_targets + i];
-    const float* nz_base = (NOISE == 1) ? P.noise + bb : nullptr;
-    const int nzs = P.B;
+    const float* nz_base = (NOISE == 1) ? P.noise + (size_t)bb * 4 : nullptr;
+    const int nzs = P.B * 4;  // floats per table row
 
     int fs_known = -1;
     bool viol = false;
@@ -545,7 +547,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_rollout(const RolloutP
           if (KIND != MTGP_EVAL_SR) {
             float y[DR];
             env.template f_obs<NOISE>(tprev, x, y, P.n_obs, P.obs_noise, P.partitionable,
-                                      nz_base + (size_t)steps * P.n_obs * nzs, nzs);
+                                      nz_base + (size_t)steps * nzs, nzs);
             if (KIND == MTGP_EVAL_STATIC) {
 #pragma unroll
               for (int i = 0; i < D; i++)
@@ -569,7 +571,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_rollout(const RolloutP
             }
           }
           for (int j = 0; j < NL; j++) {  // latent trees: state equation (:116) / SR vector field
-            const float f = mtgp_interpret_wide(wide + woff[j], lbytes);
+            const float f = mtgp_interpret_wide(wide_s + 32u * (uint32_t)woff[j], lbytes);
             lb[(P.slot_out + j) * 32] = lb[(P.slot_state + j) * 32] + dt * f;
           }
           new_tprev = tnext < t1 ? tnext : t1;
@@ -605,7 +607,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_rollout(const RolloutP
           } else {
             float ys[DR];
             env.template f_obs<NOISE>(tk, xs, ys, P.n_obs, P.obs_noise, P.partitionable,
-                                      nz_base + (size_t)(P.cap_steps + k) * P.n_obs * nzs, nzs);
+                                      nz_base + (size_t)(P.cap_steps + k) * nzs, nzs);
 #pragma unroll
             for (int i = 0; i < D; i++)
               if (i < P.n_obs) lb[i * 32] = ys[i];
@@ -721,7 +723,7 @@ int launch_kind_env(RolloutParams rp, int tmp_base, int bound, void* noise_ws, c
     if (noise == 1) {
       float* tprev = static_cast<float*>(noise_ws);
       int* n_steps = reinterpret_cast<int*>(tprev + rp.cap_steps);
-      float* table = tprev + rp.cap_steps + 64;
+      float* table = tprev + ((rp.cap_steps + 64 + 3) & ~3);  // 16-byte aligned rows
       k_schedule<<<1, 32, 0, stream>>>(rp.ts, rp.K, rp.dt0, rp.max_steps, rp.cap_steps, tprev, n_steps);
       const long long n = (long long)(rp.cap_steps + rp.K) * rp.B;
       k_noise_table<ENV><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(rp, tprev, n_steps, table);
@@ -772,7 +774,7 @@ size_t mtgp_noise_workspace_bytes(const mtgp_rollout_desc& d) {
   const char* force_inline = getenv("MTGP_NOISE_INLINE");  // test hook: exercise the in-kernel generator
   if (force_inline && force_inline[0] == '1') return 0;
   const size_t cap = (size_t)mtgp_noise_cap_steps(d);
-  const size_t bytes = (cap + 64) * sizeof(float) + (cap + d.K) * (size_t)d.n_obs * d.B * sizeof(float);
+  const size_t bytes = ((cap + 64 + 3) & ~(size_t)3) * sizeof(float) + (cap + d.K) * (size_t)4 * d.B * sizeof(float);
   return bytes <= kNoiseTableMaxBytes ? bytes : 0;
 }
 

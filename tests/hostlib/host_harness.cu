@@ -54,7 +54,7 @@ int hostlib_eval_tree(const float* tree, int N, const mtgp_node_table* tab, cons
     for (int j = 0; j < n_data; j++) vf[j * 32] = data[(size_t)p * n_data + j];
     out[p] = mtgp_interpret<1>(prog.data(), vf.data()).v[0];
     if (out_wide)
-      out_wide[p] = mtgp_interpret_wide(wide.data(), reinterpret_cast<unsigned char*>(vf.data()));
+      out_wide[p] = mtgp_interpret_wide(mtgp_saddr_of(wide.data()), mtgp_saddr_of(vf.data()));
   }
   if (prog_out)
     for (int i = 0; i < lstride && i < prog_cap; i++) memcpy(&prog_out[i], &prog[i], 8);
