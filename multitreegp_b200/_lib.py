@@ -8,7 +8,7 @@ import os
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmtgp_b200.so")
+LIB_PATH = os.environ.get("MTGP_LIB") or os.path.join(_HERE, "libmtgp_b200.so")  # MTGP_LIB: tuning builds
 _LIB = None
 
 

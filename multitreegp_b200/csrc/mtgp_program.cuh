@@ -271,46 +271,51 @@ static inline void mtgp_sts_f32(mtgp_saddr a, float v) { memcpy((void*)a, &v, 4)
 static inline uint4 mtgp_lds_v4(mtgp_saddr a) { uint4 v; memcpy(&v, (const void*)a, 16); return v; }
 #endif
 
+// Everything that is not + - * or a load: kept out of line so that the hot dispatch loop stays a
+// handful of instructions and the compiler cannot fold the fast-path test into a compare tree.
+static __host__ __device__ __noinline__ float mtgp_wide_slow_op(uint32_t wop, float x, float y) {
+  switch (wop) {
+    case W_SIN: return mtgp_sinf(x);
+    case W_COS: return mtgp_cosf(x);
+    case W_DIV: return x / y;
+    case W_RDIV: return y / x;
+    case W_MAX: return mtgp_maximumf(x, y);
+    case W_MIN: return mtgp_minimumf(x, y);
+    case W_EXP: return mtgp_expf(x);
+    case W_LOG: return mtgp_logf(x);
+    case W_SQRT: return mtgp_sqrtf(x);
+    case W_TANH: return mtgp_tanhf(x);
+    case W_NEG: return -x;
+    case W_ABS: return mtgp_absf(x);
+    case W_SQUARE: return x * x;
+    default: return y;  // W_LOADI
+  }
+}
+
 // prog: wide program in shared memory; lane: the lane's base of the value file (value file + lane*4).
 // Warp-uniform control flow throughout.
-__host__ __device__ __forceinline__ float mtgp_interpret_wide(mtgp_saddr prog, mtgp_saddr lane) {
+#ifndef MTGP_INTERP_INLINE
+#define MTGP_INTERP_INLINE __noinline__
+#endif
+static __host__ __device__ MTGP_INTERP_INLINE float mtgp_interpret_wide(mtgp_saddr prog, mtgp_saddr lane) {
   float acc = 0.0f;
   uint4 a = mtgp_lds_v4(prog), b = mtgp_lds_v4(prog + 16);
-  while (true) {
-    const uint32_t wop = a.y >> 16;
-    if (wop == W_END) break;
+  while (a.y >= (W_FAST << 16)) {  // W_END = 0
     const float xm = mtgp_lds_f32(lane + (a.x & 0xFFFFu));
     const float ym = mtgp_lds_f32(lane + (a.x >> 16));
     const mtgp_saddr st = lane + (a.y & 0xFFFFu);
+    const uint32_t ctl = a.y;
     const uint32_t xb = mtgp_bitsel(a.w, mtgp_f2u(xm), mtgp_f2u(acc));
     const uint32_t yb = mtgp_bitsel(b.x, mtgp_f2u(ym), a.z);
-    const float x = mtgp_u2f(xb), y = mtgp_u2f(yb);
     const uint32_t pb = mtgp_bitsel(b.z, yb, b.y);
     const uint32_t qb = mtgp_bitsel(b.z, 0x80000000u, yb ^ b.w);
     prog += 32;
     a = mtgp_lds_v4(prog);
     b = mtgp_lds_v4(prog + 16);
-    if (wop == W_FAST) {
-      acc = fmaf(x, mtgp_u2f(pb), mtgp_u2f(qb));
-    } else if (wop == W_SIN) {
-      acc = mtgp_sinf(x);
-    } else if (wop == W_COS) {
-      acc = mtgp_cosf(x);
+    if (ctl < ((W_FAST + 1u) << 16)) {
+      acc = fmaf(mtgp_u2f(xb), mtgp_u2f(pb), mtgp_u2f(qb));
     } else {
-      switch (wop) {
-        case W_DIV: acc = x / y; break;
-        case W_RDIV: acc = y / x; break;
-        case W_MAX: acc = mtgp_maximumf(x, y); break;
-        case W_MIN: acc = mtgp_minimumf(x, y); break;
-        case W_EXP: acc = mtgp_expf(x); break;
-        case W_LOG: acc = mtgp_logf(x); break;
-        case W_SQRT: acc = mtgp_sqrtf(x); break;
-        case W_TANH: acc = mtgp_tanhf(x); break;
-        case W_NEG: acc = -x; break;
-        case W_ABS: acc = mtgp_absf(x); break;
-        case W_SQUARE: acc = x * x; break;
-        default: acc = y; break;  // W_LOADI
-      }
+      acc = mtgp_wide_slow_op(ctl >> 16, mtgp_u2f(xb), mtgp_u2f(yb));
     }
     mtgp_sts_f32(st, acc);
   }

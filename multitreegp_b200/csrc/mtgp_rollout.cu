@@ -24,6 +24,9 @@
 namespace {
 
 constexpr int kWarpsPerCta = 4;
+#ifndef MTGP_ROLLOUT_MIN_CTAS
+#define MTGP_ROLLOUT_MIN_CTAS 8  // resident CTAs per SM the register allocation is tuned for
+#endif
 
 struct RolloutParams {
   const uint2* prog;
@@ -418,7 +421,7 @@ __global__ void __launch_bounds__(256) k_noise_table(const RolloutParams P, cons
 
 // ---- the kernel ----------------------------------------------------------------------------------
 template <int KIND, int ENV, int NOISE>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 4) k_rollout(const RolloutParams P) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_rollout(const RolloutParams P) {
   constexpr int D = (KIND == MTGP_EVAL_SR) ? 0 : EnvDim<ENV>::D;
   constexpr int DR = D > 0 ? D : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
