@@ -1,8 +1,8 @@
 """ctypes mirror of include/mtgp.h (the C ABI of libmtgp_b200.so).
 
 Pure declarations: structs, enums and helpers to fill them from numpy / torch buffers.  Used by
-the product loader (``_lib.py``) and, because the CPU oracle deliberately shares the same struct
-layouts, by ``oracle/pyoracle.py``.
+the product loader (``_lib.py``); the test-side CPU oracle deliberately uses the same struct layouts
+and imports them from here (the dependency points from the test infrastructure to the ABI, never back).
 """
 from __future__ import annotations
 

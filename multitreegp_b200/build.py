@@ -66,7 +66,29 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
+    build_ffi_shim(verbose)
     return LIB
+
+
+def build_ffi_shim(verbose: bool = False) -> str | None:
+    """Builds libmtgp_b200_ffi.so (csrc/mtgp_xla_ffi.cc) when jax's XLA-FFI headers are available;
+    returns None otherwise (this image has no jax)."""
+    try:
+        import jax
+        inc = jax.ffi.include_dir()
+    except Exception:  # noqa: BLE001 -- jax missing or too old: the shim is optional
+        return None
+    out = os.path.join(_HERE, "libmtgp_b200_ffi.so")
+    src = os.path.join(CSRC, "mtgp_xla_ffi.cc")
+    if _stale(out, [src, LIB]):
+        cmd = [_nvcc(), "-x", "cu", "-std=c++17", "-O2", "-Xcompiler", "-fPIC", "-shared", "-I", inc, src, "-o", out,
+               "-L", _HERE, "-lmtgp_b200", "-Xlinker", "-rpath", "-Xlinker", _HERE]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("building the XLA-FFI shim failed")
+    return out
 
 
 if __name__ == "__main__":

@@ -1,0 +1,64 @@
+"""Generates tests/golden/*.npz -- frozen input/output vectors of the hot path.
+
+The reference (JAX/diffrax) cannot be imported in this image, so these vectors are produced by the
+CPU oracle (oracle/mtgp_oracle.c, contract math) and are REGRESSION PINS of this repository, not
+outputs of the reference: they freeze today's semantics so that neither the oracle nor the kernels
+can drift silently.  If a machine with JAX becomes available, regenerate them there with the real
+reference and record the jax/diffrax versions.
+
+    python tools/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from multitreegp_b200 import abi  # noqa: E402
+from oracle import pyoracle as po  # noqa: E402
+from tests import util  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def save_case(name, lib, pop, data, out):
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"), pop=pop, opcodes=lib.opcodes, args=lib.args,
+        kind=data.kind, env_id=data.env_id, x0=data.x0, ts=data.ts, dt0=np.float32(data.dt0),
+        max_fitness=np.float32(data.max_fitness), targets=data.targets,
+        obs_keys=data.obs_keys if data.obs_keys is not None else np.zeros((0, 2), np.uint32),
+        params=data.params if data.params is not None else np.zeros((0, 0), np.float32),
+        ys_true=data.ys_true if data.ys_true is not None else np.zeros((0,), np.float32),
+        n_obs=data.n_obs, state_size=data.state_size, max_steps=data.max_steps, obs_noise=np.float32(data.obs_noise),
+        partitionable=int(data.threefry_partitionable), fitness=out["fitness"], traj_fitness=out["traj_fitness"],
+        steps=out["steps"])
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    po.build()
+    po.set_math(po.MATH_CONTRACT)
+    rng = np.random.default_rng(20261018)
+    lib, pop, data = util.sr_case(rng, P=48, B=6, T_end=3.0, dt0=0.01)
+    save_case("sr_vdp", lib, pop, data, po.rollout_population(pop, lib.table(), data))
+    for env, grid in (("harmonic", dict(T_end=5.0, dt_save=0.2, dt0=0.05)),
+                      ("acrobot", dict(T_end=5.0, dt_save=0.2, dt0=0.05)),
+                      ("reactor", dict(T_end=1.0, dt_save=0.04, dt0=0.002))):
+        for kind, kname in ((abi.EVAL_STATIC, "static"), (abi.EVAL_DYNAMIC, "dynamic")):
+            lib, pop, data = util.control_case(env, kind, rng, P=48, B=6, obs_noise=0.1,
+                                               param_mode="Constant" if env == "acrobot" else "Different", **grid)
+            save_case(f"{kname}_{env}", lib, pop, data, po.rollout_population(pop, lib.table(), data))
+    # jax.random vectors (threefry known answers are asserted literally in the tests)
+    keys = util.random_keys(rng, 16)
+    ts = np.float32(rng.uniform(0, 50, 16))
+    normals = np.stack([np.stack([po.normal(po.fold_in(k, int(np.float32(t).view(np.uint32))), n, part)
+                                  if True else None for k, t in zip(keys, ts)])
+                        for n, part in ((4, True),)])
+    np.savez_compressed(os.path.join(OUT, "obs_noise_normal4.npz"), keys=keys, ts=ts, normals=normals[0])
+    print("wrote", sorted(os.listdir(OUT)))
+
+
+if __name__ == "__main__":
+    main()
