@@ -158,11 +158,20 @@ class ClockSampler:
 
 
 # ---- CPU arms ---------------------------------------------------------------------------------------------
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm must not obey it)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_sample_size(w, target_s, n_threads=0):
     """How many individuals the oracle evaluates in about target_s seconds on this host."""
     from oracle import pyoracle as po
     po.build()
     probe = w["pop"][:32]
+    n_threads = n_threads or host_threads()
     t = time.perf_counter(); po.rollout_population(probe, w["lib"].table(), w["data"], n_threads)
     dt = time.perf_counter() - t
     n = int(min(w["pop"].shape[0], max(32, 32 * target_s / max(dt, 1e-4))))
@@ -172,11 +181,12 @@ def cpu_sample_size(w, target_s, n_threads=0):
 def cpu_time_rollout(w, target_s, n_threads=0, n=None):
     """Times the oracle (CPU restatement, all host threads) on a bounded sample of the workload."""
     from oracle import pyoracle as po
+    n_threads = n_threads or host_threads()
     n = n or cpu_sample_size(w, target_s, n_threads)
     sample = w["pop"][:n]
     t = time.perf_counter(); out = po.rollout_population(sample, w["lib"].table(), w["data"], n_threads)
     dt = time.perf_counter() - t
-    return out["steps"] / dt, n, out["steps"], dt, po.num_threads()
+    return out["steps"] / dt, n, out["steps"], dt, n_threads
 
 
 def run_reference(args):
@@ -216,6 +226,7 @@ def main():
     ap.add_argument("--population", type=int, default=None, help="override the per-GPU population (debug)")
     ap.add_argument("--obs-noise", type=float, default=0.1)
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--only-secondary", action="store_true", help="run only the pointwise scale-up (profiling)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ref-step-seconds", type=float, default=2.0)
     args = ap.parse_args()
@@ -234,6 +245,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, max(args.warmup, 3)
+    if args.only_secondary:
+        peaks, peak_src = measured_peaks()
+        print(json.dumps(bench_pointwise(FitnessEngine(dev), dev, K, peaks, peak_src, False)))
+        return
 
     # population shards: every rank its own individuals (weak scaling: per-GPU work fixed)
     w = make_rollout_workload(args.workload, seed=1000 + rank, P_override=args.population, obs_noise=args.obs_noise)
@@ -405,9 +420,10 @@ def bench_pointwise(eng, dev, K, peaks, peak_src, with_cpu):
     if with_cpu:
         from oracle import pyoracle as po
         n, npts = 256, 4096
-        t = time.perf_counter(); po.pointwise_population(pop[:n], table, X[:npts], Y[:npts]); dt = time.perf_counter() - t
+        t = time.perf_counter(); po.pointwise_population(pop[:n], table, X[:npts], Y[:npts], n_threads=host_threads())
+        dt = time.perf_counter() - t
         live_s = float((pop[:n, ..., 0] != 0).sum())
-        out["cpu_baseline"] = {"value": live_s * npts / dt, "unit": "live node-evals/s", "cores": po.num_threads(),
+        out["cpu_baseline"] = {"value": live_s * npts / dt, "unit": "live node-evals/s", "cores": host_threads(),
                                "kind": "port", "sample": f"{n} individuals x {npts} points ({dt:.1f} s)"}
     return out
 

@@ -190,7 +190,7 @@ extern "C" {
 int mtgp_abi_version(void) { return MTGP_ABI_VERSION; }
 const char* mtgp_last_error(void) { return g_err; }
 
-static int padded_points(int n_points) { return (int)align_up((size_t)(n_points > 0 ? n_points : 0), 256); }
+static int padded_points(int n_points) { return (int)align_up((size_t)(n_points > 0 ? n_points : 0), 1024); }
 
 size_t mtgp_workspace_bytes(int P, int T, int N, const mtgp_rollout_desc* rollout) {
   return carve(nullptr, P, T, N, 0, 0, rollout ? mtgp_noise_workspace_bytes(*rollout) : 0).bytes;

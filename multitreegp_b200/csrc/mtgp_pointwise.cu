@@ -12,6 +12,9 @@
 
 namespace {
 
+#ifndef MTGP_PW_R
+#define MTGP_PW_R 8  // points per lane per dispatched instruction in the fast pointwise launch
+#endif
 constexpr int kPwWarps = 4;
 constexpr int kPwGroup = 8;
 
@@ -55,28 +58,31 @@ __global__ void __launch_bounds__(kPwWarps * 32) k_pointwise(const PointwisePara
       need = 0;
       for (int t = 0; t < P.T; t++) need = max(need, (int)(P.meta[(size_t)(ind0 + threadIdx.x) * P.T + t] >> 16));
     }
-    s_need[threadIdx.x] = need;
+    s_need[threadIdx.x] = (need >= P.min_need && need <= P.n_tmp) ? 1 : 0;
   }
   __syncthreads();
   bool any = false;
-  for (int g = 0; g < G; g++) any |= (s_need[g] >= P.min_need && s_need[g] <= P.n_tmp);
+  for (int g = 0; g < G; g++) any |= (s_need[g] != 0);
   if (!any) return;
 
-  // stage the programs of the group (contiguous in global memory) -- plain vector copies
+  // stage the programs of the group (contiguous in global memory)
   {
     const uint4* src = reinterpret_cast<const uint4*>(P.prog + (size_t)ind0 * words_per_ind);
     uint4* dst = reinterpret_cast<uint4*>(prog_s);
     const int n16 = G * words_per_ind / 2;
     for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
   }
-  for (int i = threadIdx.x; i < kPwGroup * kPwWarps * 32; i += blockDim.x) acc_s[i] = 0.0f;
   __syncthreads();
 
   float* lb = vf + lane * R;
-  const int chunk_pts = 32 * R;
+  constexpr int chunk_pts = 32 * R;
   const int n_chunks = P.npad / chunk_pts;
+  // per-lane partial sums of squared error, one per individual of the group, in shared memory
+  for (int g = 0; g < kPwGroup; g++) acc_s[(g * kPwWarps + wic) * 32 + lane] = 0.0f;
+
   for (int c = wic; c < n_chunks; c += kPwWarps) {
     const int pt0 = c * chunk_pts + lane * R;
+    const bool ragged = (c + 1) * chunk_pts > P.n_points;  // warp-uniform: only the last chunk has padding
     // variables and targets of this chunk -> value file slots [0, n_vars) and [n_vars, n_vars+T)
     for (int v = 0; v < P.n_vars + P.T; v++) {
       const float* src = (v < P.n_vars) ? P.Xt + (size_t)v * P.npad : P.Yt + (size_t)(v - P.n_vars) * P.npad;
@@ -94,7 +100,7 @@ __global__ void __launch_bounds__(kPwWarps * 32) k_pointwise(const PointwisePara
       vf_store<R>(lb, v, d);
     }
     for (int g = 0; g < G; g++) {
-      if (s_need[g] < P.min_need || s_need[g] > P.n_tmp) continue;
+      if (!s_need[g]) continue;
       float row[R];
 #pragma unroll
       for (int r = 0; r < R; r++) row[r] = 0.0f;
@@ -105,19 +111,27 @@ __global__ void __launch_bounds__(kPwWarps * 32) k_pointwise(const PointwisePara
         for (int r = 0; r < R; r++) {
           const float e = pr.v[r] - yt.v[r];
           row[r] = row[r] + e * e;
-          if (P.pred && pt0 + r < P.n_points)
-            P.pred[((size_t)(ind0 + g) * P.n_points + pt0 + r) * P.T + t] = pr.v[r];
+        }
+        if (P.pred) {
+#pragma unroll
+          for (int r = 0; r < R; r++)
+            if (pt0 + r < P.n_points) P.pred[((size_t)(ind0 + g) * P.n_points + pt0 + r) * P.T + t] = pr.v[r];
         }
       }
       float s = 0.0f;
+      if (ragged) {
 #pragma unroll
-      for (int r = 0; r < R; r++) s = s + ((pt0 + r < P.n_points) ? row[r] : 0.0f);
+        for (int r = 0; r < R; r++) s = s + ((pt0 + r < P.n_points) ? row[r] : 0.0f);
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; r++) s = s + row[r];
+      }
       acc_s[(g * kPwWarps + wic) * 32 + lane] += s;
     }
   }
   __syncthreads();
   for (int g = wic; g < G; g += kPwWarps) {
-    if (s_need[g] < P.min_need || s_need[g] > P.n_tmp) continue;
+    if (!s_need[g]) continue;
     float s = 0.0f;
     for (int w = 0; w < kPwWarps; w++) s = s + acc_s[(g * kPwWarps + w) * 32 + lane];
 #pragma unroll
@@ -187,7 +201,7 @@ int mtgp_launch_pointwise(const mtgp_programs& progs, const int32_t* live, int P
   // grown into long combs by mutation) runs one point per lane with the worst-case bound.
   const int kFastTmp = 8;
   const int bound = mtgp_tmp_bound(N);
-  int rc = launch_pw<8>(pp, bound < kFastTmp ? bound : kFastTmp, 0, stream);
+  int rc = launch_pw<MTGP_PW_R>(pp, bound < kFastTmp ? bound : kFastTmp, 0, stream);
   if (rc != MTGP_OK) return rc;
   if (bound > kFastTmp) rc = launch_pw<1>(pp, bound, kFastTmp + 1, stream);
   return rc;
