@@ -62,6 +62,17 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
+def ncu_traffic(kernel, P):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the ncu --set full capture
+    recorded in profiles/r01_traffic.json (bytes per individual x P); None when no capture is on file."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)[kernel]
+        return t["dram_bytes_per_individual"] * P
+    except (OSError, KeyError):
+        return None
+
+
 # ---- workloads ---------------------------------------------------------------------------------------
 def control_library(env, kind, state_size):
     obs = [f"y{i + 1}" for i in range(env.n_obs)]
@@ -103,17 +114,20 @@ def _schedule(ts, dt0):
 
 
 def algorithmic_ops_per_step(w):
-    """algorithmic work of ONE rollout-step (every add/sub/mul/div/trig/... = 1)."""
+    """algorithmic flops of ONE rollout-step, every add/sub/mul/div/trig = 1:
+    F_env (Acrobot drift 75 as written) + tree operators + obs C@x n_obs(2D-1) [+ n_obs(2 n_obs-1) + n_obs
+    for the noise term] + Euler 2(D+S) + the post-pass share K/S of (obs + readout operators + cost).
+    The threefry/erfinv work of the observation noise is NOT counted: this implementation computes the
+    noise once per evaluation (it does not depend on the individual), not once per individual."""
     pop, lib, data = w["pop"], w["lib"], w["data"]
     arity = lib.slots[np.clip(pop[..., 0].astype(np.int64), 0, lib.n_ids - 1)]
     tree_ops = float((arity > 0).sum()) / pop.shape[0]           # operator rows per individual (all trees)
+    readout_ops = float((arity[:, w["S"]:] > 0).sum()) / pop.shape[0]
     D, n_obs, S = data.D, data.n_obs, w["S"]
-    flops = 75.0 + tree_ops + n_obs * (2 * D - 1) + 6.0 + 2.0 * (D + S)   # Acrobot drift, trees, C@x, wrap, Euler
-    int_ops = 0.0
-    if data.obs_noise != 0.0:
-        flops += n_obs * (2 * n_obs - 1) + n_obs + n_obs * 44.0   # normal@W, + noise, bits->normal (erfinv, log1p)
-        int_ops = (1 + n_obs) * 75.0                               # threefry2x32: fold_in + one block per value
-    return flops, int_ops, tree_ops
+    obs = n_obs * (2 * D - 1) + (n_obs * (2 * n_obs - 1) + n_obs if data.obs_noise != 0.0 else 0)
+    post = (data.K / max(w["n_sched"], 1)) * (obs + readout_ops + 8.0)     # reached test (6) + u R u (2)
+    flops = 75.0 + tree_ops + obs + 2.0 * (D + S) + post
+    return flops, 0.0, tree_ops
 
 
 # ---- clocks ---------------------------------------------------------------------------------------------
@@ -329,7 +343,7 @@ def main():
     fp32_peak = N_SM * FP32_LANES_PER_SM * 2 * sm_mhz * 1e6 / 1e12
     achieved = per_launch_steps * (flops + int_ops) / (kernel_ms * 1e-3) / 1e12
     roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": achieved / fp32_peak, "traffic": None, "kernel": "k_rollout<DYNAMIC,ACROBOT,noise>",
+                "frac": achieved / fp32_peak, "traffic": ncu_traffic("k_rollout", P), "kernel": "k_rollout<DYNAMIC,ACROBOT,noise>",
                 "kernel_ms": kernel_ms, "ops_per_rollout_step": {"fp": flops, "int_prng": int_ops, "tree_ops": tree_ops},
                 "peak_note": f"non-tensor FP32: 148 SM x 128 lanes x 2 (FMA) x {sm_mhz:.0f} MHz ({peak_src} clock); "
                              "the path runs un-fused IEEE ops by contract, whose ceiling is half of this"}
@@ -390,7 +404,7 @@ def main():
 def bench_pointwise(eng, dev, K, peaks, peak_src, with_cpu):
     import torch
     rng = np.random.default_rng(7)
-    lib = NodeLibrary(OPS_SR + [("sin", 1, 0.1), ("cos", 1, 0.1)], [[f"x{i}" for i in range(C4["n_vars"])]], [1])
+    lib = NodeLibrary(OPS_SR, [[f"x{i}" for i in range(C4["n_vars"])]], [1])   # SymbolicRegression.ipynb:138-141
     pop = sample_population(rng, C4["P"], lib, C4["depth"], C4["N"])
     X, Y = pointwise_data(rng, C4["n_points"], C4["n_vars"])
     pop_d, Xd, Yd = (torch.from_numpy(a).to(dev) for a in (pop, X, Y))

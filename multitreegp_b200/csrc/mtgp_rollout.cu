@@ -25,7 +25,7 @@ namespace {
 
 constexpr int kWarpsPerCta = 4;
 #ifndef MTGP_ROLLOUT_MIN_CTAS
-#define MTGP_ROLLOUT_MIN_CTAS 8  // resident CTAs per SM the register allocation is tuned for
+#define MTGP_ROLLOUT_MIN_CTAS 7  // resident CTAs per SM the register allocation is tuned for
 #endif
 
 struct RolloutParams {
@@ -490,12 +490,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
 
   const float* ts = P.ts;
   const int K = P.K, NL = P.n_latent;
+  // shared-space addresses of the latent-state slots of this lane (component j is 128 bytes further)
+  const mtgp_saddr a_state = lbytes + 128u * (uint32_t)P.slot_state, a_out = lbytes + 128u * (uint32_t)P.slot_out,
+                   a_lat = lbytes + 128u * (uint32_t)P.slot_lat;
   const float t0 = ts[0], t1 = ts[K - 1];
   const float dts = (K > 1) ? ts[1] - ts[0] : 0.0f;  // ts[1]-ts[0], acrobot.py:82
   const mtgp_saddr wide_s = mtgp_saddr_of(wide);
   const mtgp_saddr prog_readout = wide_s + 32u * (uint32_t)woff[(KIND == MTGP_EVAL_DYNAMIC) ? P.state_size : 0];
   float fit_sum = 0.0f;
-  unsigned long long my_steps = 0;
+  unsigned int my_steps = 0;  // Euler steps integrated by this lane (< 2^32: max_steps is capped at 2^22 per solve)
 
   for (int b0 = 0; b0 < P.B; b0 += 32) {  // B > 32: the warp takes 32 trajectories at a time
     const int b = b0 + lane;
@@ -537,6 +540,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
       float tprev = t0, tnext = t0 + P.dt0;
       tnext = tnext < t1 ? tnext : t1;
       int steps = 0, k = 0;
+      float ts_k = ts[0];  // ts[k], reloaded only when k advances
       // One iteration = one Euler step while any lane is still integrating, then the save points that
       // step covers.  Once the solve is over (t1 reached, max_steps, or every lane's event fired) the
       // remaining save points are emitted from the inf pre-fill of SaveAt -- by the same code.
@@ -575,7 +579,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
           }
           for (int j = 0; j < NL; j++) {  // latent trees: state equation (:116) / SR vector field
             const float f = mtgp_interpret_wide(wide_s + 32u * (uint32_t)woff[j], lbytes);
-            lb[(P.slot_out + j) * 32] = lb[(P.slot_state + j) * 32] + dt * f;
+            mtgp_sts_f32(a_out + 128u * j, mtgp_lds_f32(a_state + 128u * j) + dt * f);
           }
           new_tprev = tnext < t1 ? tnext : t1;
           new_tnext = tnext + P.dt0;
@@ -584,8 +588,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
         }
         const bool live_save = stepping && alive;
         // ---- SaveAt(ts): dense (linear) output for every ts[k] <= tnext ----
-        while (k < K && ts[k] <= save_until) {
-          const float tk = ts[k];
+        while (k < K && ts_k <= save_until) {
+          const float tk = ts_k;
           const float coeff = (tprev == tnext) ? 0.0f : (tk - tprev) / (tnext - tprev);
           float xs[DR];
           if (KIND != MTGP_EVAL_SR) {
@@ -594,14 +598,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
           }
           float row = 0.0f;
           for (int j = 0; j < NL; j++) {
-            const float a0 = lb[(P.slot_state + j) * 32], a1 = lb[(P.slot_out + j) * 32];
+            const float a0 = mtgp_lds_f32(a_state + 128u * j), a1 = mtgp_lds_f32(a_out + 128u * j);
             const float lat = live_save ? a0 + coeff * (a1 - a0) : mtgp_inff();
             if (KIND == MTGP_EVAL_SR) {
               const float e = lat - P.ys_true[((size_t)bb * K + k) * NL + j];
               row = row + e * e;
               if (P.xs_o && lane_valid && pass == 0) P.xs_o[(((size_t)ind * P.B + b) * K + k) * NL + j] = lat;
             } else {
-              lb[(P.slot_lat + j) * 32] = lat;
+              mtgp_sts_f32(a_lat + 128u * j, lat);
               if (P.act_o && lane_valid && pass == 0) P.act_o[(((size_t)ind * P.B + b) * K + k) * NL + j] = lat;
             }
           }
@@ -632,27 +636,28 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
             }
           }
           k++;
+          ts_k = ts[k < K ? k : K - 1];
         }
         if (stepping) {
           // ---- Event(cond_fn): sign change of cond_fn evaluated at (tnext, y1) ----
           bool bad = false;
           if (KIND != MTGP_EVAL_SR) bad = env.bad_state(x1);
-          for (int j = 0; j < NL; j++) bad |= !mtgp_isfinitef(lb[(P.slot_out + j) * 32]);
+          for (int j = 0; j < NL; j++) bad |= !mtgp_isfinitef(mtgp_lds_f32(a_out + 128u * j));
           const bool fired = (bad != ev_old_bad);
           // ---- commit ----
           if (alive) {
             ev_old_bad = bad;
-            if (pass == 0 && lane_valid) my_steps++;
+            my_steps += (pass == 0 && lane_valid) ? 1u : 0u;
             if (KIND != MTGP_EVAL_SR) {
 #pragma unroll
               for (int i = 0; i < D; i++) x[i] = x1[i];
             }
           }
           for (int j = 0; j < NL; j++) {
-            const float cur = lb[(P.slot_state + j) * 32];
-            const float nv = alive ? lb[(P.slot_out + j) * 32] : cur;
-            lb[(P.slot_state + j) * 32] = nv;
-            lb[(P.slot_lat + j) * 32] = nv;
+            const float cur = mtgp_lds_f32(a_state + 128u * j);
+            const float nv = alive ? mtgp_lds_f32(a_out + 128u * j) : cur;
+            mtgp_sts_f32(a_state + 128u * j, nv);
+            mtgp_sts_f32(a_lat + 128u * j, nv);
           }
           if (alive && fired) alive = false;
           tprev = new_tprev;
@@ -675,7 +680,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
   // mean over B (fixed shuffle tree), clip, parsimony
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) fit_sum = fit_sum + __shfl_xor_sync(0xFFFFFFFFu, fit_sum, o);
-  for (int o = 16; o > 0; o >>= 1) my_steps += __shfl_xor_sync(0xFFFFFFFFu, my_steps, o);
+  unsigned long long warp_steps = my_steps;
+  for (int o = 16; o > 0; o >>= 1) warp_steps += __shfl_xor_sync(0xFFFFFFFFu, warp_steps, o);
   if (lane == 0) {
     float f = clip_jnp(fit_sum / (float)P.B, 0.0f, P.max_fitness);
     if (P.live) {
@@ -684,7 +690,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
       f = f + P.size_parsimony * (float)cnt;
     }
     P.fitness[ind] = f;
-    if (P.steps_done) atomicAdd(P.steps_done, my_steps);
+    if (P.steps_done) atomicAdd(P.steps_done, warp_steps);
   }
 }
 
