@@ -131,8 +131,11 @@ __host__ __device__ __forceinline__ void vf_store(float* lane_base, uint32_t slo
 // prog: shared-memory program (terminated by X_END), identical for all lanes of the warp, so every
 // branch below is warp-uniform and its cost is amortised over the 32*R values a warp evaluates per
 // dispatched instruction.  lane_base = value file + lane*R.
+#ifndef MTGP_COMPACT_INLINE
+#define MTGP_COMPACT_INLINE __noinline__
+#endif
 template <int R>
-__host__ __device__ __noinline__ Vec<R> mtgp_interpret(const uint2* __restrict__ prog, float* lane_base) {
+__host__ __device__ MTGP_COMPACT_INLINE Vec<R> mtgp_interpret(const uint2* __restrict__ prog, float* lane_base) {
   Vec<R> acc;
   MTGP_FOR_R acc.v[r] = 0.0f;
   uint2 w = prog[0];
@@ -142,28 +145,58 @@ __host__ __device__ __noinline__ Vec<R> mtgp_interpret(const uint2* __restrict__
     const float imm = mtgp_u2f(w.y);
     w = prog[++pc];  // prefetch the next instruction under this one's arithmetic
     const uint32_t op = c & 15u, xk = (c >> 4) & 3u, yk = (c >> 6) & 3u, st = (c >> 8) & 0xFFu;
-    Vec<R> x = acc, y = acc;
-    if (xk == OK_MEM) x = vf_load<R>(lane_base, (c >> 16) & 0xFFu);
-    if (yk == OK_MEM) y = vf_load<R>(lane_base, c >> 24);
-    if (xk == OK_IMM) { MTGP_FOR_R x.v[r] = imm; }
-    if (yk == OK_IMM) { MTGP_FOR_R y.v[r] = imm; }
-    switch (op) {
-      case X_LOAD: acc = x; break;
-      case X_ADD: MTGP_FOR_R acc.v[r] = x.v[r] + y.v[r]; break;
-      case X_SUB: MTGP_FOR_R acc.v[r] = x.v[r] - y.v[r]; break;
-      case X_MUL: MTGP_FOR_R acc.v[r] = x.v[r] * y.v[r]; break;
-      case X_DIV: MTGP_FOR_R acc.v[r] = x.v[r] / y.v[r]; break;
-      case X_MAX: MTGP_FOR_R acc.v[r] = mtgp_maximumf(x.v[r], y.v[r]); break;
-      case X_MIN: MTGP_FOR_R acc.v[r] = mtgp_minimumf(x.v[r], y.v[r]); break;
-      case X_SIN: MTGP_FOR_R acc.v[r] = mtgp_sinf(x.v[r]); break;
-      case X_COS: MTGP_FOR_R acc.v[r] = mtgp_cosf(x.v[r]); break;
-      case X_EXP: MTGP_FOR_R acc.v[r] = mtgp_expf(x.v[r]); break;
-      case X_LOG: MTGP_FOR_R acc.v[r] = mtgp_logf(x.v[r]); break;
-      case X_SQRT: MTGP_FOR_R acc.v[r] = mtgp_sqrtf(x.v[r]); break;
-      case X_TANH: MTGP_FOR_R acc.v[r] = mtgp_tanhf(x.v[r]); break;
-      case X_NEG: MTGP_FOR_R acc.v[r] = -x.v[r]; break;
-      default: MTGP_FOR_R acc.v[r] = mtgp_absf(x.v[r]); break;  // X_ABS
+    const uint32_t xs = (c >> 16) & 0xFFu, ys = c >> 24;
+    // + - * and loads: one straight-line leaf per operand-kind combination, operands streamed from
+    // the value file straight into the arithmetic -- no control-flow merge, so no register copies
+#define MTGP_LEAF(EXPR) { MTGP_FOR_R acc.v[r] = (EXPR); }
+#define MTGP_BINOP(F)                                                                                       \
+  if (xk == OK_ACC) {                                                                                       \
+    if (yk == OK_MEM) { const Vec<R> y = vf_load<R>(lane_base, ys); MTGP_LEAF(F(acc.v[r], y.v[r])) }        \
+    else if (yk == OK_IMM) MTGP_LEAF(F(acc.v[r], imm))                                                      \
+    else MTGP_LEAF(F(acc.v[r], acc.v[r]))                                                                   \
+  } else if (xk == OK_MEM) {                                                                                \
+    const Vec<R> x = vf_load<R>(lane_base, xs);                                                             \
+    if (yk == OK_MEM) { const Vec<R> y = vf_load<R>(lane_base, ys); MTGP_LEAF(F(x.v[r], y.v[r])) }          \
+    else if (yk == OK_IMM) MTGP_LEAF(F(x.v[r], imm))                                                        \
+    else MTGP_LEAF(F(x.v[r], acc.v[r]))                                                                     \
+  } else {                                                                                                  \
+    if (yk == OK_MEM) { const Vec<R> y = vf_load<R>(lane_base, ys); MTGP_LEAF(F(imm, y.v[r])) }             \
+    else MTGP_LEAF(F(imm, acc.v[r]))                                                                        \
+  }
+#define MTGP_F_ADD(a, b) ((a) + (b))
+#define MTGP_F_SUB(a, b) ((a) - (b))
+#define MTGP_F_MUL(a, b) ((a) * (b))
+    if (op == X_ADD) {
+      MTGP_BINOP(MTGP_F_ADD)
+    } else if (op == X_MUL) {
+      MTGP_BINOP(MTGP_F_MUL)
+    } else if (op == X_SUB) {
+      MTGP_BINOP(MTGP_F_SUB)
+    } else if (op == X_LOAD) {
+      if (xk == OK_MEM) { const Vec<R> x = vf_load<R>(lane_base, xs); MTGP_LEAF(x.v[r]) }
+      else MTGP_LEAF(imm)
+    } else {
+      Vec<R> x = acc, y = acc;
+      if (xk == OK_MEM) x = vf_load<R>(lane_base, xs);
+      if (yk == OK_MEM) y = vf_load<R>(lane_base, ys);
+      if (xk == OK_IMM) { MTGP_FOR_R x.v[r] = imm; }
+      if (yk == OK_IMM) { MTGP_FOR_R y.v[r] = imm; }
+      switch (op) {
+        case X_DIV: MTGP_FOR_R acc.v[r] = x.v[r] / y.v[r]; break;
+        case X_MAX: MTGP_FOR_R acc.v[r] = mtgp_maximumf(x.v[r], y.v[r]); break;
+        case X_MIN: MTGP_FOR_R acc.v[r] = mtgp_minimumf(x.v[r], y.v[r]); break;
+        case X_SIN: MTGP_FOR_R acc.v[r] = mtgp_sinf(x.v[r]); break;
+        case X_COS: MTGP_FOR_R acc.v[r] = mtgp_cosf(x.v[r]); break;
+        case X_EXP: MTGP_FOR_R acc.v[r] = mtgp_expf(x.v[r]); break;
+        case X_LOG: MTGP_FOR_R acc.v[r] = mtgp_logf(x.v[r]); break;
+        case X_SQRT: MTGP_FOR_R acc.v[r] = mtgp_sqrtf(x.v[r]); break;
+        case X_TANH: MTGP_FOR_R acc.v[r] = mtgp_tanhf(x.v[r]); break;
+        case X_NEG: MTGP_FOR_R acc.v[r] = -x.v[r]; break;
+        default: MTGP_FOR_R acc.v[r] = mtgp_absf(x.v[r]); break;  // X_ABS
+      }
     }
+#undef MTGP_LEAF
+#undef MTGP_BINOP
     if (st != MTGP_NO_SLOT) vf_store<R>(lane_base, st, acc);
   }
   return acc;
