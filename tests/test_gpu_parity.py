@@ -146,6 +146,49 @@ def test_batch_sizes_and_ragged_edges(engine, oracle):
             _assert_fitness(gpu["fitness"], ref["fitness"], 1e4)
 
 
+def test_configuration_corners(engine, oracle):
+    """Shapes away from the notebooks' defaults: partial observability, more latent trees, big trees that
+    fall into the worst-case-provisioned launch, max_nodes 255, B > 32 with observation noise."""
+    from multitreegp_b200.environments.control_environments import Acrobot, HarmonicOscillator
+    from multitreegp_b200.synthetic import sample_population
+    rng = np.random.default_rng(13)
+    cases = []
+    # n_obs < n_var (C = eye(4)[:2]), state_size 4 -> T = 5, B = 40 (two passes) with noise
+    env = Acrobot(0.0, 0.1, n_obs=2)
+    lib = util.control_library(env, abi.EVAL_DYNAMIC, state_size=4)
+    cases.append((lib, sample_population(rng, 24, lib, 4, 30),
+                  util.control_data(env, abi.EVAL_DYNAMIC, rng, 40, 4.0, 0.2, 0.05, 4)))
+    # full trees of depth 7 (127 live rows, 63 operators per tree): beyond the fast launch's 64 instructions
+    env = HarmonicOscillator(0.0, 0.0)
+    lib = util.control_library(env, abi.EVAL_DYNAMIC, state_size=2, ops=util.OPS_SR)
+    cases.append((lib, sample_population(rng, 10, lib, 7, 127, full=True),
+                  util.control_data(env, abi.EVAL_DYNAMIC, rng, 8, 2.0, 0.2, 0.05, 2, "Different")))
+    # max_nodes 255 with ordinary (sparse) trees, static policy, noise on
+    env = HarmonicOscillator(0.0, 0.05)
+    lib = util.control_library(env, abi.EVAL_STATIC, ops=util.OPS_ALL)
+    cases.append((lib, sample_population(rng, 40, lib, 8, 255),
+                  util.control_data(env, abi.EVAL_STATIC, rng, 8, 3.0, 0.2, 0.05, 0, "Different")))
+    for lib, pop, data in cases:
+        ref = oracle.rollout_population(pop, lib.table(), data, trajectories=True)
+        gpu = _gpu_rollout(engine, lib, pop, data, trajectories=True, count_steps=True)
+        for k in ("xs", "ys", "us", "traj_fitness"):
+            assert util.same_or_both_nan(gpu[k], ref[k]).all(), k
+        _assert_fitness(gpu["fitness"], ref["fitness"], 1e4)
+        assert int(gpu["steps"][0]) == ref["steps"]
+    # SR with three trees (a 3-dimensional system)
+    from multitreegp_b200.node_library import NodeLibrary
+    from multitreegp_b200.rollout_data import RolloutData
+    lib = NodeLibrary(util.OPS_SR, [["x0", "x1", "x2"]], [3])
+    pop = sample_population(rng, 60, lib, 4, 30)
+    B, ts = 5, np.arange(0, 2, 0.1, dtype=np.float32)
+    data = RolloutData(kind=abi.EVAL_SR, env_id=abi.ENV_NONE, x0=rng.normal(size=(B, 3)).astype(np.float32), ts=ts,
+                       dt0=0.01, max_fitness=1e5, ys_true=rng.normal(size=(B, ts.size, 3)).astype(np.float32))
+    ref = oracle.rollout_population(pop, lib.table(), data, trajectories=True)
+    gpu = _gpu_rollout(engine, lib, pop, data, trajectories=True)
+    assert util.same_or_both_nan(gpu["xs"], ref["xs"]).all()
+    assert util.same_or_both_nan(gpu["traj_fitness"], ref["traj_fitness"]).all()
+
+
 def test_max_steps_and_odd_time_grids(engine, oracle):
     rng = np.random.default_rng(7)
     # dt0 larger than the save spacing (several saves per step), dt0 not dividing the horizon, max_steps hit
