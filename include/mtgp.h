@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MTGP_ABI_VERSION 1
+#define MTGP_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define MTGP_API __attribute__((visibility("default")))
@@ -113,6 +113,9 @@ typedef enum mtgp_env_id {
   MTGP_ENV_REACTOR = 3    /* reactor.py:7-99,    params: Vol, Cp, dHr, UA, q, Tf, Tcf, Volc */
 } mtgp_env_id;
 
+typedef enum mtgp_solver { MTGP_SOLVER_EULER = 0, MTGP_SOLVER_DOPRI5 = 1 } mtgp_solver;
+typedef enum mtgp_controller { MTGP_CONTROLLER_CONSTANT = 0, MTGP_CONTROLLER_PID = 1 } mtgp_controller;
+
 typedef enum mtgp_evaluator_kind {
   MTGP_EVAL_SR = 0,       /* evaluators/SR_evaluator.py        max_fitness 1e5 */
   MTGP_EVAL_STATIC = 1,   /* evaluators/feedforward_evaluate.py max_fitness 1e4 */
@@ -139,6 +142,18 @@ typedef struct mtgp_rollout_desc {
   float max_fitness;    /* penalty / clip bound */
   float obs_noise;      /* W = obs_noise * I  (0 => noise skipped, bit-identical) */
   int32_t threefry_partitionable; /* jax_threefry_partitionable (default True since JAX 0.5) */
+  /* solver / step-size controller.  All zero = the evaluators' class defaults, diffrax.Euler() +
+   * ConstantStepSize() (SR_evaluator.py:21, feedforward_evaluate.py:11, dynamic_evaluate.py:11); the
+   * shipped notebooks pass Dopri5() + PIDController(atol, rtol, dtmin=0.001) (the notebooks under examples/). */
+  int32_t solver;        /* mtgp_solver */
+  int32_t controller;    /* mtgp_controller (PID needs an embedded error estimate: Dopri5 only) */
+  float rtol, atol;      /* PIDController tolerances */
+  float dtmin;           /* PIDController dtmin with force_dtmin=True; <= 0: none */
+  float pid_safety;      /* 0 -> diffrax default 0.9 */
+  float pid_factormin;   /* 0 -> 0.2 */
+  float pid_factormax;   /* 0 -> 10.0 */
+  float pcoeff, icoeff, dcoeff; /* all 0 -> diffrax defaults (0, 1, 0): an I-controller */
+  int32_t reserved_;
   const float* x0;        /* [B, D] */
   const float* ts;        /* [K]    */
   const float* targets;   /* [B, n_targets] or NULL */

@@ -10,7 +10,7 @@ import ctypes as C
 
 import numpy as np
 
-MTGP_ABI_VERSION = 1
+MTGP_ABI_VERSION = 2
 MTGP_MAX_NODE_IDS = 64
 MTGP_MAX_NODES = 512
 
@@ -31,6 +31,8 @@ OPERATOR_STRINGS = {
 # mtgp_env_id / mtgp_evaluator_kind
 ENV_NONE, ENV_ACROBOT, ENV_HARMONIC, ENV_REACTOR = 0, 1, 2, 3
 EVAL_SR, EVAL_STATIC, EVAL_DYNAMIC = 0, 1, 2
+SOLVER_EULER, SOLVER_DOPRI5 = 0, 1
+CONTROLLER_CONSTANT, CONTROLLER_PID = 0, 1
 
 BC_CANONICAL, BC_LOSSY = 1, 2
 
@@ -73,6 +75,18 @@ class RolloutDesc(C.Structure):
         ("max_fitness", C.c_float),
         ("obs_noise", C.c_float),
         ("threefry_partitionable", C.c_int32),
+        ("solver", C.c_int32),
+        ("controller", C.c_int32),
+        ("rtol", C.c_float),
+        ("atol", C.c_float),
+        ("dtmin", C.c_float),
+        ("pid_safety", C.c_float),
+        ("pid_factormin", C.c_float),
+        ("pid_factormax", C.c_float),
+        ("pcoeff", C.c_float),
+        ("icoeff", C.c_float),
+        ("dcoeff", C.c_float),
+        ("reserved_", C.c_int32),
         ("x0", C.c_void_p),
         ("ts", C.c_void_p),
         ("targets", C.c_void_p),

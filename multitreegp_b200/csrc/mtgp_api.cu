@@ -128,6 +128,21 @@ int validate_rollout(const mtgp_rollout_desc* d, int T, int N, const mtgp_node_t
     mtgp_set_error("dt0 must be > 0 and max_steps >= 1");
     return MTGP_ERR_INVALID_ARGUMENT;
   }
+  if ((d->solver != MTGP_SOLVER_EULER && d->solver != MTGP_SOLVER_DOPRI5) ||
+      (d->controller != MTGP_CONTROLLER_CONSTANT && d->controller != MTGP_CONTROLLER_PID)) {
+    mtgp_set_error("unknown solver %d / step-size controller %d", d->solver, d->controller);
+    return MTGP_ERR_INVALID_ARGUMENT;
+  }
+  if (d->controller == MTGP_CONTROLLER_PID) {
+    if (d->solver != MTGP_SOLVER_DOPRI5) {  // diffrax raises too: Euler has no embedded error estimate
+      mtgp_set_error("PIDController needs a solver with an error estimate (Dopri5), not Euler");
+      return MTGP_ERR_INVALID_ARGUMENT;
+    }
+    if (!(d->rtol > 0.0f) && !(d->atol > 0.0f)) {
+      mtgp_set_error("PIDController needs rtol > 0 or atol > 0");
+      return MTGP_ERR_INVALID_ARGUMENT;
+    }
+  }
   int envD = 0, envP = 0;
   switch (d->env_id) {
     case MTGP_ENV_NONE: break;

@@ -1,0 +1,361 @@
+// mtgp_env.cuh -- device code shared by the rollout kernels: kernel parameters, mbarrier / bulk-copy
+// helpers, jax.random (threefry, normal), and the environment functors (observation, drift, event,
+// cost) restating MultiTreeGP/environments/control_environments/*.py.
+#pragma once
+
+#include "mtgp_internal.cuh"
+
+namespace mtgp_dev {
+
+constexpr int kWarpsPerCta = 4;
+#ifndef MTGP_ROLLOUT_MIN_CTAS
+#define MTGP_ROLLOUT_MIN_CTAS 7  // resident CTAs per SM the register allocation is tuned for
+#endif
+
+struct RolloutParams {
+  const uint2* prog;
+  const uint32_t* meta;
+  const int32_t* live;
+  int lstride;
+  int P, T;
+  int B, K, n_obs, n_targets, n_params, state_size, max_steps;
+  float dt0, max_fitness, obs_noise, size_parsimony;
+  int partitionable;
+  const float *x0, *ts, *targets, *params, *ys_true;
+  const uint32_t* obs_keys;
+  float* fitness;
+  float *xs_o, *ys_o, *us_o, *act_o, *tf_o;
+  unsigned long long* steps_done;
+  const float* noise;  // [cap_steps + K, n_obs, B] precomputed observation noise (NOISE == 1), see k_noise_table
+  int cap_steps;       // rows of the step part of the noise table
+  int fast_tmp, fast_instr, want_fast;  // launch class: programs within / beyond the fast provisioning
+  int n_latent;        // state kept in the value file: SR -> T, DYNAMIC -> state_size, STATIC -> 0
+  int slot_lat;        // data-vector slot of latent component 0
+  int slot_u;          // data-vector slot of the control (control evaluators)
+  int slot_target;     // data-vector slot of target 0
+  int slot_out;        // n_latent slots: y1 of the latent state
+  int slot_state;      // n_latent slots: master copy of the latent state
+  int slots_per_warp;      // data + latent copies + temporaries + 1 scratch slot
+  int prog_words_per_warp; // compact staging area (uint2)
+  int wide_cap;            // pre-decoded instructions provisioned per warp
+  // general Runge-Kutta path (mtgp_rollout_rk.cu): Dopri5 and/or PIDController
+  int solver, controller;
+  float rtol, atol, dtmin, safety, factormin, factormax, coeff1, coeff2, coeff3;
+  int slot_rk;             // first of the 12 * (D + n_latent) slots: Y, Y1, YI, F0, KS[7], SV
+};
+constexpr int kMaxTrees = 32;
+
+// ---- PTX helpers: mbarrier + 1-D bulk async copy (TMA) ------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// ---- jax.random on the device (THIRD-PARTY semantics; same as the oracle) -----
+__device__ __forceinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t& o0,
+                                             uint32_t& o1) {
+  const uint32_t k2 = k0 ^ k1 ^ 0x1BD11BDAu;
+#define TF_ROUND(r)                    \
+  x0 += x1;                            \
+  x1 = __funnelshift_l(x1, x1, r);     \
+  x1 ^= x0;
+  x0 += k0; x1 += k1;
+  TF_ROUND(13) TF_ROUND(15) TF_ROUND(26) TF_ROUND(6)
+  x0 += k1; x1 += k2 + 1u;
+  TF_ROUND(17) TF_ROUND(29) TF_ROUND(16) TF_ROUND(24)
+  x0 += k2; x1 += k0 + 2u;
+  TF_ROUND(13) TF_ROUND(15) TF_ROUND(26) TF_ROUND(6)
+  x0 += k0; x1 += k1 + 3u;
+  TF_ROUND(17) TF_ROUND(29) TF_ROUND(16) TF_ROUND(24)
+  x0 += k1; x1 += k2 + 4u;
+  TF_ROUND(13) TF_ROUND(15) TF_ROUND(26) TF_ROUND(6)
+  x0 += k2; x1 += k0 + 5u;
+#undef TF_ROUND
+  o0 = x0; o1 = x1;
+}
+
+__device__ __forceinline__ float bits_to_normal(uint32_t bits) {
+  const float lo = -0.99999994f;
+  const float scale = 1.0f - lo;
+  const float f = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
+  float u = f * scale + lo;
+  u = (u > lo) ? u : lo;
+  return 1.41421356f * mtgp_erfinvf(u);
+}
+
+// normal(fold_in(key, bits(t)), (n,)) for n <= 4
+template <int NMAXOBS>
+__device__ __forceinline__ void obs_normal(uint32_t key0, uint32_t key1, float t, int n, int partitionable,
+                                           float* out) {
+  uint32_t f0, f1;
+  threefry2x32(key0, key1, 0u, __float_as_uint(t), f0, f1);
+  uint32_t bits[NMAXOBS];
+  if (partitionable) {
+#pragma unroll
+    for (int i = 0; i < NMAXOBS; i++) {
+      if (i < n) {
+        uint32_t o0, o1;
+        threefry2x32(f0, f1, 0u, (uint32_t)i, o0, o1);
+        bits[i] = o0 ^ o1;
+      }
+    }
+  } else {
+    const int half = (n + 1) >> 1;
+#pragma unroll
+    for (int i = 0; i < (NMAXOBS + 1) / 2; i++) {
+      if (i < half) {
+        uint32_t o0, o1;
+        const uint32_t c1 = (half + i < n) ? (uint32_t)(half + i) : 0u;
+        threefry2x32(f0, f1, (uint32_t)i, c1, o0, o1);
+#pragma unroll
+        for (int j = 0; j < NMAXOBS; j++) {
+          if (j == i) bits[j] = o0;
+          if (j == half + i && j < n) bits[j] = o1;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NMAXOBS; i++)
+    if (i < n) out[i] = bits_to_normal(bits[i]);
+}
+
+__device__ __forceinline__ float clip_jnp(float v, float lo, float hi) {
+  if (v != v) return v;
+  v = v > lo ? v : lo;
+  return v < hi ? v : hi;
+}
+
+__device__ __forceinline__ void sincos_contract(float x, float& s, float& c) {
+  // identical to mtgp_sinf(x), mtgp_cosf(x): one shared argument reduction
+  int q;
+  const float r = mtgp_trig_reduce(x, &q);
+  const float sk = mtgp_sin_kernel(r), ck = mtgp_cos_kernel(r);
+  const float sv = (q & 1) ? ck : sk;
+  const float cv = (q & 1) ? sk : ck;
+  s = (q & 2) ? -sv : sv;
+  c = ((q + 1) & 2) ? -cv : cv;
+}
+
+// ---- environments --------------------------------------------------------------------------------
+template <int ENV>
+struct EnvDim { static constexpr int D = 1; };
+template <> struct EnvDim<MTGP_ENV_ACROBOT> { static constexpr int D = 4; };
+template <> struct EnvDim<MTGP_ENV_HARMONIC> { static constexpr int D = 2; };
+template <> struct EnvDim<MTGP_ENV_REACTOR> { static constexpr int D = 3; };
+
+template <int ENV>
+struct Env {
+  static constexpr int D = EnvDim<ENV>::D;
+  float p[8];
+  float target;
+  uint32_t key0, key1;
+  // cost accumulators
+  float sum, sum0, u_d;
+  int fs;
+
+  __device__ __forceinline__ void init(const RolloutParams& P, int b) {
+    if (ENV == MTGP_ENV_ACROBOT) {
+      const float l1 = P.params[b * P.n_params + 0], l2 = P.params[b * P.n_params + 1];
+      const float m1 = P.params[b * P.n_params + 2], m2 = P.params[b * P.n_params + 3];
+      p[0] = l1; p[1] = l2; p[2] = m1; p[3] = m2;
+      p[4] = 0.5f * l1;  // lc1
+      p[5] = 0.5f * l2;  // lc2
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) p[i] = (i < P.n_params) ? P.params[b * P.n_params + i] : 0.0f;
+    }
+    target = (P.n_targets > 0) ? P.targets[b * P.n_targets] : 0.0f;
+    key0 = P.obs_keys ? P.obs_keys[2 * b] : 0u;
+    key1 = P.obs_keys ? P.obs_keys[2 * b + 1] : 0u;
+    sum = 0.0f; sum0 = 0.0f; fs = -1;
+    if (ENV == MTGP_ENV_HARMONIC) {
+      // u_d = -pinv(b) @ A @ x_d, x_d = [target, 0]   (harmonic_oscillator.py:77-79)
+      const float r0 = ((-0.0f) * 0.0f) + ((-1.0f) * (-p[0]));
+      const float r1 = ((-0.0f) * 1.0f) + ((-1.0f) * (-p[1]));
+      u_d = (r0 * target) + (r1 * 0.0f);
+    }
+  }
+
+  // EnvironmentBase.f_obs (control_environment_base.py:43-48) + Acrobot.f_obs (acrobot.py:29-32)
+  // normal(fold_in(key, bits(t)), (n_obs,)) @ W, W = obs_noise * eye (reactor.py:43 scales it)
+  __device__ __forceinline__ void noise_term(float t, int n_obs, float obs_noise, int partitionable,
+                                             float* out) const {
+    float nrm[D];
+    obs_normal<D>(key0, key1, t, n_obs, partitionable, nrm);
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      if (i < n_obs) {
+        float nacc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+          if (j < n_obs) {
+            float w = (i == j) ? obs_noise : 0.0f;
+            if (ENV == MTGP_ENV_REACTOR) w = w * (i == 2 ? 0.1f : 15.0f);
+            const float term = nrm[j] * w;
+            nacc = (j == 0) ? term : nacc + term;
+          }
+        }
+        out[i] = nacc;
+      }
+    }
+  }
+
+  // NOISE: 0 none, 1 = noise term read from the precomputed table row `nz` (element stride `nzs`),
+  //        2 = generated inline.  All three give the same bits.
+  template <int NOISE>
+  __device__ __forceinline__ void f_obs(float t, const float* x, float* y, int n_obs, float obs_noise,
+                                        int partitionable, const float* nz, int nzs) const {
+    float nt[D];
+    if (NOISE == 2) noise_term(t, n_obs, obs_noise, partitionable, nt);
+    if (NOISE == 1) {  // table row: [b][4] floats, one 16-byte load per lane
+      const float4 v = __ldg(reinterpret_cast<const float4*>(nz));
+      const float t4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < D; i++) nt[i] = t4[i < 4 ? i : 3];
+    }
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      if (i < n_obs) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < D; j++) {  // C @ x, literally (0 * inf = NaN must survive)
+          const float term = ((i == j) ? 1.0f : 0.0f) * x[j];
+          acc = (j == 0) ? term : acc + term;
+        }
+        if (NOISE != 0) acc = acc + nt[i];
+        y[i] = acc;
+      }
+    }
+    if (ENV == MTGP_ENV_ACROBOT) {
+      const float pi = 3.14159274f, two_pi = 6.28318548f;
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+        if (i < n_obs) y[i] = mtgp_remainderf_py(y[i] + pi, two_pi) - pi;
+    }
+  }
+
+  __device__ __forceinline__ void drift(const float* s, float u_in, float* ds) const {
+    if (ENV == MTGP_ENV_ACROBOT) {  // acrobot.py:51-72
+      const float control = clip_jnp(u_in, -1.0f, 1.0f);
+      const float theta1 = s[0], theta2 = s[1], theta1_dot = s[2], theta2_dot = s[3];
+      const float l1 = p[0], m1 = p[2], m2 = p[3], lc1 = p[4], lc2 = p[5];
+      const float g = 9.81f, moi1 = 1.0f, moi2 = 1.0f, half_pi = 1.57079637f;
+      float s2, c2;
+      sincos_contract(theta2, s2, c2);
+      const float d1 = m1 * (lc1 * lc1) + m2 * (((l1 * l1) + (lc2 * lc2)) + ((2.0f * l1) * lc2) * c2) + moi1 + moi2;
+      const float d2 = m2 * ((lc2 * lc2) + (l1 * lc2) * c2) + moi2;
+      const float phi2 = ((m2 * lc2) * g) * mtgp_cosf((theta1 + theta2) - half_pi);
+      const float phi1 = ((((-m2) * l1) * lc2) * (theta2_dot * theta2_dot)) * s2 -
+                         (((((2.0f * m2) * l1) * lc2) * theta1_dot) * theta2_dot) * mtgp_sinf(theta1) +
+                         (((m1 * lc1) + (m2 * l1)) * g) * mtgp_cosf(theta1 - half_pi) + phi2;
+      const float theta2_acc =
+          (((control + (d2 / d1) * phi1) - (((m2 * l1) * lc2) * (theta1_dot * theta1_dot)) * s2) - phi2) /
+          (((m2 * (lc2 * lc2)) + moi2) - (d2 * d2) / d1);
+      const float theta1_acc = (-((d2 * theta2_acc) + phi1)) / d1;
+      ds[0] = theta1_dot; ds[1] = theta2_dot; ds[2] = theta1_acc; ds[3] = theta2_acc;
+    } else if (ENV == MTGP_ENV_HARMONIC) {  // harmonic_oscillator.py:61-63,70-71
+      const float A10 = -p[0], A11 = -p[1];
+      ds[0] = ((0.0f * s[0]) + (1.0f * s[1])) + (0.0f * u_in);
+      ds[1] = ((A10 * s[0]) + (A11 * s[1])) + (1.0f * u_in);
+    } else if (ENV == MTGP_ENV_REACTOR) {  // reactor.py:78-87
+      const float Vol = p[0], Cp = p[1], dHr = p[2], UA = p[3], q = p[4], Tf = p[5], Tcf = p[6], Volc = p[7];
+      const float Tc = s[0], T = s[1], c = s[2];
+      const float control = clip_jnp(u_in, 0.0f, 300.0f);
+      const float mEaR = (float)(-72750.0 / 8.314);
+      const float kT = 7.2e10f * mtgp_expf(mEaR / T);
+      const float dc = ((q / Vol) * (1.0f - c)) - (kT * c);
+      const float dT = (((q / Vol) * (Tf - T)) + ((((-dHr) / Cp) * kT) * c)) + (((UA / Vol) / Cp) * (Tc - T));
+      const float dTc = ((control / Volc) * (Tcf - Tc)) + (((UA / Volc) / Cp) * (T - Tc));
+      ds[0] = dTc; ds[1] = dT; ds[2] = dc;
+    }
+  }
+
+  // cond_fn_nan on the env part of the state (the latent part is OR-ed in by the caller)
+  __device__ __forceinline__ bool bad_state(const float* y) const {
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < D; i++) bad |= !mtgp_isfinitef(y[i]);
+    if (ENV == MTGP_ENV_ACROBOT) bad |= (mtgp_absf(y[2]) > 25.1327419f) | (mtgp_absf(y[3]) > 56.5486679f);
+    return bad;
+  }
+
+  // one save point of env.fitness_function; fs_known >= 0 selects the exact second pass (Acrobot)
+  __device__ __forceinline__ void cost_add(int k, float qk, const float* xs, float u, int fs_known) {
+    if (ENV == MTGP_ENV_ACROBOT) {  // acrobot.py:77-84
+      const float c = (u * 0.01f) * u;
+      if (fs_known >= 0) {
+        if (!(qk > (float)fs_known)) sum = sum + c;
+        return;
+      }
+      const bool reached = ((-mtgp_cosf(xs[0])) - mtgp_cosf(xs[0] + xs[1])) > 1.5f;
+      if (!(qk > 0.0f)) sum0 = sum0 + c;
+      if (fs < 0) {
+        if (reached) {
+          fs = k;
+          if (!(qk > (float)k)) sum = sum + c;
+        } else {
+          sum = sum + c;
+        }
+      } else if (!(qk > (float)fs)) {
+        sum = sum + c;
+      }
+    } else if (ENV == MTGP_ENV_HARMONIC) {  // harmonic_oscillator.py:76-81
+      const float v0 = xs[0] - target, v1 = xs[1] - 0.0f;
+      const float w0 = (v0 * 0.5f) + (v1 * 0.0f), w1 = (v0 * 0.0f) + (v1 * 0.0f);
+      const float quad = (w0 * v0) + (w1 * v1);
+      const float du = u - u_d;
+      sum = sum + (quad + ((du * 0.5f) * du));
+    } else if (ENV == MTGP_ENV_REACTOR) {  // reactor.py:92-96
+      const float v[3] = {xs[0] - 0.0f, xs[1] - target, xs[2] - 0.0f};
+      float w[3];
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          const float term = v[i] * ((i == j) ? (i == 1 ? 0.01f : 0.0f) : 0.0f);
+          acc = (i == 0) ? term : acc + term;
+        }
+        w[j] = acc;
+      }
+      const float quad = ((w[0] * v[0]) + (w[1] * v[1])) + (w[2] * v[2]);
+      sum = sum + (quad + ((u * 0.0001f) * u));
+    }
+  }
+
+  __device__ __forceinline__ float cost_finish(int K, int fs_known) const {
+    if (ENV == MTGP_ENV_ACROBOT) {
+      if (fs_known >= 0) return (float)(fs_known + (fs_known == 0 ? K : 0)) + sum;
+      if (fs < 0) return (float)K + sum0;
+      return (float)(fs + (fs == 0 ? K : 0)) + sum;
+    }
+    return sum;
+  }
+};
+
+
+}  // namespace mtgp_dev

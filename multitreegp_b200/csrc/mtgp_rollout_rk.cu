@@ -1,0 +1,425 @@
+// mtgp_rollout_rk.cu -- K2b: the fused rollout for the solver settings the reference's notebooks
+// actually pass: diffrax.Dopri5() with PIDController(atol, rtol, dtmin) (examples/StaticPolicy.ipynb,
+// examples/DynamicPolicy.ipynb, examples/SymbolicRegression.ipynb), and Dopri5 with a constant step.
+// (Euler + ConstantStepSize, the evaluators' class default, has its own tuned kernel in mtgp_rollout.cu.)
+//
+// Same mapping as K2 -- one warp per individual, lanes = trajectories, warp-uniform programs -- but
+// every lane now carries its OWN time grid: step sizes, accept/reject decisions, save indices and
+// the observation-noise keys (fold_in(key, bits(t)) at the stage times) are per lane.  The warp loops
+// until its slowest lane is done, exactly what the reference's vmapped while_loop does.  All solver
+// state (Y, stage increments, candidate) lives in the per-warp shared-memory value file.
+//
+// Semantics restated from diffrax (THIRD-PARTY, identical in oracle/mtgp_oracle.c: diffeqsolve):
+// ERK stepping with FSAL, b_error, PIDController.adapt_step_size with rms_norm, force_dtmin,
+// _clip_to_end, 4th-order dense output of _Dopri5Interpolation for SaveAt(ts), Event after accepted steps.
+#include "mtgp_env.cuh"
+
+using namespace mtgp_dev;
+
+namespace {
+
+__constant__ float DP_A[6][6] = {
+    {(float)(1.0 / 5), 0, 0, 0, 0, 0},
+    {(float)(3.0 / 40), (float)(9.0 / 40), 0, 0, 0, 0},
+    {(float)(44.0 / 45), (float)(-56.0 / 15), (float)(32.0 / 9), 0, 0, 0},
+    {(float)(19372.0 / 6561), (float)(-25360.0 / 2187), (float)(64448.0 / 6561), (float)(-212.0 / 729), 0, 0},
+    {(float)(9017.0 / 3168), (float)(-355.0 / 33), (float)(46732.0 / 5247), (float)(49.0 / 176), (float)(-5103.0 / 18656), 0},
+    {(float)(35.0 / 384), 0.0f, (float)(500.0 / 1113), (float)(125.0 / 192), (float)(-2187.0 / 6784), (float)(11.0 / 84)}};
+__constant__ float DP_C[6] = {(float)(1.0 / 5), (float)(3.0 / 10), (float)(4.0 / 5), (float)(8.0 / 9), 1.0f, 1.0f};
+__constant__ float DP_BERR[7] = {(float)(35.0 / 384 - 1951.0 / 21600), 0.0f, (float)(500.0 / 1113 - 22642.0 / 50085),
+                                 (float)(125.0 / 192 - 451.0 / 720), (float)(-2187.0 / 6784 - -12231.0 / 42400),
+                                 (float)(11.0 / 84 - 649.0 / 6300), (float)(-1.0 / 60)};
+__constant__ float DP_CMID[7] = {(float)(6025192743.0 / 30085553152.0 / 2), 0.0f,
+                                 (float)(51252292925.0 / 65400821598.0 / 2), (float)(-2691868925.0 / 45128329728.0 / 2),
+                                 (float)(187940372067.0 / 1594534317056.0 / 2), (float)(-1776094331.0 / 19743644256.0 / 2),
+                                 (float)(11237099.0 / 235043384.0 / 2)};
+
+constexpr int kRkWarps = 4;
+constexpr int kRkArrays = 12;  // Y, Y1, YI, F0, KS[0..6], SV
+
+template <int KIND, int ENV, bool NOISE>
+__global__ void __launch_bounds__(kRkWarps * 32) k_rollout_rk(const RolloutParams P) {
+  constexpr int D = (KIND == MTGP_EVAL_SR) ? 0 : EnvDim<ENV>::D;
+  constexpr int DR = D > 0 ? D : 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  const int ind = blockIdx.x * kRkWarps + wic;
+  const size_t per_warp = (size_t)P.prog_words_per_warp * sizeof(uint2) + kMaxTrees * sizeof(int) +
+                          (size_t)P.wide_cap * sizeof(mtgp_wide_instr) + (size_t)P.slots_per_warp * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  unsigned char* wbase = smem_raw + 16 * kRkWarps + (size_t)wic * per_warp;
+  uint2* prog_s = reinterpret_cast<uint2*>(wbase);
+  int* woff = reinterpret_cast<int*>(wbase + (size_t)P.prog_words_per_warp * sizeof(uint2));
+  mtgp_wide_instr* wide = reinterpret_cast<mtgp_wide_instr*>(woff + kMaxTrees);
+  float* vf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(wide) +
+                                       (size_t)P.wide_cap * sizeof(mtgp_wide_instr));
+  if (ind >= P.P) return;
+
+  // ---- stage + pre-decode the programs (same as K2) ----
+  uint64_t* bar = bars + 2 * wic;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    uint32_t total = 0;
+    for (int t = 0; t < P.T; t++) total += (((P.meta[(size_t)ind * P.T + t] & 0xFFFFu) + 2u) & ~1u) * 8u;
+    mbar_expect_tx(bar, total);
+    int off = 0;
+    for (int t = 0; t < P.T; t++) {
+      const uint32_t n = P.meta[(size_t)ind * P.T + t] & 0xFFFFu;
+      bulk_g2s(prog_s + (size_t)t * P.lstride, P.prog + ((size_t)ind * P.T + t) * P.lstride, ((n + 2u) & ~1u) * 8u, bar);
+      woff[t] = off;
+      off += (int)n + 1;
+    }
+  }
+  __syncwarp();
+  float* lb = vf + lane;
+  const mtgp_saddr lbytes = mtgp_saddr_of(lb);
+  for (int s = 0; s < P.slots_per_warp; s++) lb[s * 32] = 0.0f;
+  mbar_wait(bar, 0);
+  {
+    const uint32_t scratch = (uint32_t)P.slots_per_warp - 1u;
+    for (int t = 0; t < P.T; t++) {
+      const int n = (int)(P.meta[(size_t)ind * P.T + t] & 0xFFFFu) + 1;
+      mtgp_wide_instr* dst = wide + woff[t];
+      for (int i = lane; i < n; i += 32) dst[i] = mtgp_expand_instr(prog_s[(size_t)t * P.lstride + i], scratch);
+    }
+  }
+  __syncwarp();
+
+  const float* ts = P.ts;
+  const int K = P.K, NL = P.n_latent, DT = D + NL;
+  const float t0 = ts[0], t1 = ts[K - 1];
+  const float dts = (K > 1) ? ts[1] - ts[0] : 0.0f;
+  const bool dopri = P.solver == MTGP_SOLVER_DOPRI5, pid = P.controller == MTGP_CONTROLLER_PID;
+  const mtgp_saddr wide_s = mtgp_saddr_of(wide);
+  const mtgp_saddr prog_readout = wide_s + 32u * (uint32_t)woff[(KIND == MTGP_EVAL_DYNAMIC) ? P.state_size : 0];
+  // solver arrays in the value file: component i of array a is slot slot_rk + a*DT + i
+  float* const Y = lb + (size_t)(P.slot_rk + 0 * DT) * 32;
+  float* const Y1 = lb + (size_t)(P.slot_rk + 1 * DT) * 32;
+  float* const YI = lb + (size_t)(P.slot_rk + 2 * DT) * 32;
+  float* const F0 = lb + (size_t)(P.slot_rk + 3 * DT) * 32;
+  float* const KS = lb + (size_t)(P.slot_rk + 4 * DT) * 32;  // KS[st][i] at (st*DT + i)*32
+  float* const SV = lb + (size_t)(P.slot_rk + 11 * DT) * 32; // state at a save point
+  float fit_sum = 0.0f;
+  unsigned int my_steps = 0;
+
+  for (int b0 = 0; b0 < P.B; b0 += 32) {
+    const int b = b0 + lane;
+    const bool lane_valid = b < P.B;
+    const int bb = lane_valid ? b : P.B - 1;
+    Env<ENV> env;
+    if (KIND != MTGP_EVAL_SR) env.init(P, bb);
+    if (KIND != MTGP_EVAL_SR)
+      for (int i = 0; i < P.n_targets; i++) lb[(P.slot_target + i) * 32] = P.targets[bb * P.n_targets + i];
+
+    // vector field of the evaluator at (t, src): writes dst[i] = scale * f_i  (i < DT)
+    auto vector_field = [&](float t, const float* src, float* dst, float scale, float* raw) {
+      float x[DR], y[DR], dx[DR];
+      for (int j = 0; j < NL; j++) lb[(P.slot_lat + j) * 32] = src[(D + j) * 32];
+      if (KIND != MTGP_EVAL_SR) {
+#pragma unroll
+        for (int i = 0; i < D; i++) x[i] = src[i * 32];
+        env.template f_obs<NOISE ? 2 : 0>(t, x, y, P.n_obs, P.obs_noise, P.partitionable, nullptr, 0);
+        if (KIND == MTGP_EVAL_STATIC) {
+#pragma unroll
+          for (int i = 0; i < D; i++)
+            if (i < P.n_obs) lb[i * 32] = y[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < D; i++)
+            if (i < P.n_obs) lb[i * 32] = 0.0f;
+          lb[P.slot_u * 32] = 0.0f;
+        }
+        const float u = mtgp_interpret_wide(prog_readout, lbytes);
+        env.drift(x, u, dx);
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+          dst[i * 32] = scale * dx[i];
+          if (raw) raw[i * 32] = dx[i];
+        }
+        if (KIND == MTGP_EVAL_DYNAMIC) {
+#pragma unroll
+          for (int i = 0; i < D; i++)
+            if (i < P.n_obs) lb[i * 32] = y[i];
+          lb[P.slot_u * 32] = u;
+        }
+      }
+      for (int j = 0; j < NL; j++) {
+        const float f = mtgp_interpret_wide(wide_s + 32u * (uint32_t)woff[j], lbytes);
+        dst[(D + j) * 32] = scale * f;
+        if (raw) raw[(D + j) * 32] = f;
+      }
+    };
+    auto bad_state = [&](const float* src) {
+      bool bad = false;
+      if (KIND != MTGP_EVAL_SR) {
+        float x[DR];
+#pragma unroll
+        for (int i = 0; i < D; i++) x[i] = src[i * 32];
+        bad = env.bad_state(x);
+      }
+      for (int j = 0; j < NL; j++) bad |= !mtgp_isfinitef(src[(D + j) * 32]);
+      return bad;
+    };
+
+    int fs_known = -1;
+    bool viol = false;
+    float traj_fitness = 0.0f;
+    for (int pass = 0; pass < 2; pass++) {
+      if (KIND != MTGP_EVAL_SR) {
+#pragma unroll
+        for (int i = 0; i < D; i++) Y[i * 32] = P.x0[bb * D + i];
+      }
+      for (int j = 0; j < NL; j++) Y[(D + j) * 32] = (KIND == MTGP_EVAL_SR) ? P.x0[bb * NL + j] : 0.0f;
+      if (KIND != MTGP_EVAL_SR) { env.sum = 0.0f; env.sum0 = 0.0f; env.fs = -1; }
+      float sr_total = 0.0f;
+      bool ev_old_bad = bad_state(Y);
+      bool active = true, fsal_valid = false, at_dtmin = false;
+      float tprev = t0, tnext = t0 + P.dt0;
+      tnext = tnext < t1 ? tnext : t1;
+      float prev_inv = 1.0f, prev_prev_inv = 1.0f;
+      int num_steps = 0, k = 0;
+
+      // one save point of the post-pass for the lanes with `doit`; xs/lat hold the saved state
+      auto save_point = [&](bool doit, const float* sv /* DT components at sv[i*32] */) {
+        const int kk = k < K ? k : K - 1;
+        const float tk = ts[kk];
+        if (KIND == MTGP_EVAL_SR) {
+          float row = 0.0f;
+          for (int j = 0; j < NL; j++) {
+            const float lat = sv[j * 32];
+            const float e = lat - P.ys_true[((size_t)bb * K + kk) * NL + j];
+            row = row + e * e;
+            if (doit && P.xs_o && lane_valid && pass == 0) P.xs_o[(((size_t)ind * P.B + b) * K + kk) * NL + j] = lat;
+          }
+          if (doit) sr_total = sr_total + row;
+        } else {
+          float xs[DR], ys[DR];
+#pragma unroll
+          for (int i = 0; i < D; i++) xs[i] = sv[i * 32];
+          for (int j = 0; j < NL; j++) {
+            const float lat = sv[(D + j) * 32];
+            lb[(P.slot_lat + j) * 32] = lat;
+            if (doit && P.act_o && lane_valid && pass == 0) P.act_o[(((size_t)ind * P.B + b) * K + kk) * NL + j] = lat;
+          }
+          env.template f_obs<NOISE ? 2 : 0>(tk, xs, ys, P.n_obs, P.obs_noise, P.partitionable, nullptr, 0);
+#pragma unroll
+          for (int i = 0; i < D; i++)
+            if (i < P.n_obs) lb[i * 32] = ys[i];
+          if (KIND == MTGP_EVAL_DYNAMIC) lb[P.slot_u * 32] = 0.0f;
+          const float uk = mtgp_interpret_wide(prog_readout, lbytes);
+          const float qk = (ENV == MTGP_ENV_ACROBOT) ? tk / dts : 0.0f;
+          if (doit) {
+            if (ENV == MTGP_ENV_ACROBOT && qk > (float)(kk + 1)) viol = true;
+            env.cost_add(kk, qk, xs, uk, fs_known);
+            if (lane_valid && pass == 0 && (P.xs_o || P.ys_o || P.us_o)) {
+              const size_t o = ((size_t)ind * P.B + b) * K + kk;
+              if (P.xs_o)
+#pragma unroll
+                for (int i = 0; i < D; i++) P.xs_o[o * D + i] = xs[i];
+              if (P.ys_o)
+#pragma unroll
+                for (int i = 0; i < D; i++)
+                  if (i < P.n_obs) P.ys_o[o * P.n_obs + i] = ys[i];
+              if (P.us_o) P.us_o[o] = uk;
+            }
+          }
+        }
+      };
+
+      while (__ballot_sync(0xFFFFFFFFu, active && lane_valid) != 0u) {
+        const float dt = tnext - tprev;
+        // ---- stages ----
+        if (!dopri) {
+          vector_field(tprev, Y, KS, dt, nullptr);
+          for (int i = 0; i < DT; i++) Y1[i * 32] = Y[i * 32] + KS[i * 32];
+        } else {
+          if (__ballot_sync(0xFFFFFFFFu, !fsal_valid) != 0u) {
+            // first step of the solve (warp-uniform): F0 = f(t0, y0).  Later steps reuse the last
+            // stage of the previous accepted step (FSAL) or, after a rejection, the same F0.
+            vector_field(tprev, Y, F0, 1.0f, nullptr);
+            fsal_valid = true;
+          }
+          for (int i = 0; i < DT; i++) KS[i * 32] = dt * F0[i * 32];
+          for (int st = 1; st < 7; st++) {
+            for (int i = 0; i < DT; i++) {
+              float acc = 0.0f;
+              for (int j = 0; j < st; j++) {
+                const float term = DP_A[st - 1][j] * KS[(j * DT + i) * 32];
+                acc = (j == 0) ? term : acc + term;
+              }
+              YI[i * 32] = Y[i * 32] + acc;
+            }
+            if (st == 6)
+              for (int i = 0; i < DT; i++) Y1[i * 32] = YI[i * 32];
+            const float cst = DP_C[st - 1];
+            const float tst = (cst == 1.0f) ? tnext : tprev + cst * dt;
+            // the unscaled last stage (the next step's F0 under FSAL) overwrites YI, which is dead by then
+            vector_field(tst, YI, KS + (size_t)st * DT * 32, dt, st == 6 ? YI : nullptr);
+          }
+        }
+        // ---- step-size controller ----
+        bool keep = true;
+        float new_tprev, new_tnext;
+        bool nan_err = false;
+        if (!pid) {
+          new_tprev = tnext;
+          new_tnext = tnext + P.dt0;
+        } else {
+          float sumsq = 0.0f;
+          for (int i = 0; i < DT; i++) {
+            float yerr = 0.0f;
+            for (int j = 0; j < 7; j++) {
+              const float term = DP_BERR[j] * KS[(j * DT + i) * 32];
+              yerr = (j == 0) ? term : yerr + term;
+            }
+            const float ym = mtgp_maximumf(mtgp_absf(Y[i * 32]), mtgp_absf(Y1[i * 32]));
+            const float sc = yerr / (P.atol + ym * P.rtol);
+            sumsq = sumsq + sc * sc;
+          }
+          const float scaled_error = mtgp_sqrtf(sumsq / (float)DT);
+          keep = (scaled_error < 1.0f) || at_dtmin;
+          const float inv_err = (scaled_error == 0.0f) ? mtgp_inff() : 1.0f / scaled_error;
+          const float factor1 = (P.coeff1 == 0.0f) ? 1.0f : mtgp_expf(P.coeff1 * mtgp_logf(inv_err));
+          const float factor2 = (P.coeff2 == 0.0f) ? 1.0f : mtgp_expf(P.coeff2 * mtgp_logf(prev_inv));
+          const float factor3 = (P.coeff3 == 0.0f) ? 1.0f : mtgp_expf(P.coeff3 * mtgp_logf(prev_prev_inv));
+          const float fmin = keep ? 1.0f : P.factormin;
+          float factor = ((P.safety * factor1) * factor2) * factor3;
+          factor = clip_jnp(factor, fmin, P.factormax);
+          float ndt = dt * factor;
+          if (P.dtmin > 0.0f) {
+            at_dtmin = (ndt <= P.dtmin);
+            ndt = (ndt != ndt) ? ndt : (ndt > P.dtmin ? ndt : P.dtmin);
+          }
+          new_tprev = keep ? tnext : tprev;
+          new_tnext = new_tprev + ndt;
+          if (keep && active) { prev_prev_inv = prev_inv; prev_inv = inv_err; }
+          nan_err = (scaled_error != scaled_error);
+        }
+        new_tprev = new_tprev < t1 ? new_tprev : t1;
+        {
+          const bool clip = new_tnext > t1 - 1e-6f;
+          const float tclip = keep ? t1 : new_tprev + 0.5f * (t1 - new_tprev);
+          new_tnext = clip ? tclip : new_tnext;
+        }
+        const bool commit = active && keep && !nan_err;
+        // ---- SaveAt(ts) on accepted steps: every lane has its own pending save points ----
+        while (true) {
+          const bool pending = commit && (k < K) && (ts[k < K ? k : K - 1] <= tnext);
+          if (__ballot_sync(0xFFFFFFFFu, pending) == 0u) break;
+          const float tk = ts[k < K ? k : K - 1];
+          const float th = (tprev == tnext) ? 0.0f : (tk - tprev) / (tnext - tprev);
+          for (int i = 0; i < DT; i++) {
+            const float y0 = Y[i * 32], y1 = Y1[i * 32];
+            float v;
+            if (!dopri) {
+              v = y0 + th * (y1 - y0);
+            } else {
+              float acc = 0.0f;
+              for (int j = 0; j < 7; j++) {
+                const float term = DP_CMID[j] * KS[(j * DT + i) * 32];
+                acc = (j == 0) ? term : acc + term;
+              }
+              const float ymid = y0 + acc;
+              const float f0 = KS[i * 32], f1 = KS[(6 * DT + i) * 32];
+              const float a = ((2.0f * (f1 - f0)) - (8.0f * (y1 + y0))) + (16.0f * ymid);
+              const float bq = ((((5.0f * f0) - (3.0f * f1)) + (18.0f * y0)) + (14.0f * y1)) - (32.0f * ymid);
+              const float cq = ((((f1 - (4.0f * f0)) - (11.0f * y0)) - (5.0f * y1))) + (16.0f * ymid);
+              v = ((((a * th + bq) * th + cq) * th + f0) * th) + y0;
+            }
+            SV[i * 32] = v;
+          }
+          save_point(pending, SV);
+          if (pending) k++;
+        }
+        // ---- Event + commit ----
+        const bool bad = bad_state(Y1);
+        const bool fired = (bad != ev_old_bad);
+        if (commit) {
+          ev_old_bad = bad;
+          my_steps += (pass == 0 && lane_valid) ? 1u : 0u;
+          for (int i = 0; i < DT; i++) {
+            Y[i * 32] = Y1[i * 32];
+            if (dopri) F0[i * 32] = YI[i * 32];  // unscaled f at (tnext, y1)
+          }
+        }
+        if (active) {
+          num_steps++;
+          tprev = new_tprev;
+          tnext = new_tnext;
+          if ((commit && fired) || nan_err || !(tprev < t1) || num_steps >= P.max_steps) active = false;
+        }
+      }
+      // ---- save points the solve never reached keep the inf pre-fill ----
+      while (__ballot_sync(0xFFFFFFFFu, k < K) != 0u) {
+        const bool pending = k < K;
+        for (int i = 0; i < DT; i++) SV[i * 32] = mtgp_inff();
+        save_point(pending, SV);
+        if (pending) k++;
+      }
+      traj_fitness = (KIND == MTGP_EVAL_SR) ? sr_total / (float)K : env.cost_finish(K, fs_known);
+      if (ENV != MTGP_ENV_ACROBOT || pass == 1) break;
+      if (__ballot_sync(0xFFFFFFFFu, viol) == 0u) break;
+      fs_known = env.fs < 0 ? 0 : env.fs;
+    }
+    if (lane_valid) {
+      if (P.tf_o) P.tf_o[(size_t)ind * P.B + b] = traj_fitness;
+      fit_sum = fit_sum + (mtgp_isfinitef(traj_fitness) ? traj_fitness : P.max_fitness);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) fit_sum = fit_sum + __shfl_xor_sync(0xFFFFFFFFu, fit_sum, o);
+  unsigned long long warp_steps = my_steps;
+  for (int o = 16; o > 0; o >>= 1) warp_steps += __shfl_xor_sync(0xFFFFFFFFu, warp_steps, o);
+  if (lane == 0) {
+    float f = clip_jnp(fit_sum / (float)P.B, 0.0f, P.max_fitness);
+    if (P.live) {
+      int cnt = 0;
+      for (int t = 0; t < P.T; t++) cnt += P.live[(size_t)ind * P.T + t];
+      f = f + P.size_parsimony * (float)cnt;
+    }
+    P.fitness[ind] = f;
+    if (P.steps_done) atomicAdd(P.steps_done, warp_steps);
+  }
+}
+
+template <int KIND, int ENV>
+int launch_rk(RolloutParams rp, cudaStream_t stream) {
+  const size_t per_warp = (size_t)rp.prog_words_per_warp * sizeof(uint2) + kMaxTrees * sizeof(int) +
+                          (size_t)rp.wide_cap * sizeof(mtgp_wide_instr) + (size_t)rp.slots_per_warp * 128;
+  const size_t smem = 16 * kRkWarps + (size_t)kRkWarps * per_warp;
+  if (smem > 227 * 1024) {
+    mtgp_set_error("adaptive rollout needs %zu bytes of shared memory per CTA: over the 227 KB limit", smem);
+    return MTGP_ERR_UNSUPPORTED;
+  }
+  const unsigned blocks = (unsigned)((rp.P + kRkWarps - 1) / kRkWarps);
+  if (rp.obs_noise != 0.0f && KIND != MTGP_EVAL_SR) {
+    auto kern = k_rollout_rk<KIND, ENV, true>;
+    MTGP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, kRkWarps * 32, smem, stream>>>(rp);
+  } else {
+    auto kern = k_rollout_rk<KIND, ENV, false>;
+    MTGP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, kRkWarps * 32, smem, stream>>>(rp);
+  }
+  return mtgp_check_launch("k_rollout_rk");
+}
+
+}  // namespace
+
+int mtgp_launch_rollout_rk(RolloutParams rp, int kind, int env_id, cudaStream_t stream) {
+#define DISPATCH(KIND, ENV) return launch_rk<KIND, ENV>(rp, stream)
+  if (kind == MTGP_EVAL_SR) DISPATCH(MTGP_EVAL_SR, MTGP_ENV_NONE);
+  if (kind == MTGP_EVAL_STATIC) {
+    if (env_id == MTGP_ENV_ACROBOT) DISPATCH(MTGP_EVAL_STATIC, MTGP_ENV_ACROBOT);
+    if (env_id == MTGP_ENV_HARMONIC) DISPATCH(MTGP_EVAL_STATIC, MTGP_ENV_HARMONIC);
+    if (env_id == MTGP_ENV_REACTOR) DISPATCH(MTGP_EVAL_STATIC, MTGP_ENV_REACTOR);
+  }
+  if (kind == MTGP_EVAL_DYNAMIC) {
+    if (env_id == MTGP_ENV_ACROBOT) DISPATCH(MTGP_EVAL_DYNAMIC, MTGP_ENV_ACROBOT);
+    if (env_id == MTGP_ENV_HARMONIC) DISPATCH(MTGP_EVAL_DYNAMIC, MTGP_ENV_HARMONIC);
+    if (env_id == MTGP_ENV_REACTOR) DISPATCH(MTGP_EVAL_DYNAMIC, MTGP_ENV_REACTOR);
+  }
+#undef DISPATCH
+  mtgp_set_error("unknown evaluator kind %d / environment %d", kind, env_id);
+  return MTGP_ERR_INVALID_ARGUMENT;
+}

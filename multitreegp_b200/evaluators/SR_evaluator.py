@@ -18,7 +18,7 @@ class Evaluator(EvaluatorBase):
 
     def __init__(self, solver=None, dt0: float = 0.01, max_steps: int = 16 ** 4, stepsize_controller=None,
                  **bind_kwargs) -> None:
-        _check_solver(solver, stepsize_controller)
+        self._solver_settings = _check_solver(solver, stepsize_controller)
         super().__init__(**bind_kwargs)
         self.max_fitness = 1e5
         self.dt0 = dt0
@@ -29,7 +29,8 @@ class Evaluator(EvaluatorBase):
     def rollout_data(self, data) -> RolloutData:
         x0, ts, ys, _noise_keys = data  # (x0 [B,D], ts [K], ys [B,K,D], process_noise_keys) SR_evaluator.py:55
         return RolloutData(kind=self.kind, env_id=abi.ENV_NONE, x0=_np(x0), ts=_np(ts), dt0=self.dt0,
-                           max_fitness=self.max_fitness, ys_true=_np(ys), max_steps=self.max_steps)
+                           max_fitness=self.max_fitness, ys_true=_np(ys), max_steps=self.max_steps,
+                           **self._solver_settings)
 
     def evaluate_candidate(self, candidate, data, tree_evaluator=None):
         """Returns (fitness [B], pred_ys [B,K,D]) like SR_evaluator.py:47-55."""

@@ -30,17 +30,12 @@ def _np(a, dtype=None):
     return a.astype(dtype) if dtype is not None and a.dtype != dtype else a
 
 
-def _check_solver(solver, stepsize_controller) -> None:
-    """Only the evaluators' class defaults (diffrax.Euler + ConstantStepSize) are implemented on
-    the GPU; adaptive Dopri5/PIDController is the next item of SURVEY.md section 8f."""
-    for obj, ok in ((solver, ("euler",)), (stepsize_controller, ("constantstepsize", "constant"))):
-        if obj is None:
-            continue
-        name = obj if isinstance(obj, str) else type(obj).__name__
-        if name.lower() not in ok:
-            raise NotImplementedError(
-                f"{name}: the sm_100a rollout kernel implements the fixed-step Euler / ConstantStepSize "
-                "defaults of the reference evaluators; adaptive solvers are not available (no CPU fallback)")
+def _check_solver(solver, stepsize_controller) -> dict:
+    """Validates the solver / step-size controller (diffrax objects, multitreegp_b200.solvers stand-ins or
+    names) and returns the matching RolloutData settings.  Euler + ConstantStepSize are the reference
+    evaluators' class defaults; Dopri5 + PIDController is what the shipped notebooks pass."""
+    from ..solvers import solver_settings
+    return solver_settings(solver, stepsize_controller)
 
 
 class EvaluatorBase:

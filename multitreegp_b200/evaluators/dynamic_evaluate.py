@@ -17,7 +17,7 @@ class Evaluator(EvaluatorBase):
 
     def __init__(self, env, state_size: int, dt0: float, solver=None, max_steps: int = 16 ** 4,
                  stepsize_controller=None, **bind_kwargs) -> None:
-        _check_solver(solver, stepsize_controller)
+        self._solver_settings = _check_solver(solver, stepsize_controller)
         super().__init__(**bind_kwargs)
         self.env = env
         self.max_fitness = 1e4

@@ -24,7 +24,8 @@ def control_rollout_data(self, data, state_size: int) -> RolloutData:
     return RolloutData(kind=self.kind, env_id=env.env_id, x0=_np(x0), ts=_np(ts), dt0=self.dt0,
                        max_fitness=self.max_fitness, targets=_np(targets), obs_keys=keys, params=params,
                        n_obs=env.n_obs, state_size=state_size, max_steps=self.max_steps,
-                       obs_noise=float(env.obs_noise), threefry_partitionable=self.threefry_partitionable)
+                       obs_noise=float(env.obs_noise), threefry_partitionable=self.threefry_partitionable,
+                       **self._solver_settings)
 
 
 class Evaluator(EvaluatorBase):
@@ -32,7 +33,7 @@ class Evaluator(EvaluatorBase):
 
     def __init__(self, env, dt0: float, solver=None, max_steps: int = 16 ** 4, stepsize_controller=None,
                  **bind_kwargs) -> None:
-        _check_solver(solver, stepsize_controller)
+        self._solver_settings = _check_solver(solver, stepsize_controller)
         super().__init__(**bind_kwargs)
         self.env = env
         self.max_fitness = 1e4

@@ -33,6 +33,13 @@ class RolloutData:
     max_steps: int = 16 ** 4
     obs_noise: float = 0.0
     threefry_partitionable: bool = True
+    solver: int = abi.SOLVER_EULER
+    controller: int = abi.CONTROLLER_CONSTANT
+    rtol: float = 1e-3          # diffrax.PIDController(rtol, atol, dtmin=None, pcoeff=0, icoeff=1, dcoeff=0, ...)
+    atol: float = 1e-6
+    dtmin: float = 0.0
+    pid: tuple = (0.0, 1.0, 0.0)            # pcoeff, icoeff, dcoeff
+    pid_limits: tuple = (0.9, 0.2, 10.0)    # safety, factormin, factormax
     _keep: list = field(default_factory=list, repr=False)
 
     def __post_init__(self) -> None:
@@ -79,6 +86,10 @@ class RolloutData:
         d.max_fitness = float(self.max_fitness)
         d.obs_noise = float(self.obs_noise)
         d.threefry_partitionable = int(bool(self.threefry_partitionable))
+        d.solver, d.controller = int(self.solver), int(self.controller)
+        d.rtol, d.atol, d.dtmin = float(self.rtol), float(self.atol), float(self.dtmin)
+        d.pcoeff, d.icoeff, d.dcoeff = (float(v) for v in self.pid)
+        d.pid_safety, d.pid_factormin, d.pid_factormax = (float(v) for v in self.pid_limits)
         d.x0 = ptr(self.x0)
         d.ts = ptr(self.ts)
         d.targets = ptr(self.targets if self.targets.size else None)

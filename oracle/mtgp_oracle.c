@@ -44,6 +44,8 @@ static inline float m_cos(float x) { return g_math_mode ? cosf(x) : mtgp_cosf(x)
 static inline float m_exp(float x) { return g_math_mode ? expf(x) : mtgp_expf(x); }
 static inline float m_log(float x) { return g_math_mode ? logf(x) : mtgp_logf(x); }
 static inline float m_tanh(float x) { return g_math_mode ? tanhf(x) : mtgp_tanhf(x); }
+/* x ** c for the PID step-size factor: exp(c * log(x)) in contract mode, libm powf otherwise */
+static inline float m_pow(float x, float c) { return g_math_mode ? powf(x, c) : mtgp_expf(c * mtgp_logf(x)); }
 static inline float m_log1p(float x) { return g_math_mode ? log1pf(x) : mtgp_log1pf(x); }
 static inline float m_remainder_py(float x, float y) {
   if (!g_math_mode) return mtgp_remainderf_py(x, y);
@@ -504,42 +506,166 @@ ORACLE_API int oracle_schedule(const float* ts, int K, float dt0, int max_steps,
   return n;
 }
 
-/* Solves one trajectory; ys_out [K, Dtot] pre-filled with inf.  Returns the number of steps. */
-static int diffeqsolve_euler(rollout_ctx* c, const float* y0, int Dtot, float* ys_out) {
+/* Dormand-Prince 5(4) tableau (diffrax/_solver/dopri5.py, THIRD-PARTY): a_lower, b_sol (= last row,
+   FSAL), b_error = b_sol - b_hat, c, and the mid-point weights of its 4th-order dense output. */
+static const float DP_A[6][6] = {
+    {(float)(1.0 / 5), 0, 0, 0, 0, 0},
+    {(float)(3.0 / 40), (float)(9.0 / 40), 0, 0, 0, 0},
+    {(float)(44.0 / 45), (float)(-56.0 / 15), (float)(32.0 / 9), 0, 0, 0},
+    {(float)(19372.0 / 6561), (float)(-25360.0 / 2187), (float)(64448.0 / 6561), (float)(-212.0 / 729), 0, 0},
+    {(float)(9017.0 / 3168), (float)(-355.0 / 33), (float)(46732.0 / 5247), (float)(49.0 / 176), (float)(-5103.0 / 18656), 0},
+    {(float)(35.0 / 384), 0.0f, (float)(500.0 / 1113), (float)(125.0 / 192), (float)(-2187.0 / 6784), (float)(11.0 / 84)}};
+static const float DP_C[6] = {(float)(1.0 / 5), (float)(3.0 / 10), (float)(4.0 / 5), (float)(8.0 / 9), 1.0f, 1.0f};
+static const float DP_BERR[7] = {(float)(35.0 / 384 - 1951.0 / 21600), 0.0f, (float)(500.0 / 1113 - 22642.0 / 50085),
+                                 (float)(125.0 / 192 - 451.0 / 720), (float)(-2187.0 / 6784 - -12231.0 / 42400),
+                                 (float)(11.0 / 84 - 649.0 / 6300), (float)(-1.0 / 60)};
+static const float DP_CMID[7] = {(float)(6025192743.0 / 30085553152.0 / 2), 0.0f,
+                                 (float)(51252292925.0 / 65400821598.0 / 2), (float)(-2691868925.0 / 45128329728.0 / 2),
+                                 (float)(187940372067.0 / 1594534317056.0 / 2), (float)(-1776094331.0 / 19743644256.0 / 2),
+                                 (float)(11237099.0 / 235043384.0 / 2)};
+
+/* Solves one trajectory with diffrax.diffeqsolve semantics; ys_out [K, Dtot] pre-filled with inf.
+   solver: Euler or Dopri5; controller: ConstantStepSize or PIDController.  Returns the number of
+   ACCEPTED steps (rejected steps count towards max_steps like diffrax's num_steps). */
+static int diffeqsolve(rollout_ctx* c, const float* y0, int Dtot, float* ys_out) {
   const mtgp_rollout_desc* d = c->d;
   const float* ts = d->ts;
-  int K = d->K;
+  const int K = d->K;
+  const int dopri = d->solver == MTGP_SOLVER_DOPRI5, pid = d->controller == MTGP_CONTROLLER_PID;
+  const float safety = d->pid_safety > 0.0f ? d->pid_safety : 0.9f;
+  const float factormin = d->pid_factormin > 0.0f ? d->pid_factormin : 0.2f;
+  const float factormax = d->pid_factormax > 0.0f ? d->pid_factormax : 10.0f;
+  const int default_pid = (d->pcoeff == 0.0f && d->icoeff == 0.0f && d->dcoeff == 0.0f);
+  const float pc = default_pid ? 0.0f : d->pcoeff, ic = default_pid ? 1.0f : d->icoeff, dc = default_pid ? 0.0f : d->dcoeff;
+  const float error_order = 5.0f; /* Dopri5.order */
+  const float coeff1 = (ic + pc + dc) / error_order, coeff2 = -(pc + 2.0f * dc) / error_order, coeff3 = dc / error_order;
   float t0 = ts[0], t1 = ts[K - 1];
-  float y[2 * MAXD], y1[2 * MAXD], f[2 * MAXD];
+  float y[2 * MAXD], y1[2 * MAXD], yi[2 * MAXD], yerr[2 * MAXD], ymid[2 * MAXD];
+  float f[7][2 * MAXD], ks[7][2 * MAXD];
   for (int i = 0; i < Dtot; i++) y[i] = y0[i];
   for (int i = 0; i < K * Dtot; i++) ys_out[i] = INFINITY;
   float tprev = t0;
-  float tnext = t0 + d->dt0; /* ConstantStepSize.init */
+  float tnext = t0 + d->dt0; /* controller.init: t0 + dt0 */
   tnext = tnext < t1 ? tnext : t1;
   float event_old = env_cond(d->env_id, y, Dtot); /* Event: cond_fn evaluated at (t0, y0) */
-  int save_idx = 0, steps = 0;
-  while (tprev < t1 && steps < d->max_steps) {
-    vector_field(c, tprev, y, f);                                     /* Euler: f(t0, y0) */
-    float dt = tnext - tprev;                                         /* terms.contr(t0, t1) */
-    for (int i = 0; i < Dtot; i++) y1[i] = y[i] + dt * f[i];           /* y0 + vf_prod */
-    float new_tprev = tnext < t1 ? tnext : t1;                         /* adapt_step_size: (True, t1, t1+dt) */
-    float new_tnext = clip_to_end(new_tprev, tnext + d->dt0, t1);
-    while (save_idx < K && ts[save_idx] <= tnext) {                    /* SaveAt(ts): dense output */
-      float tk = ts[save_idx];
-      float coeff = (tprev == tnext) ? 0.0f : (tk - tprev) / (tnext - tprev); /* linear_rescale */
-      for (int i = 0; i < Dtot; i++) ys_out[save_idx * Dtot + i] = y[i] + coeff * (y1[i] - y[i]);
-      save_idx++;
+  int save_idx = 0, num_steps = 0, accepted = 0, fsal_valid = 0, at_dtmin = 0;
+  float prev_inv_err = 1.0f, prev_prev_inv_err = 1.0f;
+  while (tprev < t1 && num_steps < d->max_steps) {
+    const float dt = tnext - tprev; /* terms.contr(t0, t1) */
+    int keep = 1;
+    float new_tprev, new_tnext;
+    if (!dopri) {
+      vector_field(c, tprev, y, f[0]);                                  /* Euler: f(t0, y0) */
+      for (int i = 0; i < Dtot; i++) { ks[0][i] = dt * f[0][i]; y1[i] = y[i] + ks[0][i]; }
+    } else {
+      if (!fsal_valid) vector_field(c, tprev, y, f[0]);                  /* FSAL: k1 = last stage of the previous accepted step */
+      for (int i = 0; i < Dtot; i++) ks[0][i] = dt * f[0][i];
+      for (int st = 1; st < 7; st++) {
+        for (int i = 0; i < Dtot; i++) {
+          float acc = 0.0f;
+          for (int j = 0; j < st; j++) {
+            float term = DP_A[st - 1][j] * ks[j][i];
+            acc = (j == 0) ? term : acc + term;
+          }
+          yi[i] = y[i] + acc;
+        }
+        if (st == 6) for (int i = 0; i < Dtot; i++) y1[i] = yi[i];       /* b_sol = a_lower[-1] */
+        const float tst = (DP_C[st - 1] == 1.0f) ? tnext : tprev + DP_C[st - 1] * dt;
+        vector_field(c, tst, yi, f[st]);
+        for (int i = 0; i < Dtot; i++) ks[st][i] = dt * f[st][i];
+      }
+      for (int i = 0; i < Dtot; i++) {
+        float acc = 0.0f;
+        for (int j = 0; j < 7; j++) {
+          float term = DP_BERR[j] * ks[j][i];
+          acc = (j == 0) ? term : acc + term;
+        }
+        yerr[i] = acc;
+      }
     }
-    float event_new = env_cond(d->env_id, y1, Dtot);                   /* cond_fn(tnext, y1) */
-    int fired = (event_old > 0.0f) != (event_new > 0.0f);              /* sign change (values are +-1) */
-    event_old = event_new;
-    for (int i = 0; i < Dtot; i++) y[i] = y1[i];
-    tprev = new_tprev;
-    tnext = new_tnext;
-    steps++;
-    if (fired) break;
+    if (!pid) { /* ConstantStepSize.adapt_step_size: (True, t1, t1 + dt0) */
+      new_tprev = tnext;
+      new_tnext = tnext + d->dt0;
+    } else {    /* PIDController.adapt_step_size */
+      float sumsq = 0.0f;
+      for (int i = 0; i < Dtot; i++) {
+        float ay0 = fabsf(y[i]), ay1 = fabsf(y1[i]);
+        float ym = (ay0 != ay0 || ay1 != ay1) ? NAN : (ay0 > ay1 ? ay0 : ay1);   /* jnp.maximum */
+        float sc = yerr[i] / (d->atol + ym * d->rtol);
+        sumsq = sumsq + sc * sc;
+      }
+      const float scaled_error = sqrtf(sumsq / (float)Dtot);             /* rms_norm */
+      keep = (scaled_error < 1.0f) || at_dtmin;
+      float inv_err = (scaled_error == 0.0f) ? INFINITY : 1.0f / scaled_error;
+      float factor1 = (coeff1 == 0.0f) ? 1.0f : m_pow(inv_err, coeff1);
+      float factor2 = (coeff2 == 0.0f) ? 1.0f : m_pow(prev_inv_err, coeff2);
+      float factor3 = (coeff3 == 0.0f) ? 1.0f : m_pow(prev_prev_inv_err, coeff3);
+      float fmin = keep ? 1.0f : factormin;
+      float factor = ((safety * factor1) * factor2) * factor3;
+      factor = clipf(factor, fmin, factormax);
+      float ndt = dt * factor;
+      if (d->dtmin > 0.0f) {                                              /* force_dtmin=True */
+        at_dtmin = (ndt <= d->dtmin);
+        ndt = (ndt != ndt) ? ndt : (ndt > d->dtmin ? ndt : d->dtmin);
+      }
+      new_tprev = keep ? tnext : tprev;
+      new_tnext = new_tprev + ndt;
+      if (keep) { prev_prev_inv_err = prev_inv_err; prev_inv_err = inv_err; }
+      if (scaled_error != scaled_error) { /* NaN error estimate: no further step can be accepted; the
+                                             solve ends here and the remaining save points keep inf */
+        break;
+      }
+    }
+    new_tprev = new_tprev < t1 ? new_tprev : t1;
+    {
+      const int clip = new_tnext > t1 - 1e-6f;                            /* _clip_to_end */
+      const float tclip = keep ? t1 : new_tprev + 0.5f * (t1 - new_tprev);
+      new_tnext = clip ? tclip : new_tnext;
+    }
+    num_steps++;
+    if (keep) {
+      if (dopri) { /* 4th-order dense output through (y0, f0, ymid, y1, f1) */
+        for (int i = 0; i < Dtot; i++) {
+          float acc = 0.0f;
+          for (int j = 0; j < 7; j++) {
+            float term = DP_CMID[j] * ks[j][i];
+            acc = (j == 0) ? term : acc + term;
+          }
+          ymid[i] = y[i] + acc;
+        }
+      }
+      while (save_idx < K && ts[save_idx] <= tnext) {                      /* SaveAt(ts) */
+        float tk = ts[save_idx];
+        float th = (tprev == tnext) ? 0.0f : (tk - tprev) / (tnext - tprev); /* linear_rescale */
+        for (int i = 0; i < Dtot; i++) {
+          if (!dopri) {
+            ys_out[save_idx * Dtot + i] = y[i] + th * (y1[i] - y[i]);
+          } else {
+            float f0 = ks[0][i], f1 = ks[6][i];
+            float a = ((2.0f * (f1 - f0)) - (8.0f * (y1[i] + y[i]))) + (16.0f * ymid[i]);
+            float bq = ((((5.0f * f0) - (3.0f * f1)) + (18.0f * y[i])) + (14.0f * y1[i])) - (32.0f * ymid[i]);
+            float cq = ((((f1 - (4.0f * f0)) - (11.0f * y[i])) - (5.0f * y1[i]))) + (16.0f * ymid[i]);
+            ys_out[save_idx * Dtot + i] = ((((a * th + bq) * th + cq) * th + f0) * th) + y[i];
+          }
+        }
+        save_idx++;
+      }
+      float event_new = env_cond(d->env_id, y1, Dtot);                     /* cond_fn(tnext, y1) */
+      int fired = (event_old > 0.0f) != (event_new > 0.0f);
+      event_old = event_new;
+      for (int i = 0; i < Dtot; i++) { y[i] = y1[i]; f[0][i] = f[6][i]; }
+      fsal_valid = dopri;
+      accepted++;
+      tprev = new_tprev;
+      tnext = new_tnext;
+      if (fired) break;
+    } else {
+      tprev = new_tprev; /* unchanged */
+      tnext = new_tnext;
+      /* f[0] stays valid: same (t0, y0) */
+    }
   }
-  return steps;
+  return accepted;
 }
 
 /* Evaluator.evaluate_control_loop / evaluate_time_series for trajectory b of candidate `cand`.
@@ -562,7 +688,7 @@ static float eval_trajectory(const float* cand, int T, int N, const mtgp_node_ta
     Dtot = D;
     for (int i = 0; i < D; i++) y0[i] = d->x0[(size_t)b * D + i];
     c.env.id = MTGP_ENV_NONE;
-    int steps = diffeqsolve_euler(&c, y0, Dtot, sol);
+    int steps = diffeqsolve(&c, y0, Dtot, sol);
     if (steps_acc) *steps_acc += (unsigned long long)steps;
     /* fitness_function: mean(sum(square(pred - true), axis=-1)) (SR_evaluator.py:24) */
     const float* ytrue = d->ys_true + (size_t)b * K * D;
@@ -583,7 +709,7 @@ static float eval_trajectory(const float* cand, int T, int N, const mtgp_node_ta
   Dtot = D + S;
   for (int i = 0; i < D; i++) y0[i] = d->x0[(size_t)b * D + i];
   for (int i = 0; i < S; i++) y0[D + i] = 0.0f; /* _x0 = concat([x0, zeros(state_size)]) (dynamic_evaluate.py:89) */
-  int steps = diffeqsolve_euler(&c, y0, Dtot, sol);
+  int steps = diffeqsolve(&c, y0, Dtot, sol);
   if (steps_acc) *steps_acc += (unsigned long long)steps;
   /* post-pass at the save points (feedforward_evaluate.py:95-99, dynamic_evaluate.py:98-103) */
   int n_obs = d->n_obs, nt = d->n_targets, nc = T - S;

@@ -125,6 +125,51 @@ def test_inline_noise_generator_matches_the_table(engine, oracle, monkeypatch):
         assert util.same_or_both_nan(g["ys"], a["ys"]).all()
 
 
+@pytest.mark.parametrize("env_name", ["harmonic", "acrobot", "reactor"])
+@pytest.mark.parametrize("kind", [abi.EVAL_STATIC, abi.EVAL_DYNAMIC])
+@pytest.mark.parametrize("obs_noise", [0.0, 0.1])
+def test_dopri5_pid_rollout_parity(engine, oracle, env_name, kind, obs_noise):
+    """The notebooks' solver settings: Dopri5 + PIDController(atol, rtol, dtmin=0.001), max_steps 1000.
+    Every lane adapts its own step size; the kernel must reproduce the oracle's accept/reject sequence
+    exactly (same arithmetic), hence bit-identical trajectories."""
+    rng = np.random.default_rng(hash(("dopri", env_name, kind, obs_noise > 0)) % 2 ** 32)
+    grid = dict(T_end=1.0, dt_save=0.04, dt0=0.002) if env_name == "reactor" else dict(T_end=6.0, dt_save=0.2, dt0=0.05)
+    lib, pop, data = util.control_case(env_name, kind, rng, P=60, B=8, obs_noise=obs_noise, max_steps=1000,
+                                       param_mode="Constant" if env_name == "acrobot" else "Different", **grid)
+    util.with_solver(data, **util.DOPRI_PID)
+    ref = oracle.rollout_population(pop, lib.table(), data, trajectories=True)
+    gpu = _gpu_rollout(engine, lib, pop, data, trajectories=True, count_steps=True)
+    for k in ("xs", "ys", "us", "traj_fitness") + (("activities",) if kind == abi.EVAL_DYNAMIC else ()):
+        ok = util.same_or_both_nan(gpu[k], ref[k])
+        assert ok.all(), f"{k}: {(~ok).sum()} of {ok.size} elements differ"
+    _assert_fitness(gpu["fitness"], ref["fitness"], 1e4)
+    assert int(gpu["steps"][0]) == ref["steps"]
+
+
+def test_dopri5_other_settings(engine, oracle):
+    rng = np.random.default_rng(21)
+    # SR with Dopri5 + PID as in SymbolicRegression.ipynb:136 (tolerances 1e-6, max_steps 500)
+    lib, pop, data = util.sr_case(rng, P=80, B=8, T_end=4.0, dt0=0.01)
+    util.with_solver(data, solver=abi.SOLVER_DOPRI5, controller=abi.CONTROLLER_PID, rtol=1e-6, atol=1e-6, dtmin=0.001,
+                     max_steps=500)
+    ref = oracle.rollout_population(pop, lib.table(), data, trajectories=True)
+    gpu = _gpu_rollout(engine, lib, pop, data, trajectories=True, count_steps=True)
+    assert util.same_or_both_nan(gpu["xs"], ref["xs"]).all()
+    assert util.same_or_both_nan(gpu["traj_fitness"], ref["traj_fitness"]).all()
+    assert int(gpu["steps"][0]) == ref["steps"]
+    # fixed-step Dopri5, a PID controller with P and D terms and no dtmin, B > 32
+    lib, pop, data = util.control_case("harmonic", abi.EVAL_DYNAMIC, rng, P=20, B=40, T_end=4.0, dt0=0.1)
+    for kw in (dict(solver=abi.SOLVER_DOPRI5),
+               dict(solver=abi.SOLVER_DOPRI5, controller=abi.CONTROLLER_PID, rtol=1e-5, atol=1e-7, dtmin=0.0,
+                    pid=(0.3, 0.3, 0.1), pid_limits=(0.8, 0.1, 5.0))):
+        util.with_solver(data, **kw)
+        ref = oracle.rollout_population(pop, lib.table(), data, trajectories=True)
+        gpu = _gpu_rollout(engine, lib, pop, data, trajectories=True, count_steps=True)
+        assert util.same_or_both_nan(gpu["xs"], ref["xs"]).all() and util.same_or_both_nan(gpu["activities"], ref["activities"]).all()
+        assert util.same_or_both_nan(gpu["traj_fitness"], ref["traj_fitness"]).all()
+        assert int(gpu["steps"][0]) == ref["steps"]
+
+
 def test_threefry_original_mode(engine, oracle):
     rng = np.random.default_rng(5)
     for env_name in ("acrobot", "reactor", "harmonic"):  # n_obs = 4, 3 (odd: zero pad), 2
@@ -311,6 +356,14 @@ def test_evaluator_classes_drop_in(engine, oracle):
     assert xs.shape == (B, ts.size, 4) and us.shape == (B, ts.size, 1) and act.shape == (B, ts.size, 2)
     assert util.same_or_both_nan(xs, ref["xs"][5]).all() and util.same_or_both_nan(f, ref["traj_fitness"][5]).all()
     with pytest.raises(NotImplementedError):
-        feedforward_evaluate.Evaluator(env, 0.05, solver="Dopri5")
+        feedforward_evaluate.Evaluator(env, 0.05, solver="Tsit5")
+    # the notebook's own construction (StaticPolicy.ipynb:102) with the stand-in solver classes
+    from multitreegp_b200.solvers import Dopri5, PIDController
+    lib_s = util.control_library(env, abi.EVAL_STATIC)
+    ev2 = feedforward_evaluate.Evaluator(env, 0.05, solver=Dopri5(), max_steps=1000, library=lib_s,
+                                         stepsize_controller=PIDController(atol=1e-4, rtol=1e-4, dtmin=0.001))
+    pop_s = util.sample_population(rng, 16, lib_s, 4, 30)
+    ref2 = oracle.rollout_population(pop_s, lib_s.table(), ev2.rollout_data(data))
+    np.testing.assert_allclose(ev2.evaluate_population(pop_s, data), ref2["fitness"], rtol=RTOL)
     with pytest.raises(ValueError):
         SR_evaluator.Evaluator().bind([("pow", 2)], [["x0"]], [1])

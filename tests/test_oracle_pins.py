@@ -259,3 +259,43 @@ def test_penalty_mean_clip(oracle):
     np.testing.assert_allclose(out["fitness"], want, rtol=1e-6)
     assert (~np.isfinite(tf)).any() and np.isfinite(tf).any()
     np.testing.assert_array_equal(oracle.live_count(pop), (pop[..., 0] != 0).sum((1, 2)))
+
+
+# ---- Dopri5 + PIDController (what the notebooks pass) ---------------------------------------------------
+def test_dopri5_accuracy_and_adaptivity(oracle):
+    """Constant policy on the harmonic oscillator: the exact solution is known (scipy, 1e-12).  Fixed-step
+    Dopri5 must be float32-exact at h = 0.125, the PID controller must take fewer steps at looser
+    tolerances and land within a few times the tolerance, including at the dense-output save points."""
+    from scipy.integrate import solve_ivp
+    env = HarmonicOscillator(0.0, 0.0)
+    lib = util.control_library(env, abi.EVAL_STATIC)
+    rng = np.random.default_rng(2)
+    B = 4
+    x0, targets = env.sample_init_states(B, rng)
+    omega, zeta = env.sample_params(B, "Different", None, rng)
+    ts = np.arange(0, 8, 0.37, dtype=F32)          # save points that never coincide with steps
+    pop = _const_policy_pop(lib, 12, 0.75)
+
+    def run(**kw):
+        data = RolloutData(kind=abi.EVAL_STATIC, env_id=env.env_id, x0=x0, ts=ts, dt0=kw.pop("dt0"), max_fitness=1e4,
+                           targets=targets, params=np.stack([omega, zeta], 1), n_obs=2, **kw)
+        return oracle.rollout_population(pop, lib.table(), data, trajectories=True)
+
+    ref = []
+    for b in range(B):
+        A = np.array([[0, 1], [-omega[b], -zeta[b]]], dtype=np.float64)
+        sol = solve_ivp(lambda t, x: A @ x + np.array([0, 0.75]), (0, float(ts[-1])), x0[b].astype(np.float64),
+                        t_eval=ts.astype(np.float64), rtol=1e-12, atol=1e-12)
+        ref.append(sol.y.T)
+    ref = np.array(ref)
+    fixed = run(dt0=0.125, solver=abi.SOLVER_DOPRI5)
+    assert np.abs(fixed["xs"][0] - ref).max() < 3e-5
+    loose = run(dt0=0.05, solver=abi.SOLVER_DOPRI5, controller=abi.CONTROLLER_PID, rtol=1e-3, atol=1e-3, dtmin=0.001)
+    tight = run(dt0=0.05, solver=abi.SOLVER_DOPRI5, controller=abi.CONTROLLER_PID, rtol=1e-6, atol=1e-6, dtmin=0.001)
+    assert loose["steps"] < tight["steps"] < fixed["steps"]
+    assert np.abs(loose["xs"][0] - ref).max() < 2e-2 and np.abs(tight["xs"][0] - ref).max() < 5e-5
+    # max_steps counts rejected steps too and leaves the tail inf (throw=False)
+    short = run(dt0=0.05, solver=abi.SOLVER_DOPRI5, controller=abi.CONTROLLER_PID, rtol=1e-6, atol=1e-6, dtmin=0.001,
+                max_steps=8)
+    assert np.isinf(short["xs"][0, :, -1]).all() and np.isfinite(short["xs"][0, :, 0]).all()
+    assert (short["fitness"] == 1e4).all()

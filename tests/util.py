@@ -58,6 +58,15 @@ def control_case(env_name: str, kind: int, rng, P: int, B: int = 8, T_end: float
     return lib, pop, data
 
 
+DOPRI_PID = dict(solver=abi.SOLVER_DOPRI5, controller=abi.CONTROLLER_PID, rtol=1e-4, atol=1e-4, dtmin=0.001)  # StaticPolicy.ipynb:102
+
+
+def with_solver(data: RolloutData, **kw) -> RolloutData:
+    for k, v in kw.items():
+        setattr(data, k, v)
+    return data
+
+
 def same_or_both_nan(a, b):
     a, b = np.asarray(a), np.asarray(b)
     return (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))

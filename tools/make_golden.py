@@ -32,7 +32,8 @@ def save_case(name, lib, pop, data, out):
         params=data.params if data.params is not None else np.zeros((0, 0), np.float32),
         ys_true=data.ys_true if data.ys_true is not None else np.zeros((0,), np.float32),
         n_obs=data.n_obs, state_size=data.state_size, max_steps=data.max_steps, obs_noise=np.float32(data.obs_noise),
-        partitionable=int(data.threefry_partitionable), fitness=out["fitness"], traj_fitness=out["traj_fitness"],
+        partitionable=int(data.threefry_partitionable), solver=data.solver, controller=data.controller,
+        rtol=np.float32(data.rtol), atol=np.float32(data.atol), dtmin=np.float32(data.dtmin), fitness=out["fitness"], traj_fitness=out["traj_fitness"],
         steps=out["steps"])
 
 
@@ -50,6 +51,11 @@ def main():
             lib, pop, data = util.control_case(env, kind, rng, P=48, B=6, obs_noise=0.1,
                                                param_mode="Constant" if env == "acrobot" else "Different", **grid)
             save_case(f"{kname}_{env}", lib, pop, data, po.rollout_population(pop, lib.table(), data))
+    # the notebooks' solver settings: Dopri5 + PIDController(1e-4, 1e-4, dtmin=0.001), max_steps 1000
+    lib, pop, data = util.control_case("acrobot", abi.EVAL_DYNAMIC, rng, P=32, B=6, T_end=6.0, dt_save=0.2, dt0=0.05,
+                                       obs_noise=0.1, max_steps=1000)
+    util.with_solver(data, **util.DOPRI_PID)
+    save_case("dynamic_acrobot_dopri5_pid", lib, pop, data, po.rollout_population(pop, lib.table(), data))
     # jax.random vectors (threefry known answers are asserted literally in the tests)
     keys = util.random_keys(rng, 16)
     ts = np.float32(rng.uniform(0, 50, 16))
