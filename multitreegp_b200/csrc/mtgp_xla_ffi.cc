@@ -30,7 +30,8 @@ static ffi::Error RolloutImpl(cudaStream_t stream, ffi::ScratchAllocator scratch
                               ffi::Buffer<ffi::F32> ys_true, ffi::ResultBuffer<ffi::F32> fitness,
                               ffi::Span<const int32_t> opcodes, ffi::Span<const int32_t> args, int32_t kind,
                               int32_t env_id, int32_t n_obs, int32_t state_size, int32_t max_steps, float dt0,
-                              float max_fitness, float obs_noise, int32_t threefry_partitionable) {
+                              float max_fitness, float obs_noise, int32_t threefry_partitionable, int32_t solver,
+                              int32_t controller, float rtol, float atol, float dtmin) {
   auto nd = nodes.dimensions();
   if (nd.size() < 4 || nd[nd.size() - 1] != 3) return ffi::Error::InvalidArgument("nodes must be [..., T, N, 3]");
   const int N = (int)nd[nd.size() - 2], T = (int)nd[nd.size() - 3];
@@ -56,6 +57,7 @@ static ffi::Error RolloutImpl(cudaStream_t stream, ffi::ScratchAllocator scratch
   d.n_params = params.element_count() ? (int)params.dimensions().back() : 0;
   d.state_size = state_size; d.max_steps = max_steps; d.dt0 = dt0; d.max_fitness = max_fitness;
   d.obs_noise = obs_noise; d.threefry_partitionable = threefry_partitionable;
+  d.solver = solver; d.controller = controller; d.rtol = rtol; d.atol = atol; d.dtmin = dtmin;  // PID gains: diffrax defaults
   d.x0 = x0.typed_data(); d.ts = ts.typed_data();
   d.targets = d.n_targets ? targets.typed_data() : nullptr;
   d.obs_keys = obs_keys.element_count() ? obs_keys.typed_data() : nullptr;
@@ -96,5 +98,10 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(
         .Attr<float>("dt0")
         .Attr<float>("max_fitness")
         .Attr<float>("obs_noise")
-        .Attr<int32_t>("threefry_partitionable"));
+        .Attr<int32_t>("threefry_partitionable")
+        .Attr<int32_t>("solver")
+        .Attr<int32_t>("controller")
+        .Attr<float>("rtol")
+        .Attr<float>("atol")
+        .Attr<float>("dtmin"));
 #endif  // xla/ffi/api/ffi.h

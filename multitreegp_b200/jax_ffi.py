@@ -52,6 +52,7 @@ class JaxEvaluator:
         import jax.numpy as jnp
         from . import abi
         ev, lib = self.ev, self.ev.library
+        ss = ev._solver_settings   # Euler/Dopri5, ConstantStepSize/PIDController (diffrax objects are accepted)
         if ev.kind == abi.EVAL_SR:
             x0, ts, ys, _ = data
             targets, keys, params = jnp.zeros((x0.shape[0], 0)), jnp.zeros((0, 2), jnp.uint32), jnp.zeros((0, 0))
@@ -69,4 +70,7 @@ class JaxEvaluator:
                     kind=np.int32(ev.kind), env_id=np.int32(env_id), n_obs=np.int32(n_obs),
                     state_size=np.int32(state_size), max_steps=np.int32(ev.max_steps), dt0=np.float32(ev.dt0),
                     max_fitness=np.float32(ev.max_fitness), obs_noise=np.float32(obs_noise),
-                    threefry_partitionable=np.int32(bool(jax.config.jax_threefry_partitionable)))
+                    threefry_partitionable=np.int32(bool(jax.config.jax_threefry_partitionable)),
+                    solver=np.int32(ss.get("solver", 0)), controller=np.int32(ss.get("controller", 0)),
+                    rtol=np.float32(ss.get("rtol", 0.0)), atol=np.float32(ss.get("atol", 0.0)),
+                    dtmin=np.float32(ss.get("dtmin", 0.0)))
