@@ -329,6 +329,37 @@ def test_deep_comb_trees_take_the_slow_pointwise_path(engine, oracle):
     _assert_fitness(fit.cpu().numpy(), ref_f, 1e5)
 
 
+def test_fuzz_arbitrary_row_arrays_on_device(engine, oracle):
+    """Populations of RANDOM rows (arbitrary operand indices, shared rows, non-integral ids): the device
+    encoder + lowering + both interpreters against body_fun as restated by the oracle."""
+    from multitreegp_b200.node_library import NodeLibrary
+    from multitreegp_b200.rollout_data import RolloutData
+    rng = np.random.default_rng(31)
+    lib = NodeLibrary(util.OPS_ALL, [["x0", "x1"]], [2])
+    P, T, N = 600, 2, 20
+    pop = np.zeros((P, T, N, 4), np.float32)
+    pop[..., 0] = rng.integers(0, lib.n_ids, (P, T, N))
+    back = np.arange(N)[None, None, :]
+    pop[..., 1] = np.where(rng.random((P, T, N)) < 0.7, rng.integers(-1, N, (P, T, N)) % np.maximum(back, 1), rng.integers(-2, N + 2, (P, T, N)))
+    pop[..., 2] = np.where(rng.random((P, T, N)) < 0.7, rng.integers(-1, N, (P, T, N)) % np.maximum(back, 1), rng.integers(-2, N + 2, (P, T, N)))
+    pop[..., 3] = np.where(rng.random((P, T, N)) < 0.7, rng.normal(size=(P, T, N)), 0)
+    pop[::17, 0, 3, 0] = 1.5
+    X = rng.normal(size=(300, 2)).astype(np.float32)
+    Y = rng.normal(size=(300, 2)).astype(np.float32)
+    ref_f, ref_p = oracle.pointwise_population(pop, lib.table(), X, Y, predictions=True)
+    fit, pred = engine.pointwise_fitness(_dev(engine, pop), lib.table(), _dev(engine, X), _dev(engine, Y), predictions=True)
+    assert util.same_or_both_nan(pred.cpu().numpy(), ref_p).all()
+    _assert_fitness(fit.cpu().numpy(), ref_f, 1e5)
+    # the same population as a 2-dimensional ODE right-hand side through the rollout kernel (pre-decoded programs)
+    B, ts = 4, np.arange(0, 1.0, 0.1, dtype=np.float32)
+    data = RolloutData(kind=abi.EVAL_SR, env_id=abi.ENV_NONE, x0=rng.normal(size=(B, 2)).astype(np.float32), ts=ts,
+                       dt0=0.02, max_fitness=1e5, ys_true=rng.normal(size=(B, ts.size, 2)).astype(np.float32))
+    ref = oracle.rollout_population(pop, lib.table(), data, trajectories=True)
+    gpu = _gpu_rollout(engine, lib, pop, data, trajectories=True)
+    assert util.same_or_both_nan(gpu["xs"], ref["xs"]).all()
+    assert util.same_or_both_nan(gpu["traj_fitness"], ref["traj_fitness"]).all()
+
+
 def test_evaluator_classes_drop_in(engine, oracle):
     """The reference-facing classes: same constructor/call protocol as the reference evaluators."""
     from multitreegp_b200.evaluators import dynamic_evaluate, feedforward_evaluate, SR_evaluator

@@ -145,3 +145,29 @@ def test_comb_needs_many_temporaries(hostlib, oracle):
     build2(5)
     n_instr, n_tmp, flags = _check(hostlib, oracle, np.float32(rows), lib.table())
     assert flags == 1 and n_tmp == 5
+
+
+def test_fuzz_arbitrary_row_arrays(hostlib, oracle):
+    """Rows drawn at random -- arbitrary operand indices (backward, forward, self, -1, out of range),
+    shared rows, empty rows anywhere.  body_fun defines a value for every such array; the lowering pass
+    (reachability, reference counts, spills, constant folding) must reproduce it bit for bit."""
+    rng = np.random.default_rng(99)
+    lib = NodeLibrary(util.OPS_ALL, [["x0", "x1", "x2"]], [1])
+    tab, F = lib.table(), lib.n_ids
+    n_checked = 0
+    for trial in range(1500):
+        N = int(rng.integers(1, 24))
+        tree = np.zeros((N, 4), np.float32)
+        tree[:, 0] = rng.integers(0, F, N)
+        if trial % 3 == 0:   # mostly backward references: deep DAGs with heavy sharing
+            tree[:, 1] = [rng.integers(-1, max(i, 1)) for i in range(N)]
+            tree[:, 2] = [rng.integers(-1, max(i, 1)) for i in range(N)]
+        else:                # anything goes
+            tree[:, 1] = rng.integers(-2, N + 2, N)
+            tree[:, 2] = rng.integers(-2, N + 2, N)
+        tree[:, 3] = np.where(rng.random(N) < 0.7, rng.normal(size=N), 0).astype(np.float32)
+        if trial % 7 == 0:
+            tree[rng.integers(0, N), 0] = rng.choice([-1.0, 1.5, F + 3, 0.5])
+        _check(hostlib, oracle, tree, tab)
+        n_checked += 1
+    assert n_checked == 1500
