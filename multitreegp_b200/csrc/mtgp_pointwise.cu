@@ -15,8 +15,14 @@ namespace {
 #ifndef MTGP_PW_R
 #define MTGP_PW_R 8  // points per lane per dispatched instruction in the fast pointwise launch
 #endif
+#ifndef MTGP_PW_MIN_CTAS
+#define MTGP_PW_MIN_CTAS 8  // resident CTAs per SM the register allocation is tuned for
+#endif
 constexpr int kPwWarps = 4;
-constexpr int kPwGroup = 8;
+#ifndef MTGP_PW_GROUP
+#define MTGP_PW_GROUP 8  // individuals sharing one CTA (and every data chunk a warp loads)
+#endif
+constexpr int kPwGroup = MTGP_PW_GROUP;
 
 struct PointwiseParams {
   const uint2* prog;
@@ -31,46 +37,54 @@ struct PointwiseParams {
   float* fitness;
   float* pred;
   int tmp_base;    // = n_vars + T
-  int n_tmp;       // temporaries provisioned per warp
-  int min_need;    // this launch handles individuals whose max temporaries are in (min_need-1, n_tmp]
+  int fast_tmp, fast_instr;  // the fast class: <= fast_tmp temporaries and <= fast_instr instructions (incl. END) per tree
+  int want_fast;   // this launch handles the fast class (1) or everything else (0)
+  int pstride;     // instructions reserved per tree in shared memory
   int slots_per_warp;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <int R>
-__global__ void __launch_bounds__(kPwWarps * 32) k_pointwise(const PointwiseParams P) {
+__global__ void __launch_bounds__(kPwWarps * 32, MTGP_PW_MIN_CTAS) k_pointwise(const PointwiseParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_need[kPwGroup];
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const int ind0 = blockIdx.x * kPwGroup;
   const int G = min(kPwGroup, P.P - ind0);
-  const int words_per_ind = P.T * P.lstride;
-
+  const int words_per_ind = P.T * P.pstride;
   uint2* prog_s = reinterpret_cast<uint2*>(smem_raw);
   float* acc_s = reinterpret_cast<float*>(smem_raw + (size_t)kPwGroup * words_per_ind * sizeof(uint2));
   float* vf = acc_s + kPwGroup * kPwWarps * 32 + (size_t)wic * P.slots_per_warp * 32 * R;
 
-  // which individuals of the group belong to this launch (by temporaries needed)
+  // which individuals of the group belong to this launch (by temporaries and program length)
   if (threadIdx.x < kPwGroup) {
-    int need = -1;
+    int mine = 0;
     if ((int)threadIdx.x < G) {
-      need = 0;
-      for (int t = 0; t < P.T; t++) need = max(need, (int)(P.meta[(size_t)(ind0 + threadIdx.x) * P.T + t] >> 16));
+      int need = 0, len = 0;
+      for (int t = 0; t < P.T; t++) {
+        const uint32_t m = P.meta[(size_t)(ind0 + threadIdx.x) * P.T + t];
+        need = max(need, (int)(m >> 16));
+        len = max(len, (int)(m & 0xFFFFu) + 1);
+      }
+      const bool fast = (need <= P.fast_tmp) && (len <= P.fast_instr);
+      mine = (fast == (P.want_fast != 0)) ? 1 : 0;
     }
-    s_need[threadIdx.x] = (need >= P.min_need && need <= P.n_tmp) ? 1 : 0;
+    s_need[threadIdx.x] = mine;
   }
   __syncthreads();
   bool any = false;
   for (int g = 0; g < G; g++) any |= (s_need[g] != 0);
   if (!any) return;
 
-  // stage the programs of the group (contiguous in global memory)
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(P.prog + (size_t)ind0 * words_per_ind);
-    uint4* dst = reinterpret_cast<uint4*>(prog_s);
-    const int n16 = G * words_per_ind / 2;
-    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+  // stage the programs of the group: only the instructions each tree actually has
+  for (int gt = wic; gt < G * P.T; gt += kPwWarps) {
+    if (!s_need[gt / P.T]) continue;
+    const size_t tree = (size_t)ind0 * P.T + gt;
+    const int n = (int)(P.meta[tree] & 0xFFFFu) + 1;
+    const uint2* src = P.prog + tree * P.lstride;
+    uint2* dst = prog_s + (size_t)gt * P.pstride;
+    for (int i = lane; i < n; i += 32) dst[i] = __ldg(src + i);
   }
   __syncthreads();
 
@@ -105,7 +119,7 @@ __global__ void __launch_bounds__(kPwWarps * 32) k_pointwise(const PointwisePara
 #pragma unroll
       for (int r = 0; r < R; r++) row[r] = 0.0f;
       for (int t = 0; t < P.T; t++) {
-        const Vec<R> pr = mtgp_interpret<R>(prog_s + (size_t)g * words_per_ind + (size_t)t * P.lstride, lb);
+        const Vec<R> pr = mtgp_interpret<R>(prog_s + (size_t)g * words_per_ind + (size_t)t * P.pstride, lb);
         const Vec<R> yt = vf_load<R>(lb, P.n_vars + t);
 #pragma unroll
         for (int r = 0; r < R; r++) {
@@ -160,11 +174,11 @@ __global__ void k_transpose_points(const float* __restrict__ X, const float* __r
 }
 
 template <int R>
-int launch_pw(PointwiseParams pp, int n_tmp, int min_need, cudaStream_t stream) {
-  pp.n_tmp = n_tmp;
-  pp.min_need = min_need;
+int launch_pw(PointwiseParams pp, int n_tmp, int pstride, int want_fast, cudaStream_t stream) {
+  pp.want_fast = want_fast;
+  pp.pstride = pstride;
   pp.slots_per_warp = pp.tmp_base + n_tmp;
-  const size_t smem = (size_t)kPwGroup * pp.T * pp.lstride * sizeof(uint2) + (size_t)kPwGroup * kPwWarps * 32 * 4 +
+  const size_t smem = (size_t)kPwGroup * pp.T * pstride * sizeof(uint2) + (size_t)kPwGroup * kPwWarps * 32 * 4 +
                       (size_t)kPwWarps * pp.slots_per_warp * 32 * R * 4;
   if (smem > 227 * 1024) {
     mtgp_set_error("pointwise kernel needs %zu bytes of shared memory per CTA: over the 227 KB limit", smem);
@@ -197,12 +211,17 @@ int mtgp_launch_pointwise(const mtgp_programs& progs, const int32_t* live, int P
   pp.max_fitness = max_fitness; pp.size_parsimony = size_parsimony;
   pp.fitness = fitness; pp.pred = pred;
   pp.tmp_base = progs.tmp_base;
-  // fast path: up to kFastTmp temporaries with R points per lane; anything deeper (only trees
-  // grown into long combs by mutation) runs one point per lane with the worst-case bound.
-  const int kFastTmp = 8;
+  // fast class: programs of up to kFastInstr instructions needing up to kFastTmp temporaries (every
+  // tree of ordinary size and depth) run R points per lane with a small shared-memory footprint, hence
+  // many resident warps; anything bigger (long combs grown by mutation, near-full deep trees) runs one
+  // point per lane provisioned with the worst-case bounds.  Each launch skips the other's individuals.
+  const int kFastTmp = 4, kFastInstr = 32;
   const int bound = mtgp_tmp_bound(N);
-  int rc = launch_pw<MTGP_PW_R>(pp, bound < kFastTmp ? bound : kFastTmp, 0, stream);
+  const bool all_fast = (bound <= kFastTmp) && (progs.lstride <= kFastInstr);
+  pp.fast_tmp = all_fast ? bound : kFastTmp;
+  pp.fast_instr = all_fast ? progs.lstride : kFastInstr;
+  int rc = launch_pw<MTGP_PW_R>(pp, pp.fast_tmp, pp.fast_instr, 1, stream);
   if (rc != MTGP_OK) return rc;
-  if (bound > kFastTmp) rc = launch_pw<1>(pp, bound, kFastTmp + 1, stream);
+  if (!all_fast) rc = launch_pw<1>(pp, bound, progs.lstride, 0, stream);
   return rc;
 }
