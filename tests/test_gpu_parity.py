@@ -398,3 +398,33 @@ def test_evaluator_classes_drop_in(engine, oracle):
     np.testing.assert_allclose(ev2.evaluate_population(pop_s, data), ref2["fitness"], rtol=RTOL)
     with pytest.raises(ValueError):
         SR_evaluator.Evaluator().bind([("pow", 2)], [["x0"]], [1])
+
+
+def test_evaluation_driver_mirrors_evaluate_population(engine, oracle):
+    """genetic_programming.py:403-433: flatten islands, evaluate, + parsimony, best-of-generation, reshape."""
+    from multitreegp_b200.evaluators import feedforward_evaluate
+    from multitreegp_b200.environments.control_environments import HarmonicOscillator
+    from multitreegp_b200.strategy_eval import EvaluationDriver
+    rng = np.random.default_rng(41)
+    env = HarmonicOscillator(0.0, 0.05)
+    lib = util.control_library(env, abi.EVAL_STATIC)
+    ev = feedforward_evaluate.Evaluator(env, 0.05, library=lib)
+    num_pop, pop_size, B = 3, 20, 8
+    pops = util.sample_population(rng, num_pop * pop_size, lib, 4, 30).reshape(num_pop, pop_size, 1, 30, 4)
+    x0, targets = env.sample_init_states(B, rng)
+    ts = np.arange(0, 4, 0.2, dtype=np.float32)
+    keys = util.random_keys(rng, B)
+    data = (x0, ts, targets, keys, keys, env.sample_params(B, "Different", ts, rng))
+    drv = EvaluationDriver(5, pop_size, ev, num_populations=num_pop, size_parsinomy=0.5)
+    fit, same = drv.evaluate_population(pops, data)
+    assert fit.shape == (num_pop, pop_size) and same is pops
+    flat = pops.reshape(-1, 1, 30, 4)
+    want = oracle.rollout_population(flat, lib.table(), ev.rollout_data(data))["fitness"] + np.float32(0.5) * oracle.live_count(flat)
+    np.testing.assert_allclose(fit.reshape(-1), want, rtol=RTOL)
+    bf, bs = drv.get_statistics(0)
+    assert bf == fit.min() and (bs == flat[int(np.argmin(want))]).all()
+    # CUDA tensors in -> CUDA tensors out
+    drv.next_generation()
+    fit_d, _ = drv.evaluate_population(_dev(engine, pops), data)
+    np.testing.assert_array_equal(fit_d.cpu().numpy(), fit)
+    assert drv.get_statistics(1)[0] == bf
