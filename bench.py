@@ -62,6 +62,14 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
+def ncu_field(kernel, field):
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return json.load(f)[kernel].get(field)
+    except (OSError, KeyError):
+        return None
+
+
 def ncu_traffic(kernel, P):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the ncu --set full capture
     recorded in profiles/r01_traffic.json (bytes per individual x P); None when no capture is on file."""
@@ -239,6 +247,9 @@ def main():
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--population", type=int, default=None, help="override the per-GPU population (debug)")
     ap.add_argument("--obs-noise", type=float, default=0.1)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU evaluates its own full-size population (default); strong: the named "
+                         "population is split over the GPUs")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--only-secondary", action="store_true", help="run only the pointwise scale-up (profiling)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -265,7 +276,12 @@ def main():
         return
 
     # population shards: every rank its own individuals (weak scaling: per-GPU work fixed)
-    w = make_rollout_workload(args.workload, seed=1000 + rank, P_override=args.population, obs_noise=args.obs_noise)
+    P_named = args.population or WORKLOADS[args.workload][2]
+    if args.scaling == "strong":
+        if P_named % world:
+            raise SystemExit(f"population {P_named} is not divisible by {world} GPUs (shard_map would refuse it too)")
+        P_named //= world
+    w = make_rollout_workload(args.workload, seed=1000 + rank, P_override=P_named, obs_noise=args.obs_noise)
     P = w["pop"].shape[0]
     eng = FitnessEngine(dev)
     table = w["lib"].table()
@@ -344,6 +360,8 @@ def main():
     achieved = per_launch_steps * (flops + int_ops) / (kernel_ms * 1e-3) / 1e12
     roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp32_peak, "traffic": ncu_traffic("k_rollout", P), "kernel": "k_rollout<DYNAMIC,ACROBOT,noise>",
+                "issue_slots_busy_pct_ncu": ncu_field("k_rollout", "issue_active_pct"),
+                "warp_instructions_per_warp_step_ncu": ncu_field("k_rollout", "warp_instructions_per_warp_step"),
                 "kernel_ms": kernel_ms, "ops_per_rollout_step": {"fp": flops, "int_prng": int_ops, "tree_ops": tree_ops},
                 "peak_note": f"non-tensor FP32: 148 SM x 128 lanes x 2 (FMA) x {sm_mhz:.0f} MHz ({peak_src} clock); "
                              "the path runs un-fused IEEE ops by contract, whose ceiling is half of this"}
@@ -377,7 +395,7 @@ def main():
         return
 
     line = {"metric": "rollout_steps_per_s", "value": value, "unit": "rollout-steps/s", "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak",
+            "warmup": W, "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["desc"], "population_per_gpu": P, "trees": int(w["pop"].shape[1]),
                        "max_nodes": w["N"], "trajectories": w["B"], "euler_steps": w["n_sched"],

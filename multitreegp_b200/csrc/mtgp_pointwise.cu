@@ -37,8 +37,9 @@ struct PointwiseParams {
   float* fitness;
   float* pred;
   int tmp_base;    // = n_vars + T
-  int fast_tmp, fast_instr;  // the fast class: <= fast_tmp temporaries and <= fast_instr instructions (incl. END) per tree
-  int want_fast;   // this launch handles the fast class (1) or everything else (0)
+  // this launch handles the individuals whose programs fit (cap_tmp temporaries, cap_instr instructions
+  // incl. END per tree) but do not fit the previous, smaller class (prev_tmp, prev_instr; -1 = none)
+  int cap_tmp, cap_instr, prev_tmp, prev_instr;
   int pstride;     // instructions reserved per tree in shared memory
   int slots_per_warp;
 };
@@ -67,8 +68,9 @@ __global__ void __launch_bounds__(kPwWarps * 32, MTGP_PW_MIN_CTAS) k_pointwise(c
         need = max(need, (int)(m >> 16));
         len = max(len, (int)(m & 0xFFFFu) + 1);
       }
-      const bool fast = (need <= P.fast_tmp) && (len <= P.fast_instr);
-      mine = (fast == (P.want_fast != 0)) ? 1 : 0;
+      const bool fits = (need <= P.cap_tmp) && (len <= P.cap_instr);
+      const bool fits_prev = (need <= P.prev_tmp) && (len <= P.prev_instr);
+      mine = (fits && !fits_prev) ? 1 : 0;
     }
     s_need[threadIdx.x] = mine;
   }
@@ -174,8 +176,11 @@ __global__ void k_transpose_points(const float* __restrict__ X, const float* __r
 }
 
 template <int R>
-int launch_pw(PointwiseParams pp, int n_tmp, int pstride, int want_fast, cudaStream_t stream) {
-  pp.want_fast = want_fast;
+int launch_pw(PointwiseParams pp, int n_tmp, int pstride, int prev_tmp, int prev_instr, cudaStream_t stream) {
+  pp.cap_tmp = n_tmp;
+  pp.cap_instr = pstride;
+  pp.prev_tmp = prev_tmp;
+  pp.prev_instr = prev_instr;
   pp.pstride = pstride;
   pp.slots_per_warp = pp.tmp_base + n_tmp;
   const size_t smem = (size_t)kPwGroup * pp.T * pstride * sizeof(uint2) + (size_t)kPwGroup * kPwWarps * 32 * 4 +
@@ -211,17 +216,18 @@ int mtgp_launch_pointwise(const mtgp_programs& progs, const int32_t* live, int P
   pp.max_fitness = max_fitness; pp.size_parsimony = size_parsimony;
   pp.fitness = fitness; pp.pred = pred;
   pp.tmp_base = progs.tmp_base;
-  // fast class: programs of up to kFastInstr instructions needing up to kFastTmp temporaries (every
-  // tree of ordinary size and depth) run R points per lane with a small shared-memory footprint, hence
-  // many resident warps; anything bigger (long combs grown by mutation, near-full deep trees) runs one
-  // point per lane provisioned with the worst-case bounds.  Each launch skips the other's individuals.
-  const int kFastTmp = 4, kFastInstr = 32;
-  const int bound = mtgp_tmp_bound(N);
-  const bool all_fast = (bound <= kFastTmp) && (progs.lstride <= kFastInstr);
-  pp.fast_tmp = all_fast ? bound : kFastTmp;
-  pp.fast_instr = all_fast ? progs.lstride : kFastInstr;
-  int rc = launch_pw<MTGP_PW_R>(pp, pp.fast_tmp, pp.fast_instr, 1, stream);
-  if (rc != MTGP_OK) return rc;
-  if (!all_fast) rc = launch_pw<1>(pp, bound, progs.lstride, 0, stream);
+  // Three provisioning classes, smallest first; each launch skips the individuals of the others.
+  //   fast   : <= 4 temporaries, <= 32 instructions per tree (every tree of ordinary size and depth):
+  //            R points per lane, small shared-memory footprint, 6-8 resident CTAs per SM
+  //   medium : <= 8 temporaries, <= 128 instructions: still R points per lane, fewer resident CTAs
+  //   worst  : anything a max_nodes-row array can hold (long combs grown by mutation): one point per lane
+  const int bound = mtgp_tmp_bound(N), worst_instr = progs.lstride;
+  const int t0 = bound < 4 ? bound : 4, i0 = worst_instr < 32 ? worst_instr : 32;
+  int rc = launch_pw<MTGP_PW_R>(pp, t0, i0, -1, -1, stream);
+  if (rc != MTGP_OK || (t0 == bound && i0 == worst_instr)) return rc;
+  const int t1 = bound < 8 ? bound : 8, i1 = worst_instr < 128 ? worst_instr : 128;
+  rc = launch_pw<MTGP_PW_R>(pp, t1, i1, t0, i0, stream);
+  if (rc != MTGP_OK || (t1 == bound && i1 == worst_instr)) return rc;
+  rc = launch_pw<1>(pp, bound, worst_instr, t1, i1, stream);
   return rc;
 }
