@@ -252,6 +252,7 @@ def main():
                          "population is split over the GPUs")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--only-secondary", action="store_true", help="run only the pointwise scale-up (profiling)")
+    ap.add_argument("--only-notebooks", action="store_true", help="run only the as-shipped notebook configs (profiling)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ref-step-seconds", type=float, default=2.0)
     args = ap.parse_args()
@@ -270,6 +271,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, max(args.warmup, 3)
+    if args.only_notebooks:
+        print(json.dumps(bench_notebooks(FitnessEngine(dev), dev)))
+        return
     if args.only_secondary:
         peaks, peak_src = measured_peaks()
         print(json.dumps(bench_pointwise(FitnessEngine(dev), dev, K, peaks, peak_src, False)))

@@ -224,13 +224,29 @@ struct Env {
     }
   }
 
+  // out-of-line copy for the in-kernel generator: ~700 instructions that must not be replicated at
+  // every observation site
+  struct Noise4 { float v[4]; };
+  __device__ __noinline__ Noise4 noise_term_ool(float t, int n_obs, float obs_noise, int partitionable) const {
+    float nt[D];
+    noise_term(t, n_obs, obs_noise, partitionable, nt);
+    Noise4 r;
+#pragma unroll
+    for (int i = 0; i < 4; i++) r.v[i] = (i < D) ? nt[i < D ? i : 0] : 0.0f;
+    return r;
+  }
+
   // NOISE: 0 none, 1 = noise term read from the precomputed table row `nz` (element stride `nzs`),
   //        2 = generated inline.  All three give the same bits.
   template <int NOISE>
   __device__ __forceinline__ void f_obs(float t, const float* x, float* y, int n_obs, float obs_noise,
                                         int partitionable, const float* nz, int nzs) const {
     float nt[D];
-    if (NOISE == 2) noise_term(t, n_obs, obs_noise, partitionable, nt);
+    if (NOISE == 2) {
+      const Noise4 r = noise_term_ool(t, n_obs, obs_noise, partitionable);
+#pragma unroll
+      for (int i = 0; i < D; i++) nt[i] = r.v[i < 4 ? i : 3];
+    }
     if (NOISE == 1) {  // table row: [b][4] floats, one 16-byte load per lane
       const float4 v = __ldg(reinterpret_cast<const float4*>(nz));
       const float t4[4] = {v.x, v.y, v.z, v.w};

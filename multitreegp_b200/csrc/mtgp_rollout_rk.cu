@@ -34,7 +34,7 @@ __constant__ float DP_CMID[7] = {(float)(6025192743.0 / 30085553152.0 / 2), 0.0f
                                  (float)(187940372067.0 / 1594534317056.0 / 2), (float)(-1776094331.0 / 19743644256.0 / 2),
                                  (float)(11237099.0 / 235043384.0 / 2)};
 
-constexpr int kRkWarps = 4;
+constexpr int kRkWarps = 1;  // one warp per CTA: the adaptive workloads are small populations, fine-grained CTAs balance the SMs
 constexpr int kRkArrays = 12;  // Y, Y1, YI, F0, KS[0..6], SV
 
 template <int KIND, int ENV, bool NOISE>
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kRkWarps * 32) k_rollout_rk(const RolloutParam
       if (KIND != MTGP_EVAL_SR) { env.sum = 0.0f; env.sum0 = 0.0f; env.fs = -1; }
       float sr_total = 0.0f;
       bool ev_old_bad = bad_state(Y);
-      bool active = true, fsal_valid = false, at_dtmin = false;
+      bool active = true, fsal_valid = false, at_dtmin = false;  // fsal_valid: F0 holds f(tprev, Y)
       float tprev = t0, tnext = t0 + P.dt0;
       tnext = tnext < t1 ? tnext : t1;
       float prev_inv = 1.0f, prev_prev_inv = 1.0f;
@@ -226,87 +226,98 @@ __global__ void __launch_bounds__(kRkWarps * 32) k_rollout_rk(const RolloutParam
         }
       };
 
-      while (__ballot_sync(0xFFFFFFFFu, active && lane_valid) != 0u) {
+      // One iteration = one attempted step of every lane that is still integrating, followed by the
+      // save points that step covers (per lane).  When no lane integrates any more, the remaining save
+      // points of every lane are drained from the inf pre-fill of SaveAt -- through the same code.
+      while (true) {
+        const bool stepping = __ballot_sync(0xFFFFFFFFu, active && lane_valid) != 0u;
+        if (!stepping && __ballot_sync(0xFFFFFFFFu, k < K) == 0u) break;
         const float dt = tnext - tprev;
-        // ---- stages ----
-        if (!dopri) {
-          vector_field(tprev, Y, KS, dt, nullptr);
-          for (int i = 0; i < DT; i++) Y1[i * 32] = Y[i * 32] + KS[i * 32];
-        } else {
-          if (__ballot_sync(0xFFFFFFFFu, !fsal_valid) != 0u) {
-            // first step of the solve (warp-uniform): F0 = f(t0, y0).  Later steps reuse the last
-            // stage of the previous accepted step (FSAL) or, after a rejection, the same F0.
-            vector_field(tprev, Y, F0, 1.0f, nullptr);
-            fsal_valid = true;
-          }
-          for (int i = 0; i < DT; i++) KS[i * 32] = dt * F0[i * 32];
-          for (int st = 1; st < 7; st++) {
-            for (int i = 0; i < DT; i++) {
-              float acc = 0.0f;
-              for (int j = 0; j < st; j++) {
-                const float term = DP_A[st - 1][j] * KS[(j * DT + i) * 32];
-                acc = (j == 0) ? term : acc + term;
+        bool keep = true, nan_err = false;
+        float new_tprev = tprev, new_tnext = tnext;
+        if (stepping) {
+          // ---- stages (Euler: one; Dopri5: seven, the first one reused under FSAL) ----
+          const int n_stages = dopri ? 7 : 1;
+          const bool need_f0 = !dopri || (__ballot_sync(0xFFFFFFFFu, !fsal_valid) != 0u);
+          for (int st = 0; st < n_stages; st++) {
+            const float* src = Y;
+            float tst = tprev;
+            if (st > 0) {
+              for (int i = 0; i < DT; i++) {
+                float acc = 0.0f;
+                for (int j = 0; j < st; j++) {
+                  const float term = DP_A[st - 1][j] * KS[(j * DT + i) * 32];
+                  acc = (j == 0) ? term : acc + term;
+                }
+                YI[i * 32] = Y[i * 32] + acc;
               }
-              YI[i * 32] = Y[i * 32] + acc;
+              if (st == 6)
+                for (int i = 0; i < DT; i++) Y1[i * 32] = YI[i * 32];
+              const float cst = DP_C[st - 1];
+              tst = (cst == 1.0f) ? tnext : tprev + cst * dt;
+              src = YI;
             }
-            if (st == 6)
-              for (int i = 0; i < DT; i++) Y1[i * 32] = YI[i * 32];
-            const float cst = DP_C[st - 1];
-            const float tst = (cst == 1.0f) ? tnext : tprev + cst * dt;
-            // the unscaled last stage (the next step's F0 under FSAL) overwrites YI, which is dead by then
-            vector_field(tst, YI, KS + (size_t)st * DT * 32, dt, st == 6 ? YI : nullptr);
-          }
-        }
-        // ---- step-size controller ----
-        bool keep = true;
-        float new_tprev, new_tnext;
-        bool nan_err = false;
-        if (!pid) {
-          new_tprev = tnext;
-          new_tnext = tnext + P.dt0;
-        } else {
-          float sumsq = 0.0f;
-          for (int i = 0; i < DT; i++) {
-            float yerr = 0.0f;
-            for (int j = 0; j < 7; j++) {
-              const float term = DP_BERR[j] * KS[(j * DT + i) * 32];
-              yerr = (j == 0) ? term : yerr + term;
+            if (st == 0 && !need_f0) {
+              for (int i = 0; i < DT; i++) KS[i * 32] = dt * F0[i * 32];  // FSAL / same point after a rejection
+            } else {
+              // unscaled copies: stage 0 -> F0; the last stage overwrites YI (dead by then) and becomes
+              // the next step's F0 when this step is accepted
+              float* raw = dopri ? (st == 0 ? F0 : (st == 6 ? YI : nullptr)) : nullptr;
+              vector_field(tst, src, KS + (size_t)st * DT * 32, dt, raw);
             }
-            const float ym = mtgp_maximumf(mtgp_absf(Y[i * 32]), mtgp_absf(Y1[i * 32]));
-            const float sc = yerr / (P.atol + ym * P.rtol);
-            sumsq = sumsq + sc * sc;
           }
-          const float scaled_error = mtgp_sqrtf(sumsq / (float)DT);
-          keep = (scaled_error < 1.0f) || at_dtmin;
-          const float inv_err = (scaled_error == 0.0f) ? mtgp_inff() : 1.0f / scaled_error;
-          const float factor1 = (P.coeff1 == 0.0f) ? 1.0f : mtgp_expf(P.coeff1 * mtgp_logf(inv_err));
-          const float factor2 = (P.coeff2 == 0.0f) ? 1.0f : mtgp_expf(P.coeff2 * mtgp_logf(prev_inv));
-          const float factor3 = (P.coeff3 == 0.0f) ? 1.0f : mtgp_expf(P.coeff3 * mtgp_logf(prev_prev_inv));
-          const float fmin = keep ? 1.0f : P.factormin;
-          float factor = ((P.safety * factor1) * factor2) * factor3;
-          factor = clip_jnp(factor, fmin, P.factormax);
-          float ndt = dt * factor;
-          if (P.dtmin > 0.0f) {
-            at_dtmin = (ndt <= P.dtmin);
-            ndt = (ndt != ndt) ? ndt : (ndt > P.dtmin ? ndt : P.dtmin);
+          fsal_valid = true;
+          if (!dopri)
+            for (int i = 0; i < DT; i++) Y1[i * 32] = Y[i * 32] + KS[i * 32];
+          // ---- step-size controller ----
+          if (!pid) {
+            new_tprev = tnext;
+            new_tnext = tnext + P.dt0;
+          } else {
+            float sumsq = 0.0f;
+            for (int i = 0; i < DT; i++) {
+              float yerr = 0.0f;
+              for (int j = 0; j < 7; j++) {
+                const float term = DP_BERR[j] * KS[(j * DT + i) * 32];
+                yerr = (j == 0) ? term : yerr + term;
+              }
+              const float ym = mtgp_maximumf(mtgp_absf(Y[i * 32]), mtgp_absf(Y1[i * 32]));
+              const float sc = yerr / (P.atol + ym * P.rtol);
+              sumsq = sumsq + sc * sc;
+            }
+            const float scaled_error = mtgp_sqrtf(sumsq / (float)DT);
+            keep = (scaled_error < 1.0f) || at_dtmin;
+            const float inv_err = (scaled_error == 0.0f) ? mtgp_inff() : 1.0f / scaled_error;
+            const float factor1 = (P.coeff1 == 0.0f) ? 1.0f : mtgp_expf(P.coeff1 * mtgp_logf(inv_err));
+            const float factor2 = (P.coeff2 == 0.0f) ? 1.0f : mtgp_expf(P.coeff2 * mtgp_logf(prev_inv));
+            const float factor3 = (P.coeff3 == 0.0f) ? 1.0f : mtgp_expf(P.coeff3 * mtgp_logf(prev_prev_inv));
+            const float fmin = keep ? 1.0f : P.factormin;
+            float factor = ((P.safety * factor1) * factor2) * factor3;
+            factor = clip_jnp(factor, fmin, P.factormax);
+            float ndt = dt * factor;
+            if (P.dtmin > 0.0f) {
+              at_dtmin = (ndt <= P.dtmin);
+              ndt = (ndt != ndt) ? ndt : (ndt > P.dtmin ? ndt : P.dtmin);
+            }
+            new_tprev = keep ? tnext : tprev;
+            new_tnext = new_tprev + ndt;
+            if (keep && active) { prev_prev_inv = prev_inv; prev_inv = inv_err; }
+            nan_err = (scaled_error != scaled_error);
           }
-          new_tprev = keep ? tnext : tprev;
-          new_tnext = new_tprev + ndt;
-          if (keep && active) { prev_prev_inv = prev_inv; prev_inv = inv_err; }
-          nan_err = (scaled_error != scaled_error);
+          new_tprev = new_tprev < t1 ? new_tprev : t1;
+          {
+            const bool clip = new_tnext > t1 - 1e-6f;
+            const float tclip = keep ? t1 : new_tprev + 0.5f * (t1 - new_tprev);
+            new_tnext = clip ? tclip : new_tnext;
+          }
         }
-        new_tprev = new_tprev < t1 ? new_tprev : t1;
-        {
-          const bool clip = new_tnext > t1 - 1e-6f;
-          const float tclip = keep ? t1 : new_tprev + 0.5f * (t1 - new_tprev);
-          new_tnext = clip ? tclip : new_tnext;
-        }
-        const bool commit = active && keep && !nan_err;
-        // ---- SaveAt(ts) on accepted steps: every lane has its own pending save points ----
+        const bool commit = stepping && active && keep && !nan_err;
+        // ---- SaveAt(ts): every lane has its own pending save points ----
         while (true) {
-          const bool pending = commit && (k < K) && (ts[k < K ? k : K - 1] <= tnext);
+          const int kk = k < K ? k : K - 1;
+          const float tk = ts[kk];
+          const bool pending = (k < K) && (stepping ? (commit && tk <= tnext) : true);
           if (__ballot_sync(0xFFFFFFFFu, pending) == 0u) break;
-          const float tk = ts[k < K ? k : K - 1];
           const float th = (tprev == tnext) ? 0.0f : (tk - tprev) / (tnext - tprev);
           for (int i = 0; i < DT; i++) {
             const float y0 = Y[i * 32], y1 = Y1[i * 32];
@@ -326,35 +337,30 @@ __global__ void __launch_bounds__(kRkWarps * 32) k_rollout_rk(const RolloutParam
               const float cq = ((((f1 - (4.0f * f0)) - (11.0f * y0)) - (5.0f * y1))) + (16.0f * ymid);
               v = ((((a * th + bq) * th + cq) * th + f0) * th) + y0;
             }
-            SV[i * 32] = v;
+            SV[i * 32] = stepping ? v : mtgp_inff();  // drained save points keep the inf pre-fill
           }
           save_point(pending, SV);
           if (pending) k++;
         }
-        // ---- Event + commit ----
-        const bool bad = bad_state(Y1);
-        const bool fired = (bad != ev_old_bad);
-        if (commit) {
-          ev_old_bad = bad;
-          my_steps += (pass == 0 && lane_valid) ? 1u : 0u;
-          for (int i = 0; i < DT; i++) {
-            Y[i * 32] = Y1[i * 32];
-            if (dopri) F0[i * 32] = YI[i * 32];  // unscaled f at (tnext, y1)
+        if (stepping) {
+          // ---- Event + commit ----
+          const bool bad = bad_state(Y1);
+          const bool fired = (bad != ev_old_bad);
+          if (commit) {
+            ev_old_bad = bad;
+            my_steps += (pass == 0 && lane_valid) ? 1u : 0u;
+            for (int i = 0; i < DT; i++) {
+              Y[i * 32] = Y1[i * 32];
+              if (dopri) F0[i * 32] = YI[i * 32];  // unscaled f at (tnext, y1)
+            }
+          }
+          if (active) {
+            num_steps++;
+            tprev = new_tprev;
+            tnext = new_tnext;
+            if ((commit && fired) || nan_err || !(tprev < t1) || num_steps >= P.max_steps) active = false;
           }
         }
-        if (active) {
-          num_steps++;
-          tprev = new_tprev;
-          tnext = new_tnext;
-          if ((commit && fired) || nan_err || !(tprev < t1) || num_steps >= P.max_steps) active = false;
-        }
-      }
-      // ---- save points the solve never reached keep the inf pre-fill ----
-      while (__ballot_sync(0xFFFFFFFFu, k < K) != 0u) {
-        const bool pending = k < K;
-        for (int i = 0; i < DT; i++) SV[i * 32] = mtgp_inff();
-        save_point(pending, SV);
-        if (pending) k++;
       }
       traj_fitness = (KIND == MTGP_EVAL_SR) ? sr_total / (float)K : env.cost_finish(K, fs_known);
       if (ENV != MTGP_ENV_ACROBOT || pass == 1) break;
