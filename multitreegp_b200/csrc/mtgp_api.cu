@@ -224,6 +224,7 @@ int mtgp_encode(const float* nodes, int nodes_stride, const float* coef, int coe
                 const mtgp_node_table* table, mtgp_bytecode out, void* stream) {
   int rc = validate_shape(P, T, N);
   if (rc) return rc;
+  if (P == 0) return MTGP_OK;  // an empty population is a legal no-op (buffers may be NULL)
   if ((rc = validate_table(table))) return rc;
   if (!nodes || !coef || nodes_stride < 3 || coef_stride < 1) {
     mtgp_set_error("mtgp_encode: nodes/coef must not be NULL, strides must be >= 3 / >= 1");
@@ -239,6 +240,7 @@ int mtgp_encode(const float* nodes, int nodes_stride, const float* coef, int coe
 int mtgp_decode(mtgp_bytecode in, int P, int T, int N, float* trees_out, void* stream) {
   int rc = validate_shape(P, T, N);
   if (rc) return rc;
+  if (P == 0) return MTGP_OK;  // an empty population is a legal no-op (buffers may be NULL)
   if (!trees_out || !in.op || !in.a || !in.b || !in.coef) {
     mtgp_set_error("mtgp_decode: NULL buffer");
     return MTGP_ERR_INVALID_ARGUMENT;
@@ -251,6 +253,7 @@ int mtgp_lower(mtgp_bytecode bc, int P, int T, int N, const mtgp_node_table* tab
                void* prog_out, uint32_t* meta_out, void* stream) {
   int rc = validate_shape(P, T, N);
   if (rc) return rc;
+  if (P == 0) return MTGP_OK;  // an empty population is a legal no-op (buffers may be NULL)
   if ((rc = validate_table(table))) return rc;
   return mtgp_launch_lower(bc, P, T, N, table, tmp_base, mtgp_lstride(N), static_cast<uint2*>(prog_out), meta_out,
                            (cudaStream_t)stream);
@@ -262,6 +265,7 @@ int mtgp_rollout(mtgp_bytecode bc, int P, int T, int N, const mtgp_node_table* t
                  unsigned long long* steps_done, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = validate_shape(P, T, N);
   if (rc) return rc;
+  if (P == 0) return MTGP_OK;  // an empty population is a legal no-op (buffers may be NULL)
   if ((rc = validate_table(table))) return rc;
   int tmp_base = 0;
   if ((rc = validate_rollout(desc, T, N, table, &tmp_base))) return rc;
@@ -284,6 +288,7 @@ int mtgp_population_fitness_ex(const float* nodes, int nodes_stride, const float
                                void* stream) {
   int rc = validate_shape(P, T, N);
   if (rc) return rc;
+  if (P == 0) return MTGP_OK;  // an empty population is a legal no-op (buffers may be NULL)
   if ((rc = validate_table(table))) return rc;
   int tmp_base = 0;
   if ((rc = validate_rollout(desc, T, N, table, &tmp_base))) return rc;
@@ -313,6 +318,7 @@ int mtgp_eval_pointwise(mtgp_bytecode bc, int P, int T, int N, const mtgp_node_t
                         void* workspace, size_t workspace_bytes, void* stream) {
   int rc = validate_shape(P, T, N);
   if (rc) return rc;
+  if (P == 0) return MTGP_OK;  // an empty population is a legal no-op (buffers may be NULL)
   if ((rc = validate_table(table))) return rc;
   if (!X || !Y || !fitness || n_points < 1 || n_vars < 1) {
     mtgp_set_error("pointwise: X, Y, fitness must not be NULL; n_points, n_vars >= 1");
@@ -345,6 +351,7 @@ int mtgp_population_fitness_pointwise(const float* nodes, int nodes_stride, cons
                                       size_t workspace_bytes, void* stream) {
   int rc = validate_shape(P, T, N);
   if (rc) return rc;
+  if (P == 0) return MTGP_OK;  // an empty population is a legal no-op (buffers may be NULL)
   if ((rc = validate_table(table))) return rc;
   if (!X || !Y || !fitness || !nodes || !coef || n_points < 1 || n_vars < 1) {
     mtgp_set_error("pointwise: NULL buffer or empty data set");
@@ -402,6 +409,7 @@ int mtgp_population_fitness_host(const float* population_host, int P, int T, int
                                  void* stream) {
   int rc = validate_shape(P, T, N);
   if (rc) return rc;
+  if (P == 0) return MTGP_OK;  // an empty population is a legal no-op (buffers may be NULL)
   if (!dh || !population_host || !fitness_host) { mtgp_set_error("NULL host buffer"); return MTGP_ERR_INVALID_ARGUMENT; }
   cudaStream_t s = (cudaStream_t)stream;
   const size_t pop_bytes = (size_t)P * T * N * 4 * sizeof(float);
@@ -456,6 +464,7 @@ int mtgp_population_fitness_pointwise_host(const float* population_host, int P, 
                                            float* fitness_host, void* stream) {
   int rc = validate_shape(P, T, N);
   if (rc) return rc;
+  if (P == 0) return MTGP_OK;  // an empty population is a legal no-op (buffers may be NULL)
   if (!population_host || !fitness_host || !X_host || !Y_host || n_points < 1 || n_vars < 1) {
     mtgp_set_error("NULL host buffer or empty data set");
     return MTGP_ERR_INVALID_ARGUMENT;
