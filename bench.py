@@ -425,28 +425,31 @@ def main():
 
 
 def bench_notebooks(eng, dev):
-    """BASELINE configs[1] and [2] with the solver settings the notebooks actually pass
-    (Dopri5 + PIDController(1e-4, 1e-4, dtmin=0.001), max_steps 1000): ms per evaluation and accepted
-    solver steps per second.  Small workloads (1 000 / 4 096 individuals) -- reported for completeness."""
+    """BASELINE configs[1] and [2] (StaticPolicy / DynamicPolicy notebooks, 1 000 x 16 and 4 096 x 32): ms per
+    evaluation with (a) the fixed-step Euler stepper the configs name (the evaluators' class default) and
+    (b) the solver settings the notebooks actually pass, Dopri5 + PIDController(1e-4, 1e-4, dtmin=1e-3),
+    max_steps 1000.  Small, latency-bound workloads -- reported for completeness, not as the headline."""
     import torch
     from multitreegp_b200.engine import DeviceData
     out = {}
     for name in ("c2", "c3"):
-        w = make_rollout_workload(name, seed=5)
-        d = w["data"]
-        d.solver, d.controller, d.rtol, d.atol, d.dtmin, d.max_steps = (abi.SOLVER_DOPRI5, abi.CONTROLLER_PID, 1e-4,
-                                                                          1e-4, 0.001, 1000)
-        pop_d, data_d, table = torch.from_numpy(w["pop"]).to(dev), DeviceData(d, dev), w["lib"].table()
-        for _ in range(2):
-            eng.rollout_fitness(pop_d, table, data_d, count_steps=True)
-        torch.cuda.synchronize(dev)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        o = eng.rollout_fitness(pop_d, table, data_d, count_steps=True)
-        b.record(); torch.cuda.synchronize(dev)
-        ms = a.elapsed_time(b)
-        out[name] = {"workload": w["desc"] + ", Dopri5 + PIDController(1e-4,1e-4,dtmin=1e-3), max_steps 1000 (as shipped)",
-                     "ms_per_evaluation": ms, "accepted_steps_per_s": int(o["steps"].item()) / (ms * 1e-3)}
+        for solver in ("euler", "dopri5_pid"):
+            w = make_rollout_workload(name, seed=5)
+            d = w["data"]
+            if solver == "dopri5_pid":
+                d.solver, d.controller, d.rtol, d.atol, d.dtmin, d.max_steps = (abi.SOLVER_DOPRI5, abi.CONTROLLER_PID,
+                                                                                  1e-4, 1e-4, 0.001, 1000)
+            pop_d, data_d, table = torch.from_numpy(w["pop"]).to(dev), DeviceData(d, dev), w["lib"].table()
+            for _ in range(3):
+                eng.rollout_fitness(pop_d, table, data_d, count_steps=True)
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            o = eng.rollout_fitness(pop_d, table, data_d, count_steps=True)
+            b.record(); torch.cuda.synchronize(dev)
+            ms = a.elapsed_time(b)
+            out[f"{name}_{solver}"] = {"workload": w["desc"], "solver": solver, "ms_per_evaluation": ms,
+                                       "solver_steps_per_s": int(o["steps"].item()) / (ms * 1e-3)}
     return out
 
 

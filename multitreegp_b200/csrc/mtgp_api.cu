@@ -119,6 +119,10 @@ int check_vars(const mtgp_node_table* t, int n_data) {
 
 int validate_rollout(const mtgp_rollout_desc* d, int T, int N, const mtgp_node_table* table, int* tmp_base) {
   if (!d) { mtgp_set_error("rollout descriptor is NULL"); return MTGP_ERR_INVALID_ARGUMENT; }
+  if (T > 32) {  // per-warp table of program offsets in the rollout kernels (kMaxTrees)
+    mtgp_set_error("rollout kernels support at most 32 trees per individual (got %d)", T);
+    return MTGP_ERR_UNSUPPORTED;
+  }
   if (d->B < 1 || d->K < 2) {
     mtgp_set_error("need B >= 1 trajectories and K >= 2 time points (got B=%d K=%d)", d->B, d->K);
     return MTGP_ERR_INVALID_ARGUMENT;
