@@ -44,7 +44,6 @@ struct PointwiseParams {
   int slots_per_warp;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <int R>
 __global__ void __launch_bounds__(kPwWarps * 32, MTGP_PW_MIN_CTAS) k_pointwise(const PointwiseParams P) {
