@@ -299,3 +299,94 @@ def test_dopri5_accuracy_and_adaptivity(oracle):
                 max_steps=8)
     assert np.isinf(short["xs"][0, :, -1]).all() and np.isfinite(short["xs"][0, :, 0]).all()
     assert (short["fitness"] == 1e4).all()
+
+
+def test_dynamic_acrobot_against_numpy_restatement(oracle):
+    """The C oracle's DynamicPolicy/Acrobot path (obs with noise and wrap, readout on [0,a,0], drift, state
+    equation on [y,a,u], Euler, SaveAt interpolation, post-pass, Acrobot cost) against an independent NumPy
+    float32 restatement written from the reference sources.  Short horizon, libm-vs-NumPy tolerance."""
+    rng = np.random.default_rng(17)
+    env = Acrobot(0.0, 0.1)
+    lib = util.control_library(env, abi.EVAL_DYNAMIC, state_size=2)
+    fns = np_reference.node_functions(lib)
+    P, B = 12, 3
+    pop = sample_population(rng, P, lib, 4, 30)
+    data = util.control_data(env, abi.EVAL_DYNAMIC, rng, B, 2.0, 0.2, 0.07, 2)   # dt0 does not divide the save spacing
+    oracle.set_math(oracle.MATH_LIBM)
+    try:
+        out = oracle.rollout_population(pop, lib.table(), data, trajectories=True)
+    finally:
+        oracle.set_math(oracle.MATH_CONTRACT)
+    checked = 0
+    for p in range(P):
+        for b in range(B):
+            key = data.obs_keys[b]
+
+            def noise_at(t, key=key):
+                fk = oracle.fold_in(key, int(np.float32(t).view(np.uint32)))
+                return (oracle.normal(fk, 4, True) * F32(0.1)).astype(F32)
+            xs, acts, us, fit = np_reference.dynamic_acrobot_rollout(pop[p], fns, 2, data.x0[b], data.ts, data.dt0,
+                                                                    data.params[b], noise_at)
+            ref_xs, ref_us = out["xs"][p, b], out["us"][p, b, :, 0]
+            fin = np.isfinite(xs).all(axis=1)
+            np.testing.assert_array_equal(fin, np.isfinite(ref_xs).all(axis=1))
+            np.testing.assert_allclose(ref_xs[fin], xs[fin], rtol=2e-4, atol=2e-4)
+            np.testing.assert_allclose(out["activities"][p, b][fin], acts[fin], rtol=2e-3, atol=2e-3)
+            ok = np.isfinite(us) & np.isfinite(ref_us)
+            np.testing.assert_allclose(ref_us[ok], us[ok], rtol=2e-3, atol=2e-3)
+            if np.isfinite(fit) and np.isfinite(out["traj_fitness"][p, b]):
+                np.testing.assert_allclose(out["traj_fitness"][p, b], fit, rtol=1e-3)
+            checked += 1
+    assert checked == P * B
+
+
+@pytest.mark.filterwarnings("ignore::RuntimeWarning")
+def test_reactor_against_numpy_restatement(oracle):
+    """StirredTankReactor drift (reactor.py:78-87, Arrhenius term, clipped control) and cost (:92-96) with a
+    constant policy: independent NumPy float32 Euler vs the oracle (libm mode)."""
+    from multitreegp_b200.environments.control_environments import StirredTankReactor
+    env = StirredTankReactor(0.0, 0.0)
+    lib = util.control_library(env, abi.EVAL_STATIC)
+    rng = np.random.default_rng(23)
+    B, h, u0 = 4, F32(0.002), F32(120.0)
+    x0, targets = env.sample_init_states(B, rng)
+    params = np.stack(env.sample_params(B, "Different", None, rng), 1)
+    ts = np.arange(0, 0.4, 0.02, dtype=F32)
+    data = RolloutData(kind=abi.EVAL_STATIC, env_id=env.env_id, x0=x0, ts=ts, dt0=float(h), max_fitness=1e4,
+                       targets=targets, params=params, n_obs=3)
+    oracle.set_math(oracle.MATH_LIBM)
+    try:
+        out = oracle.rollout_population(_const_policy_pop(lib, 10, float(u0)), lib.table(), data, trajectories=True)
+    finally:
+        oracle.set_math(oracle.MATH_CONTRACT)
+    for b in range(B):
+        Vol, Cp, dHr, UA, q, Tf, Tcf, Volc = [F32(v) for v in params[b]]
+        k = lambda T: F32(7.2e10) * np.exp(F32(-72750 / 8.314) / T)
+        x = x0[b].astype(F32)
+        t, saved, kk = F32(0), [], 0
+        tprev, tnext, t1 = F32(ts[0]), F32(ts[0] + h), F32(ts[-1])
+        while tprev < t1:
+            Tc, T, c = x
+            control = np.clip(u0, F32(0), F32(300))
+            dc = (q / Vol) * (F32(1.0) - c) - k(T) * c
+            dT = (q / Vol) * (Tf - T) + (-dHr / Cp) * k(T) * c + (UA / Vol / Cp) * (Tc - T)
+            dTc = (control / Volc) * (Tcf - Tc) + (UA / Volc / Cp) * (T - Tc)
+            x1 = (x + (tnext - tprev) * np.array([dTc, dT, dc], dtype=F32)).astype(F32)
+            while kk < len(ts) and ts[kk] <= tnext:
+                w = F32((ts[kk] - tprev) / (tnext - tprev))
+                saved.append((x + w * (x1 - x)).astype(F32)); kk += 1
+            x, tprev = x1, min(tnext, t1)
+            nn = F32(tnext + h)
+            tnext = t1 if nn > F32(t1 - F32(1e-6)) else nn
+            if not np.isfinite(x1).all():          # cond_fn_nan (reactor.py:98-99): the solve stops here
+                break
+        saved += [np.full(3, np.inf, F32)] * (len(ts) - len(saved))
+        xs = np.array(saved)
+        fin = np.isfinite(xs).all(axis=1)
+        np.testing.assert_array_equal(fin, np.isfinite(out["xs"][0, b]).all(axis=1))
+        np.testing.assert_allclose(out["xs"][0, b][fin], xs[fin], rtol=1e-5, atol=1e-4)
+        if fin.all():
+            cost = np.sum(0.01 * (xs[:, 1].astype(np.float64) - targets[b, 0]) ** 2 + 1e-4 * float(u0) ** 2)
+            np.testing.assert_allclose(out["traj_fitness"][0, b], cost, rtol=1e-4)
+        else:
+            assert not np.isfinite(out["traj_fitness"][0, b])
