@@ -428,3 +428,46 @@ def test_evaluation_driver_mirrors_evaluate_population(engine, oracle):
     fit_d, _ = drv.evaluate_population(_dev(engine, pops), data)
     np.testing.assert_array_equal(fit_d.cpu().numpy(), fit)
     assert drv.get_statistics(1)[0] == bf
+
+
+def test_sr_and_static_evaluator_classes(engine, oracle):
+    """SR_evaluator.Evaluator and feedforward_evaluate.Evaluator through their reference-facing methods, with
+    host (numpy) populations: __call__, evaluate_population (host C-ABI entry), evaluate_candidate."""
+    from multitreegp_b200.evaluators import SR_evaluator, feedforward_evaluate, pointwise_evaluate
+    from multitreegp_b200.environments.control_environments import StirredTankReactor
+    from multitreegp_b200.synthetic import van_der_pol_data, pointwise_data
+    rng = np.random.default_rng(51)
+    # --- symbolic regression on Van der Pol trajectories (SymbolicRegression.ipynb) ---
+    ev = SR_evaluator.Evaluator(dt0=0.01).bind(util.OPS_SR, [["x0", "x1"]], [2])
+    x0, ts, ys, keys = van_der_pol_data(rng, 6, 3.0, 0.2)
+    data = (x0, ts, ys, keys)
+    pop = util.sample_population(rng, 40, ev.library, 4, 30)
+    ref = oracle.rollout_population(pop, ev.library.table(), ev.rollout_data(data), trajectories=True)
+    np.testing.assert_allclose(ev.evaluate_population(pop, data), ref["fitness"], rtol=RTOL)
+    np.testing.assert_allclose(ev(pop[..., 3:], pop[..., :3], data, None), ref["fitness"], rtol=RTOL)
+    fit_b, pred = ev.evaluate_candidate(pop[7], data, None)
+    assert util.same_or_both_nan(pred, ref["xs"][7]).all() and util.same_or_both_nan(fit_b, ref["traj_fitness"][7]).all()
+    # --- static policy on the reactor, parameters as a tuple of 8 arrays like sample_params returns ---
+    env = StirredTankReactor(0.0, 0.05)
+    lib = util.control_library(env, abi.EVAL_STATIC)
+    ev = feedforward_evaluate.Evaluator(env, 0.002, library=lib)
+    B = 5
+    x0, targets = env.sample_init_states(B, rng)
+    ts = np.arange(0, 0.6, 0.04, dtype=np.float32)
+    keys = util.random_keys(rng, B)
+    data = (x0, ts, targets, keys, keys, env.sample_params(B, "Different", ts, rng))
+    pop = util.sample_population(rng, 24, lib, 4, 30)
+    ref = oracle.rollout_population(pop, lib.table(), ev.rollout_data(data), trajectories=True)
+    np.testing.assert_allclose(ev.evaluate_population(pop, data, 0.125),
+                               ref["fitness"] + np.float32(0.125) * oracle.live_count(pop), rtol=RTOL)
+    xs, ys_, us, fit_b = ev.evaluate_candidate(pop[3], data, None)
+    assert util.same_or_both_nan(xs, ref["xs"][3]).all() and util.same_or_both_nan(ys_, ref["ys"][3]).all()
+    assert util.same_or_both_nan(us, ref["us"][3]).all() and util.same_or_both_nan(fit_b, ref["traj_fitness"][3]).all()
+    # --- pointwise evaluator class ---
+    ev = pointwise_evaluate.Evaluator().bind(util.OPS_SR, [["x0", "x1"]], [1])
+    X, Y = pointwise_data(rng, 700, 2)
+    pop = util.sample_population(rng, 30, ev.library, 5, 40)
+    ref_f, ref_p = oracle.pointwise_population(pop, ev.library.table(), X, Y, predictions=True)
+    np.testing.assert_allclose(ev.evaluate_population(pop, (X, Y)), ref_f, rtol=RTOL)
+    f1, p1 = ev.evaluate_candidate(pop[4], (X, Y))
+    assert util.same_or_both_nan(p1, ref_p[4]).all() and abs(f1 - ref_f[4]) <= RTOL * abs(ref_f[4])
