@@ -365,6 +365,7 @@ def main():
     roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp32_peak, "traffic": ncu_traffic("k_rollout", P), "kernel": "k_rollout<DYNAMIC,ACROBOT,noise>",
                 "issue_slots_busy_pct_ncu": ncu_field("k_rollout", "issue_active_pct"),
+                "executed_fp32_frac_of_fma_peak_ncu": ncu_field("k_rollout", "executed_fp32_frac_of_fma_peak"),
                 "warp_instructions_per_warp_step_ncu": ncu_field("k_rollout", "warp_instructions_per_warp_step"),
                 "kernel_ms": kernel_ms, "ops_per_rollout_step": {"fp": flops, "int_prng": int_ops, "tree_ops": tree_ops},
                 "peak_note": f"non-tensor FP32: 148 SM x 128 lanes x 2 (FMA) x {sm_mhz:.0f} MHz ({peak_src} clock); "
