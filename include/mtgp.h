@@ -264,6 +264,20 @@ MTGP_API int mtgp_population_fitness_pointwise_host(const float* population_host
                                            float max_fitness, float size_parsimony,
                                            float* fitness_host, void* stream);
 
+/* What the strategy does with the gathered fitness vector, without a host round trip:
+ *   best_index = argmin(fitness) over the flattened population, best_fitness = fitness[best_index],
+ *   best_solution = population[best_index]                   (genetic_programming.py:426-431)
+ *   elite[s, :] = argsort(fitness[s, :])[:elite_size] per sub-population s, indices local to s
+ *                                                             (reproduction.py:82)
+ * with numpy / jax.numpy ordering: argmin returns the first index of the minimum and treats NaN as
+ * the minimum; argsort is stable, -0 == +0, NaN last.  fitness [device] [num_populations *
+ * population_size]; every output is optional (NULL) and [device]: best_index int32[1],
+ * best_fitness f32[1], elite int32[num_populations, elite_size]; population [device]
+ * [P, row_floats] and best_solution [device] [row_floats] go together (row_floats = T*N*4). */
+MTGP_API int mtgp_select(const float* fitness, int num_populations, int population_size, int elite_size,
+                         int32_t* best_index, float* best_fitness, int32_t* elite,
+                         const float* population, int row_floats, float* best_solution, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,8 @@ def lib() -> C.CDLL:
                                                     vp, vp, sz, vp]
     L.mtgp_population_fitness_pointwise_host.restype = i32
     L.mtgp_population_fitness_pointwise_host.argtypes = [vp, i32, i32, i32, tab, vp, vp, i32, i32, f32, f32, vp, vp]
+    L.mtgp_select.restype = i32
+    L.mtgp_select.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp]
     if L.mtgp_abi_version() != abi.MTGP_ABI_VERSION:
         raise RuntimeError("libmtgp_b200.so ABI version mismatch: rebuild with python -m multitreegp_b200.build")
     _LIB = L
@@ -79,4 +81,5 @@ EXPORTED_SYMBOLS = [
     "mtgp_bytecode_bytes", "mtgp_program_stride", "mtgp_encode", "mtgp_decode", "mtgp_lower",
     "mtgp_eval_pointwise", "mtgp_rollout", "mtgp_population_fitness", "mtgp_population_fitness_ex",
     "mtgp_population_fitness_host", "mtgp_population_fitness_pointwise", "mtgp_population_fitness_pointwise_host",
+    "mtgp_select",
 ]

@@ -191,3 +191,30 @@ class FitnessEngine:
                 pop.ctypes.data, P, T, N, C.byref(table), X.ctypes.data, Y.ctypes.data, X.shape[0], X.shape[1],
                 float(max_fitness), float(size_parsimony), fitness.ctypes.data, self._stream()))
         return fitness
+
+    # -- selection (the consumer of the fitness vector) ------------------------------------
+    def select(self, fitness: torch.Tensor, num_populations: int, elite_size: int = 0,
+               population: torch.Tensor | None = None):
+        """argmin / best candidate (genetic_programming.py:426-431) and the per-sub-population elite
+        indices (reproduction.py:82) without leaving the device.  ``fitness`` is the flat f32[P]
+        vector (or [num_populations, population_size]); ``population`` f32[P,T,N,4] is optional.
+        Returns (best_index i32[1], best_fitness f32[1], elite i32[num_populations, elite_size],
+        best_solution f32[T,N,4] | None) as device tensors -- nothing is synchronised."""
+        f = fitness.reshape(-1)
+        assert f.is_cuda and f.dtype == torch.float32 and f.is_contiguous()
+        P = f.numel()
+        assert P % num_populations == 0
+        best_i = torch.empty((1,), dtype=torch.int32, device=self.device)
+        best_f = torch.empty((1,), dtype=torch.float32, device=self.device)
+        elite = torch.empty((num_populations, elite_size), dtype=torch.int32, device=self.device)
+        best_sol, pop_ptr, row = None, None, 0
+        if population is not None:
+            assert population.is_cuda and population.dtype == torch.float32 and population.is_contiguous()
+            assert population.shape[0] == P
+            best_sol = torch.empty(tuple(population.shape[1:]), dtype=torch.float32, device=self.device)
+            pop_ptr, row = population.data_ptr(), best_sol.numel()
+        check(self.lib.mtgp_select(f.data_ptr(), num_populations, P // num_populations, elite_size,
+                                   best_i.data_ptr(), best_f.data_ptr(), elite.data_ptr() if elite_size else None,
+                                   pop_ptr, row, best_sol.data_ptr() if best_sol is not None else None,
+                                   self._stream()))
+        return best_i, best_f, elite, best_sol

@@ -45,14 +45,31 @@ class EvaluationDriver:
                                                   self.size_parsinomy)
         else:
             fitness = self.fitness_function.evaluate_population(flat, data, self.size_parsinomy)
-        best = int(fitness.argmin())
-        best_solution = flat[best]
+        if is_np:
+            best = int(np.argmin(fitness))
+            best_solution, best_fitness = flat[best], float(fitness[best])
+        else:
+            # device-resident generation: argmin + copy of the winner in one launch (mtgp_select);
+            # the only device->host traffic is the winning candidate, once per generation
+            eng = self.fitness_function._get_engine()
+            _, best_f, _, best_sol = eng.select(fitness, self.num_populations, 0, flat.contiguous())
+            best_solution, best_fitness = best_sol.cpu().numpy(), float(best_f.cpu()[0])
         if self.best_solutions is None:
             shape = (len(self.best_fitnesses),) + tuple(flat.shape[1:])
             self.best_solutions = np.zeros(shape, dtype=np.float32)
-        self.best_solutions[self.current_generation] = best_solution if is_np else best_solution.cpu().numpy()
-        self.best_fitnesses[self.current_generation] = float(fitness[best])
+        self.best_solutions[self.current_generation] = best_solution
+        self.best_fitnesses[self.current_generation] = best_fitness
         return fitness.reshape((self.num_populations, self.population_size)), populations
+
+    def elite(self, fitness, elite_size: int):
+        """Indices (local to each sub-population) of the ``elite_size`` fittest candidates,
+        ``argsort(fitness)[:elite_size]`` of reproduction.py:82, for fitness
+        [num_populations, population_size]: numpy in -> numpy out, CUDA tensor in -> CUDA tensor out."""
+        if isinstance(fitness, np.ndarray):
+            f = fitness.reshape(self.num_populations, self.population_size)
+            return np.argsort(f, axis=1, kind="stable")[:, :elite_size].astype(np.int32)
+        eng = self.fitness_function._get_engine()
+        return eng.select(fitness.contiguous(), self.num_populations, elite_size)[2]
 
     def next_generation(self) -> None:
         """The reference increments ``current_generation`` inside ``evolve`` (genetic_programming.py:496)."""

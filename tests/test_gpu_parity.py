@@ -471,3 +471,37 @@ def test_sr_and_static_evaluator_classes(engine, oracle):
     np.testing.assert_allclose(ev.evaluate_population(pop, (X, Y)), ref_f, rtol=RTOL)
     f1, p1 = ev.evaluate_candidate(pop[4], (X, Y))
     assert util.same_or_both_nan(p1, ref_p[4]).all() and abs(f1 - ref_f[4]) <= RTOL * abs(ref_f[4])
+
+
+def test_select_matches_numpy_ordering(engine):
+    """mtgp_select against numpy: argmin (first minimum, NaN counts as minimum; genetic_programming.py:426),
+    stable argsort per sub-population with -0 == +0 and NaN last (reproduction.py:82), gather of the winner."""
+    import torch
+    rng = np.random.default_rng(77)
+    for num_pop, pop_size, elite, special in [(1, 1, 1, False), (3, 20, 5, False), (4, 1000, 50, True),
+                                              (2, 65536, 16, True), (1, 37, 37, True)]:
+        f = rng.choice(np.array([0.0, 1.5, 3.25, 1e4, 7.0], np.float32), size=(num_pop, pop_size)) \
+            if pop_size < 100 else np.round(rng.normal(size=(num_pop, pop_size)) * 8).astype(np.float32) / 4
+        if special and pop_size > 30:
+            f[0, 5], f[0, 9], f[-1, 3], f[-1, 7] = -0.0, 0.0, np.inf, -np.inf
+            f[f == 0.25] = -0.0
+        pop = rng.normal(size=(num_pop * pop_size, 2, 5, 4)).astype(np.float32)
+        bi, bf, el, sol = engine.select(_dev(engine, f), num_pop, elite, _dev(engine, pop))
+        want_i = int(np.argmin(f.reshape(-1)))
+        assert int(bi.cpu()[0]) == want_i and float(bf.cpu()[0]) == f.reshape(-1)[want_i]
+        np.testing.assert_array_equal(sol.cpu().numpy(), pop[want_i])
+        np.testing.assert_array_equal(el.cpu().numpy(), np.argsort(f, axis=1, kind="stable")[:, :elite])
+    # NaN rules
+    f = np.array([[3.0, np.nan, 1.0, np.nan, -2.0, 1.0]], np.float32)
+    bi, bf, el, _ = engine.select(_dev(engine, f), 1, 6)
+    assert int(bi.cpu()[0]) == int(np.argmin(f)) == 1 and np.isnan(float(bf.cpu()[0]))
+    np.testing.assert_array_equal(el.cpu().numpy()[0], np.argsort(f[0], kind="stable"))
+    # argument errors
+    from multitreegp_b200._lib import MtgpError
+    with pytest.raises(MtgpError):
+        engine.select(_dev(engine, f), 1, 7)
+    # the driver's elite() helper
+    from multitreegp_b200.strategy_eval import EvaluationDriver
+    drv = EvaluationDriver(1, 6, type("E", (), {"_get_engine": lambda self: engine})(), num_populations=1)
+    np.testing.assert_array_equal(drv.elite(_dev(engine, f), 3).cpu().numpy(), drv.elite(f, 3))
+    assert isinstance(drv.elite(_dev(engine, f), 3), torch.Tensor)
