@@ -409,7 +409,7 @@ def main():
                        "executed_rollout_steps_per_step": steps_done / K,
                        "l2": "inputs larger than L2 (population 198 MB per GPU re-read from HBM every step)",
                        "step": "encode + lower + fused rollout" + (" + NCCL all-gather" if world > 1 else "")},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": (6 if args.obs_noise != 0.0 else 4) * K, "roofline": roofline}
+            "clocks": clocks, "e2e": e2e, "gpu_launches": (7 if args.obs_noise != 0.0 else 5) * K, "roofline": roofline}
 
     # ---- secondary metric of BASELINE.json: tree-node evals/s on the pointwise scale-up (configs[3]) ----
     if not args.no_secondary and world == 1:

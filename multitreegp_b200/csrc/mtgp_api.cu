@@ -51,6 +51,7 @@ struct Workspace {
   mtgp_bytecode bc;
   uint2* prog;
   uint32_t* meta;
+  int32_t* order;
   float* Xt;
   float* Yt;
   void* noise;
@@ -70,6 +71,7 @@ Workspace carve(void* ws, int P, int T, int N, int n_points_padded, int n_vars, 
   w.bc.flags = c.take<uint8_t>(trees);
   w.prog = c.take<uint2>(trees * (size_t)mtgp_lstride(N));
   w.meta = c.take<uint32_t>(trees);
+  w.order = c.take<int32_t>((size_t)P);
   w.Xt = c.take<float>((size_t)n_points_padded * (n_vars > 0 ? n_vars : 0));
   w.Yt = c.take<float>((size_t)n_points_padded * T);
   w.noise = noise_bytes ? c.take<unsigned char>(noise_bytes) : nullptr;
@@ -281,7 +283,7 @@ int mtgp_rollout(mtgp_bytecode bc, int P, int T, int N, const mtgp_node_table* t
   }
   cudaStream_t s = (cudaStream_t)stream;
   if ((rc = mtgp_launch_lower(bc, P, T, N, table, tmp_base, mtgp_lstride(N), w.prog, w.meta, s))) return rc;
-  mtgp_programs progs{w.prog, w.meta, mtgp_lstride(N), tmp_base, mtgp_tmp_bound(N)};
+  mtgp_programs progs{w.prog, w.meta, mtgp_lstride(N), tmp_base, mtgp_tmp_bound(N), w.order};
   return mtgp_launch_rollout(progs, nullptr, P, T, N, *desc, 0.0f, fitness, traj, steps_done, w.noise, s);
 }
 
@@ -305,7 +307,7 @@ int mtgp_population_fitness_ex(const float* nodes, int nodes_stride, const float
   cudaStream_t s = (cudaStream_t)stream;
   if ((rc = mtgp_launch_encode(nodes, nodes_stride, coef, coef_stride, P, T, N, table, w.bc, s))) return rc;
   if ((rc = mtgp_launch_lower(w.bc, P, T, N, table, tmp_base, mtgp_lstride(N), w.prog, w.meta, s))) return rc;
-  mtgp_programs progs{w.prog, w.meta, mtgp_lstride(N), tmp_base, mtgp_tmp_bound(N)};
+  mtgp_programs progs{w.prog, w.meta, mtgp_lstride(N), tmp_base, mtgp_tmp_bound(N), w.order};
   return mtgp_launch_rollout(progs, w.bc.live, P, T, N, *desc, size_parsimony, fitness, traj, steps_done, w.noise, s);
 }
 
@@ -343,7 +345,7 @@ int mtgp_eval_pointwise(mtgp_bytecode bc, int P, int T, int N, const mtgp_node_t
   cudaStream_t s = (cudaStream_t)stream;
   if ((rc = mtgp_launch_transpose_points(X, Y, n_points, npad, n_vars, T, w.Xt, w.Yt, s))) return rc;
   if ((rc = mtgp_launch_lower(bc, P, T, N, table, tmp_base, mtgp_lstride(N), w.prog, w.meta, s))) return rc;
-  mtgp_programs progs{w.prog, w.meta, mtgp_lstride(N), tmp_base, mtgp_tmp_bound(N)};
+  mtgp_programs progs{w.prog, w.meta, mtgp_lstride(N), tmp_base, mtgp_tmp_bound(N), w.order};
   return mtgp_launch_pointwise(progs, nullptr, P, T, N, w.Xt, w.Yt, n_points, npad, n_vars, max_fitness, 0.0f,
                                fitness, pred, s);
 }
@@ -377,7 +379,7 @@ int mtgp_population_fitness_pointwise(const float* nodes, int nodes_stride, cons
   if ((rc = mtgp_launch_encode(nodes, nodes_stride, coef, coef_stride, P, T, N, table, w.bc, s))) return rc;
   if ((rc = mtgp_launch_transpose_points(X, Y, n_points, npad, n_vars, T, w.Xt, w.Yt, s))) return rc;
   if ((rc = mtgp_launch_lower(w.bc, P, T, N, table, tmp_base, mtgp_lstride(N), w.prog, w.meta, s))) return rc;
-  mtgp_programs progs{w.prog, w.meta, mtgp_lstride(N), tmp_base, mtgp_tmp_bound(N)};
+  mtgp_programs progs{w.prog, w.meta, mtgp_lstride(N), tmp_base, mtgp_tmp_bound(N), w.order};
   return mtgp_launch_pointwise(progs, w.bc.live, P, T, N, w.Xt, w.Yt, n_points, npad, n_vars, max_fitness,
                                size_parsimony, fitness, nullptr, s);
 }

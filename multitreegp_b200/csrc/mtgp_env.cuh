@@ -7,15 +7,19 @@
 
 namespace mtgp_dev {
 
-constexpr int kWarpsPerCta = 4;
+#ifndef MTGP_ROLLOUT_WARPS
+#define MTGP_ROLLOUT_WARPS 1
+#endif
+constexpr int kWarpsPerCta = MTGP_ROLLOUT_WARPS;  // one individual per warp; warps of a CTA share nothing but the launch
 #ifndef MTGP_ROLLOUT_MIN_CTAS
-#define MTGP_ROLLOUT_MIN_CTAS 7  // resident CTAs per SM the register allocation is tuned for
+#define MTGP_ROLLOUT_MIN_CTAS 28  // resident CTAs per SM the register allocation is tuned for
 #endif
 
 struct RolloutParams {
   const uint2* prog;
   const uint32_t* meta;
   const int32_t* live;
+  const int32_t* order;  // schedule slot -> individual, costliest first (k_cost_order); NULL = identity
   int lstride;
   int P, T;
   int B, K, n_obs, n_targets, n_params, state_size, max_steps;

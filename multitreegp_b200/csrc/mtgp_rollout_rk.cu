@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kRkWarps * 32) k_rollout_rk(const RolloutParam
   constexpr int DR = D > 0 ? D : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
-  const int ind = blockIdx.x * kRkWarps + wic;
+  const int slot = blockIdx.x * kRkWarps + wic;
   const size_t per_warp = (size_t)P.prog_words_per_warp * sizeof(uint2) + kMaxTrees * sizeof(int) +
                           (size_t)P.wide_cap * sizeof(mtgp_wide_instr) + (size_t)P.slots_per_warp * 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(kRkWarps * 32) k_rollout_rk(const RolloutParam
   mtgp_wide_instr* wide = reinterpret_cast<mtgp_wide_instr*>(woff + kMaxTrees);
   float* vf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(wide) +
                                        (size_t)P.wide_cap * sizeof(mtgp_wide_instr));
-  if (ind >= P.P) return;
+  if (slot >= P.P) return;
+  const int ind = P.order ? P.order[slot] : slot;
 
   // ---- stage + pre-decode the programs (same as K2) ----
   uint64_t* bar = bars + 2 * wic;

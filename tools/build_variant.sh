@@ -8,7 +8,7 @@ nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=fals
   -Xcompiler -fPIC -Xcompiler -fvisibility=hidden "$@" -Xptxas -v -c mtgp_$tu.cu -o /tmp/var_$name.o 2>&1 | grep -A2 -E "k_rolloutILi2ELi1ELi1|k_pointwiseILi8" | grep -E "Used|spill" | tr '\n' ' '
 echo " <- $name"
 objs=""
-for o in api encode rollout rollout_rk pointwise; do
+for o in api encode rollout rollout_rk pointwise select; do
   if [ "$o" == "$tu" ]; then objs="$objs /tmp/var_$name.o"; else objs="$objs ../build/mtgp_$o.o"; fi
 done
 nvcc -shared -o /root/repo/variants/libmtgp_$name.so $objs -gencode arch=compute_100a,code=sm_100a -lcudart
