@@ -12,7 +12,7 @@ namespace mtgp_dev {
 #endif
 constexpr int kWarpsPerCta = MTGP_ROLLOUT_WARPS;  // one individual per warp; warps of a CTA share nothing but the launch
 #ifndef MTGP_ROLLOUT_MIN_CTAS
-#define MTGP_ROLLOUT_MIN_CTAS 28  // resident CTAs per SM the register allocation is tuned for
+#define MTGP_ROLLOUT_MIN_CTAS 32  // resident one-warp CTAs per SM the register allocation is tuned for (64 registers)
 #endif
 
 struct RolloutParams {
