@@ -158,10 +158,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
     }
     mbar_expect_tx(bar, total);
     int off = 0;
+    uint32_t soff = 0;  // compact programs are staged back to back (16-byte granules)
     for (int t = 0; t < P.T; t++) {
       const uint32_t n = P.meta[(size_t)ind * P.T + t] & 0xFFFFu;
-      bulk_g2s(prog_s + (size_t)t * P.lstride, P.prog + ((size_t)ind * P.T + t) * P.lstride,
-               ((n + 2u) & ~1u) * 8u, bar);
+      bulk_g2s(prog_s + soff, P.prog + ((size_t)ind * P.T + t) * P.lstride, ((n + 2u) & ~1u) * 8u, bar);
+      soff += (n + 2u) & ~1u;
       woff[t] = off;
       off += (int)n + 1;
     }
@@ -174,10 +175,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
   // ---- pre-decode: compact (8 B) -> wide (32 B) instructions, once per individual -------------
   {
     const uint32_t scratch = (uint32_t)P.slots_per_warp - 1u;
+    uint32_t soff = 0;
     for (int t = 0; t < P.T; t++) {
       const int n = (int)(P.meta[(size_t)ind * P.T + t] & 0xFFFFu) + 1;  // including X_END
       mtgp_wide_instr* dst = wide + woff[t];
-      for (int i = lane; i < n; i += 32) dst[i] = mtgp_expand_instr(prog_s[(size_t)t * P.lstride + i], scratch);
+      for (int i = lane; i < n; i += 32) dst[i] = mtgp_expand_instr(prog_s[soff + i], scratch);
+      soff += ((uint32_t)n + 1u) & ~1u;
     }
   }
   __syncwarp();
@@ -398,6 +401,7 @@ template <int KIND, int ENV, int NOISE>
 int launch_one(RolloutParams rp, int tmp_base, int n_tmp, int wide_cap, int want_fast, cudaStream_t stream) {
   rp.slots_per_warp = tmp_base + n_tmp + 1;
   rp.wide_cap = wide_cap;
+  rp.prog_words_per_warp = (wide_cap + rp.T + 1) & ~1;  // sum over trees of (n + 2) & ~1 <= instructions + T
   rp.want_fast = want_fast;
   const size_t smem = rollout_smem(rp);
   if (smem > 227 * 1024) {
