@@ -118,3 +118,43 @@ int mtgp_launch_lower(mtgp_bytecode bc, int P, int T, int N, const mtgp_node_tab
 #undef LOWER
   return mtgp_check_launch("k_lower");
 }
+
+// ---- cost-ordered schedule ------------------------------------------------------------------------------
+// A warp's (rollout) or CTA's (pointwise) run time grows with the instructions of its individuals'
+// programs: a 60-instruction individual takes several times as long as a 5-instruction one.  CTAs are
+// dispatched in blockIdx order, so handing out the individuals costliest-first (longest-processing-
+// time-first) keeps the last wave short; it also makes neighbours alike, which the pointwise kernel's
+// groups of 8 and its launch classes profit from.  One CTA, counting sort on the total instruction
+// count: order[slot] = individual.
+namespace {
+constexpr int kCostBins = 256;
+__global__ void __launch_bounds__(1024) k_cost_order(const uint32_t* __restrict__ meta, int P, int T,
+                                                     int32_t* __restrict__ order) {
+  __shared__ int bin_start[kCostBins];
+  for (int i = threadIdx.x; i < kCostBins; i += blockDim.x) bin_start[i] = 0;
+  __syncthreads();
+  auto cost_bin = [&](int ind) {
+    int c = 0;
+    for (int t = 0; t < T; t++) c += (int)(meta[(size_t)ind * T + t] & 0xFFFFu) + 1;
+    return kCostBins - 1 - min(c, kCostBins - 1);  // bin 0 = costliest
+  };
+  for (int i = threadIdx.x; i < P; i += blockDim.x) atomicAdd(&bin_start[cost_bin(i)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int b = 0; b < kCostBins; b++) {
+      const int n = bin_start[b];
+      bin_start[b] = run;
+      run += n;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < P; i += blockDim.x) order[atomicAdd(&bin_start[cost_bin(i)], 1)] = i;
+}
+}  // namespace
+
+int mtgp_launch_cost_order(const uint32_t* meta, int P, int T, int32_t* order, cudaStream_t stream) {
+  if (P == 0) return MTGP_OK;
+  k_cost_order<<<1, 1024, 0, stream>>>(meta, P, T, order);
+  return mtgp_check_launch("k_cost_order");
+}

@@ -26,6 +26,9 @@ int mtgp_launch_decode(mtgp_bytecode in, int P, int T, int N, float* trees_out, 
 int mtgp_launch_lower(mtgp_bytecode bc, int P, int T, int N, const mtgp_node_table* table, int tmp_base,
                       int lstride, uint2* prog, uint32_t* meta, cudaStream_t stream);
 
+// order[slot] = individual, costliest (most instructions) first; see mtgp_encode.cu
+int mtgp_launch_cost_order(const uint32_t* meta, int P, int T, int32_t* order, cudaStream_t stream);
+
 struct mtgp_programs {
   const uint2* prog;     // [P*T, lstride]
   const uint32_t* meta;  // [P*T]  n_instr | n_tmp_slots << 16

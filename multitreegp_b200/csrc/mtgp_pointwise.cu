@@ -28,6 +28,7 @@ struct PointwiseParams {
   const uint2* prog;
   const uint32_t* meta;
   const int32_t* live;
+  const int32_t* order;  // schedule slot -> individual (cost-ordered), NULL = identity
   int lstride;
   int P, T;
   const float* Xt;  // [n_vars, npad]
@@ -49,6 +50,7 @@ template <int R>
 __global__ void __launch_bounds__(kPwWarps * 32, MTGP_PW_MIN_CTAS) k_pointwise(const PointwiseParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_need[kPwGroup];
+  __shared__ int s_ind[kPwGroup];  // the individuals of this CTA's group
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const int ind0 = blockIdx.x * kPwGroup;
   const int G = min(kPwGroup, P.P - ind0);
@@ -61,9 +63,11 @@ __global__ void __launch_bounds__(kPwWarps * 32, MTGP_PW_MIN_CTAS) k_pointwise(c
   if (threadIdx.x < kPwGroup) {
     int mine = 0;
     if ((int)threadIdx.x < G) {
+      const int ind = P.order ? P.order[ind0 + threadIdx.x] : ind0 + (int)threadIdx.x;
+      s_ind[threadIdx.x] = ind;
       int need = 0, len = 0;
       for (int t = 0; t < P.T; t++) {
-        const uint32_t m = P.meta[(size_t)(ind0 + threadIdx.x) * P.T + t];
+        const uint32_t m = P.meta[(size_t)ind * P.T + t];
         need = max(need, (int)(m >> 16));
         len = max(len, (int)(m & 0xFFFFu) + 1);
       }
@@ -81,7 +85,7 @@ __global__ void __launch_bounds__(kPwWarps * 32, MTGP_PW_MIN_CTAS) k_pointwise(c
   // stage the programs of the group: only the instructions each tree actually has
   for (int gt = wic; gt < G * P.T; gt += kPwWarps) {
     if (!s_need[gt / P.T]) continue;
-    const size_t tree = (size_t)ind0 * P.T + gt;
+    const size_t tree = (size_t)s_ind[gt / P.T] * P.T + gt % P.T;
     const int n = (int)(P.meta[tree] & 0xFFFFu) + 1;
     const uint2* src = P.prog + tree * P.lstride;
     uint2* dst = prog_s + (size_t)gt * P.pstride;
@@ -130,7 +134,7 @@ __global__ void __launch_bounds__(kPwWarps * 32, MTGP_PW_MIN_CTAS) k_pointwise(c
         if (P.pred) {
 #pragma unroll
           for (int r = 0; r < R; r++)
-            if (pt0 + r < P.n_points) P.pred[((size_t)(ind0 + g) * P.n_points + pt0 + r) * P.T + t] = pr.v[r];
+            if (pt0 + r < P.n_points) P.pred[((size_t)s_ind[g] * P.n_points + pt0 + r) * P.T + t] = pr.v[r];
         }
       }
       float s = 0.0f;
@@ -157,10 +161,10 @@ __global__ void __launch_bounds__(kPwWarps * 32, MTGP_PW_MIN_CTAS) k_pointwise(c
       f = f < 0.0f ? 0.0f : (f > P.max_fitness ? P.max_fitness : f);
       if (P.live) {
         int cnt = 0;
-        for (int t = 0; t < P.T; t++) cnt += P.live[(size_t)(ind0 + g) * P.T + t];
+        for (int t = 0; t < P.T; t++) cnt += P.live[(size_t)s_ind[g] * P.T + t];
         f = f + P.size_parsimony * (float)cnt;
       }
-      P.fitness[ind0 + g] = f;
+      P.fitness[s_ind[g]] = f;
     }
   }
 }
@@ -215,6 +219,10 @@ int mtgp_launch_pointwise(const mtgp_programs& progs, const int32_t* live, int P
   pp.max_fitness = max_fitness; pp.size_parsimony = size_parsimony;
   pp.fitness = fitness; pp.pred = pred;
   pp.tmp_base = progs.tmp_base;
+  if (progs.order) {  // groups of similar cost, costliest first
+    if (int rc = mtgp_launch_cost_order(progs.meta, P, T, progs.order, stream)) return rc;
+    pp.order = progs.order;
+  }
   // Three provisioning classes, smallest first; each launch skips the individuals of the others.
   //   fast   : <= 4 temporaries, <= 32 instructions per tree (every tree of ordinary size and depth):
   //            R points per lane, small shared-memory footprint, 6-8 resident CTAs per SM

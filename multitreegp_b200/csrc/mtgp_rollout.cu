@@ -82,36 +82,6 @@ __global__ void __launch_bounds__(256) k_noise_table(const RolloutParams P, cons
     if (i < P.n_obs) table[((size_t)r * P.B + b) * 4 + i] = nt[i];
 }
 
-// ---- cost-ordered schedule ------------------------------------------------------------------------------
-// One warp's run time grows with the instructions of its individual's programs (a 60-instruction
-// individual takes several times as long as a 5-instruction one).  CTAs are dispatched in blockIdx
-// order, so handing out the individuals costliest-first (longest-processing-time-first) keeps the
-// last wave short.  One CTA, counting sort on the total instruction count: order[slot] = individual.
-constexpr int kCostBins = 256;
-__global__ void __launch_bounds__(1024) k_cost_order(const uint32_t* __restrict__ meta, int P, int T,
-                                                     int32_t* __restrict__ order) {
-  __shared__ int bin_start[kCostBins];
-  for (int i = threadIdx.x; i < kCostBins; i += blockDim.x) bin_start[i] = 0;
-  __syncthreads();
-  auto cost_bin = [&](int ind) {
-    int c = 0;
-    for (int t = 0; t < T; t++) c += (int)(meta[(size_t)ind * T + t] & 0xFFFFu) + 1;
-    return kCostBins - 1 - min(c, kCostBins - 1);  // bin 0 = costliest
-  };
-  for (int i = threadIdx.x; i < P; i += blockDim.x) atomicAdd(&bin_start[cost_bin(i)], 1);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int run = 0;
-    for (int b = 0; b < kCostBins; b++) {
-      const int n = bin_start[b];
-      bin_start[b] = run;
-      run += n;
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < P; i += blockDim.x) order[atomicAdd(&bin_start[cost_bin(i)], 1)] = i;
-}
-
 // ---- the kernel ----------------------------------------------------------------------------------
 template <int KIND, int ENV, int NOISE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_rollout(const RolloutParams P) {
@@ -500,8 +470,7 @@ int mtgp_launch_rollout(const mtgp_programs& progs, const int32_t* live, int P, 
   rp.prog = progs.prog; rp.meta = progs.meta; rp.live = live; rp.lstride = progs.lstride;
   rp.P = P; rp.T = T;
   if (progs.order) {
-    k_cost_order<<<1, 1024, 0, stream>>>(progs.meta, P, T, progs.order);
-    if (int rc = mtgp_check_launch("k_cost_order")) return rc;
+    if (int rc = mtgp_launch_cost_order(progs.meta, P, T, progs.order, stream)) return rc;
     rp.order = progs.order;
   }
   rp.B = d.B; rp.K = d.K; rp.n_obs = d.n_obs; rp.n_targets = d.n_targets; rp.n_params = d.n_params;
