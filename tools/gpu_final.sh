@@ -1,18 +1,27 @@
 #!/bin/bash
-# full bench + ncu launch list + full captures of both interpreter kernels at the bench sizes
+# Round-end measurement, one profiler invocation per gpurun call:
+#   bash tools/gpu_final.sh bench      full bench.py line + the ncu launch list of the same command
+#   bash tools/gpu_final.sh rollout    ncu --set full capture of k_rollout at the bench size
+#   bash tools/gpu_final.sh pointwise  ncu --set full capture of k_pointwise at the bench size
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
-python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
-echo "bench rc=$?"; tail -2 gpurun_out/bench.err; cat gpurun_out/bench.json
-python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_launch.log 2>&1
-echo "ncu launches rc=$?"
-python bench.py --steps 1 --warmup 3 --no-secondary --no-cpu > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_rollout -s 6 -c 1 -f -o gpurun_out/prof_rollout_full \
-    python bench.py --steps 1 --warmup 3 --no-secondary --no-cpu > gpurun_out/ncu_full.log 2>&1
-echo "ncu rollout rc=$?"
-python bench.py --only-secondary --steps 2 > gpurun_out/plain3.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_pointwise -s 6 -c 1 -f -o gpurun_out/prof_pointwise_full \
-    python bench.py --only-secondary --steps 2 > gpurun_out/ncu_full2.log 2>&1
-echo "ncu pointwise rc=$?"
+case "$1" in
+bench)
+  python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
+  echo "bench rc=$?"; tail -2 gpurun_out/bench.err; cat gpurun_out/bench.json
+  python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/plain.log 2>&1 &&
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_launch.log 2>&1
+  echo "ncu launches rc=$?" ;;
+rollout)
+  python bench.py --steps 1 --warmup 3 --no-secondary --no-cpu > gpurun_out/plain2.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:k_rollout -s 6 -c 1 -f -o gpurun_out/prof_rollout_full \
+      python bench.py --steps 1 --warmup 3 --no-secondary --no-cpu > gpurun_out/ncu_full.log 2>&1
+  echo "ncu rollout rc=$?" ;;
+pointwise)
+  python bench.py --only-secondary --steps 2 > gpurun_out/plain3.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:k_pointwise -s 6 -c 1 -f -o gpurun_out/prof_pointwise_full \
+      python bench.py --only-secondary --steps 2 > gpurun_out/ncu_full2.log 2>&1
+  echo "ncu pointwise rc=$?" ;;
+*) echo "usage: gpu_final.sh bench|rollout|pointwise"; exit 2 ;;
+esac
