@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
   const mtgp_saddr lbytes = mtgp_saddr_of(lb);
   for (int s = 0; s < P.slots_per_warp; s++) lb[s * 32] = 0.0f;
   mbar_wait(bar, 0);
+  bool readout_reads_y = false;
   // ---- pre-decode: compact (8 B) -> wide (32 B) instructions, once per individual -------------
   {
     const uint32_t scratch = (uint32_t)P.slots_per_warp - 1u;
@@ -149,11 +150,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
     for (int t = 0; t < P.T; t++) {
       const int n = (int)(P.meta[(size_t)ind * P.T + t] & 0xFFFFu) + 1;  // including X_END
       mtgp_wide_instr* dst = wide + woff[t];
-      for (int i = lane; i < n; i += 32) dst[i] = mtgp_expand_instr(prog_s[soff + i], scratch);
+      for (int i = lane; i < n; i += 32) {
+        const uint2 c = prog_s[soff + i];
+        dst[i] = mtgp_expand_instr(c, scratch);
+        if (KIND == MTGP_EVAL_DYNAMIC && t == P.state_size) {
+          // does the readout read an observation or the control slot?  (conservative: unused operand fields count)
+          const uint32_t xk = (c.x >> 4) & 3u, yk = (c.x >> 6) & 3u, xs = (c.x >> 16) & 0xFFu, ys = c.x >> 24;
+          const bool rx = xk == OK_MEM && ((int)xs < P.n_obs || (int)xs == P.slot_u);
+          const bool ry = yk == OK_MEM && ((int)ys < P.n_obs || (int)ys == P.slot_u);
+          readout_reads_y |= (rx || ry) && (c.x & 15u) != X_END;
+        }
+      }
       soff += ((uint32_t)n + 1u) & ~1u;
     }
   }
   __syncwarp();
+  // The dynamic readout sees zeros for the observations and the control inside the step
+  // (dynamic_evaluate.py:113) and the saved observations in the post-pass (:100-101).  With the
+  // notebooks' variable lists it reads neither (only the latent state), and the slots need no care.
+  const bool readout_sees_y = (KIND == MTGP_EVAL_DYNAMIC) && (__any_sync(0xFFFFFFFFu, readout_reads_y) != 0);
 
   const float* ts = P.ts;
   const int K = P.K, NL = P.n_latent;
@@ -207,6 +222,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
       float tprev = t0, tnext = t0 + P.dt0;
       tnext = tnext < t1 ? tnext : t1;
       int steps = 0, k = 0;
+      unsigned int lane_steps = 0;  // steps this lane integrated before its event fired
       float ts_k = ts[0];  // ts[k], reloaded only when k advances
       // One iteration = one Euler step while any lane is still integrating, then the save points that
       // step covers.  Once the solve is over (t1 reached, max_steps, or every lane's event fired) the
@@ -226,7 +242,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
 #pragma unroll
               for (int i = 0; i < D; i++)
                 if (i < P.n_obs) lb[i * 32] = y[i];
-            } else {
+            } else if (readout_sees_y) {
 #pragma unroll
               for (int i = 0; i < D; i++)
                 if (i < P.n_obs) lb[i * 32] = 0.0f;
@@ -282,10 +298,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
             float ys[DR];
             env.template f_obs<NOISE>(tk, xs, ys, P.n_obs, P.obs_noise, P.partitionable,
                                       nz_base + (size_t)(P.cap_steps + k) * nzs, nzs);
+            if (KIND == MTGP_EVAL_STATIC || readout_sees_y) {
 #pragma unroll
-            for (int i = 0; i < D; i++)
-              if (i < P.n_obs) lb[i * 32] = ys[i];
-            if (KIND == MTGP_EVAL_DYNAMIC) lb[P.slot_u * 32] = 0.0f;  // zeros(control_size) (dynamic_evaluate.py:101)
+              for (int i = 0; i < D; i++)
+                if (i < P.n_obs) lb[i * 32] = ys[i];
+              if (KIND == MTGP_EVAL_DYNAMIC) lb[P.slot_u * 32] = 0.0f;  // zeros(control_size) (dynamic_evaluate.py:101)
+            }
             const float uk = mtgp_interpret_wide(prog_readout, lbytes);
             const float qk = (ENV == MTGP_ENV_ACROBOT) ? tk / dts : 0.0f;
             if (ENV == MTGP_ENV_ACROBOT && qk > (float)(k + 1)) viol = true;
@@ -314,7 +332,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
           // ---- commit ----
           if (alive) {
             ev_old_bad = bad;
-            my_steps += (pass == 0 && lane_valid) ? 1u : 0u;
+            lane_steps++;
             if (KIND != MTGP_EVAL_SR) {
 #pragma unroll
               for (int i = 0; i < D; i++) x[i] = x1[i];
@@ -332,6 +350,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
           steps++;
         }
       }
+      if (pass == 0 && lane_valid) my_steps += lane_steps;
       traj_fitness = (KIND == MTGP_EVAL_SR) ? sr_total / (float)K : env.cost_finish(K, fs_known);
       // Acrobot with a ts grid for which the running-prefix cost is not exact (ts[k]/dts > k+1
       // somewhere): redo the solve with first_success known.  Warp-uniform decision.

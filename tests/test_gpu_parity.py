@@ -111,6 +111,36 @@ def test_control_rollout_parity(engine, oracle, env_name, kind, obs_noise):
     assert int(gpu["steps"][0]) == ref["steps"]
 
 
+@pytest.mark.parametrize("env_name", ["harmonic", "acrobot"])
+@pytest.mark.parametrize("solver", ["euler", "dopri5_pid"])
+def test_dynamic_readout_that_reads_observations(engine, oracle, env_name, solver):
+    """dynamic_evaluate.py:113 / :100-101: inside the step the readout sees ZEROS for the observations and the
+    control, in the post-pass it sees the saved observations (and a zero control).  The notebooks' readout layer
+    only lists the latent variables, so this matters only for a readout layer that also lists y / u -- which the
+    reference allows.  The kernel skips the zero/restore traffic unless the program reads those slots."""
+    from multitreegp_b200.node_library import NodeLibrary
+    rng = np.random.default_rng(hash(("readout", env_name, solver)) % 2 ** 32)
+    env = util.ENVS[env_name](0.05, 0.1)
+    every = [f"y{i + 1}" for i in range(env.n_obs)] + ["a1", "a2", "u"] + [f"tar{i + 1}" for i in range(env.n_targets)]
+    lib = NodeLibrary(util.OPS_CONTROL, [every, every], [2, env.n_control])
+    pop = util.sample_population(rng, 96, lib, 4, 30)
+    data = util.control_data(env, abi.EVAL_DYNAMIC, rng, 8, 6.0, 0.2, 0.05, 2,
+                             "Constant" if env_name == "acrobot" else "Different", max_steps=1000)
+    if solver == "dopri5_pid":
+        util.with_solver(data, **util.DOPRI_PID)
+    # both kinds of readout are present: some read an observation / the control, some do not
+    y_or_u = [lib.string_to_node[v] for v in every if v[0] in "yu"]
+    reads = np.isin(pop[:, 2, :, 0].astype(np.int64), y_or_u).any(axis=1)
+    assert reads.any() and not reads.all()
+    ref = oracle.rollout_population(pop, lib.table(), data, trajectories=True)
+    gpu = _gpu_rollout(engine, lib, pop, data, trajectories=True, count_steps=True)
+    for k in ("xs", "ys", "us", "activities", "traj_fitness"):
+        ok = util.same_or_both_nan(gpu[k], ref[k])
+        assert ok.all(), f"{k}: {(~ok).sum()} of {ok.size} elements differ"
+    _assert_fitness(gpu["fitness"], ref["fitness"], 1e4)
+    assert int(gpu["steps"][0]) == ref["steps"]
+
+
 def test_inline_noise_generator_matches_the_table(engine, oracle, monkeypatch):
     """The rollout kernel normally reads the observation noise from a table computed once per
     evaluation; when the table would be too large it generates the noise in-kernel.  Same bits."""
