@@ -83,10 +83,11 @@ __global__ void __launch_bounds__(256) k_noise_table(const RolloutParams P, cons
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
-template <int KIND, int ENV, int NOISE>
+template <int KIND, int ENV, int NOISE, bool FULLOBS>  // FULLOBS: every state component is observed (n_obs == D)
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_rollout(const RolloutParams P) {
   constexpr int D = (KIND == MTGP_EVAL_SR) ? 0 : EnvDim<ENV>::D;
   constexpr int DR = D > 0 ? D : 1;
+  const int n_obs = FULLOBS ? D : P.n_obs;  // compile-time in the usual case: no per-component predicates
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const int slot = blockIdx.x * kWarpsPerCta + wic;
@@ -156,8 +157,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
         if (KIND == MTGP_EVAL_DYNAMIC && t == P.state_size) {
           // does the readout read an observation or the control slot?  (conservative: unused operand fields count)
           const uint32_t xk = (c.x >> 4) & 3u, yk = (c.x >> 6) & 3u, xs = (c.x >> 16) & 0xFFu, ys = c.x >> 24;
-          const bool rx = xk == OK_MEM && ((int)xs < P.n_obs || (int)xs == P.slot_u);
-          const bool ry = yk == OK_MEM && ((int)ys < P.n_obs || (int)ys == P.slot_u);
+          const bool rx = xk == OK_MEM && ((int)xs < n_obs || (int)xs == P.slot_u);
+          const bool ry = yk == OK_MEM && ((int)ys < n_obs || (int)ys == P.slot_u);
           readout_reads_y |= (rx || ry) && (c.x & 15u) != X_END;
         }
       }
@@ -236,16 +237,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
           float u = 0.0f;
           if (KIND != MTGP_EVAL_SR) {
             float y[DR];
-            env.template f_obs<NOISE>(tprev, x, y, P.n_obs, P.obs_noise, P.partitionable,
+            env.template f_obs<NOISE>(tprev, x, y, n_obs, P.obs_noise, P.partitionable,
                                       nz_base + (size_t)steps * nzs, nzs);
             if (KIND == MTGP_EVAL_STATIC) {
 #pragma unroll
               for (int i = 0; i < D; i++)
-                if (i < P.n_obs) lb[i * 32] = y[i];
+                if (i < n_obs) lb[i * 32] = y[i];
             } else if (readout_sees_y) {
 #pragma unroll
               for (int i = 0; i < D; i++)
-                if (i < P.n_obs) lb[i * 32] = 0.0f;
+                if (i < n_obs) lb[i * 32] = 0.0f;
               lb[P.slot_u * 32] = 0.0f;
             }
             u = mtgp_interpret_wide(prog_readout, lbytes);  // feedforward :107 / dynamic readout :113
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
             if (KIND == MTGP_EVAL_DYNAMIC) {
 #pragma unroll
               for (int i = 0; i < D; i++)
-                if (i < P.n_obs) lb[i * 32] = y[i];
+                if (i < n_obs) lb[i * 32] = y[i];
               lb[P.slot_u * 32] = u;
             }
           }
@@ -296,12 +297,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
             sr_total = sr_total + row;
           } else {
             float ys[DR];
-            env.template f_obs<NOISE>(tk, xs, ys, P.n_obs, P.obs_noise, P.partitionable,
+            env.template f_obs<NOISE>(tk, xs, ys, n_obs, P.obs_noise, P.partitionable,
                                       nz_base + (size_t)(P.cap_steps + k) * nzs, nzs);
             if (KIND == MTGP_EVAL_STATIC || readout_sees_y) {
 #pragma unroll
               for (int i = 0; i < D; i++)
-                if (i < P.n_obs) lb[i * 32] = ys[i];
+                if (i < n_obs) lb[i * 32] = ys[i];
               if (KIND == MTGP_EVAL_DYNAMIC) lb[P.slot_u * 32] = 0.0f;  // zeros(control_size) (dynamic_evaluate.py:101)
             }
             const float uk = mtgp_interpret_wide(prog_readout, lbytes);
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
               if (P.ys_o)
 #pragma unroll
                 for (int i = 0; i < D; i++)
-                  if (i < P.n_obs) P.ys_o[o * P.n_obs + i] = ys[i];
+                  if (i < n_obs) P.ys_o[o * n_obs + i] = ys[i];
               if (P.us_o) P.us_o[o] = uk;
             }
           }
@@ -386,7 +387,7 @@ size_t rollout_smem(const RolloutParams& rp) {
   return 16 * kWarpsPerCta + (size_t)kWarpsPerCta * per_warp;
 }
 
-template <int KIND, int ENV, int NOISE>
+template <int KIND, int ENV, int NOISE, bool FULLOBS>
 int launch_one(RolloutParams rp, int tmp_base, int n_tmp, int wide_cap, int want_fast, cudaStream_t stream) {
   rp.slots_per_warp = tmp_base + n_tmp + 1;
   rp.wide_cap = wide_cap;
@@ -397,7 +398,7 @@ int launch_one(RolloutParams rp, int tmp_base, int n_tmp, int wide_cap, int want
     mtgp_set_error("rollout needs %zu bytes of shared memory per CTA: over the 227 KB limit", smem);
     return MTGP_ERR_UNSUPPORTED;
   }
-  auto kern = k_rollout<KIND, ENV, NOISE>;
+  auto kern = k_rollout<KIND, ENV, NOISE, FULLOBS>;
   MTGP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned blocks = (unsigned)((rp.P + kWarpsPerCta - 1) / kWarpsPerCta);
   kern<<<blocks, kWarpsPerCta * 32, smem, stream>>>(rp);
@@ -433,9 +434,16 @@ int launch_kind_env(RolloutParams rp, int tmp_base, int bound, void* noise_ws, c
   rp.fast_tmp = all_fast ? bound : kFastTmp;
   rp.fast_instr = all_fast ? worst_instr : kFastInstr;
   int rc;
+  constexpr int ENVD = (KIND == MTGP_EVAL_SR) ? 0 : EnvDim<ENV>::D;
+  const bool full_obs = (KIND != MTGP_EVAL_SR) && rp.n_obs == ENVD;
 #define LAUNCH2(NZ)                                                                                  \
-  rc = launch_one<KIND, ENV, NZ>(rp, tmp_base, rp.fast_tmp, rp.fast_instr, 1, stream);                \
-  if (rc == MTGP_OK && !all_fast) rc = launch_one<KIND, ENV, NZ>(rp, tmp_base, bound, worst_instr, 0, stream);
+  if (full_obs) {                                                                                      \
+    rc = launch_one<KIND, ENV, NZ, true>(rp, tmp_base, rp.fast_tmp, rp.fast_instr, 1, stream);                \
+    if (rc == MTGP_OK && !all_fast) rc = launch_one<KIND, ENV, NZ, true>(rp, tmp_base, bound, worst_instr, 0, stream); \
+  } else {                                                                                             \
+    rc = launch_one<KIND, ENV, NZ, false>(rp, tmp_base, rp.fast_tmp, rp.fast_instr, 1, stream);               \
+    if (rc == MTGP_OK && !all_fast) rc = launch_one<KIND, ENV, NZ, false>(rp, tmp_base, bound, worst_instr, 0, stream); \
+  }
   if (noise == 0) { LAUNCH2(0) } else if (noise == 1) { LAUNCH2(1) } else { LAUNCH2(2) }
 #undef LAUNCH2
   return rc;
