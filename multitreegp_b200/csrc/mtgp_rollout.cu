@@ -83,11 +83,16 @@ __global__ void __launch_bounds__(256) k_noise_table(const RolloutParams P, cons
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
-template <int KIND, int ENV, int NOISE, bool FULLOBS>  // FULLOBS: every state component is observed (n_obs == D)
+// SPEC: launch-time facts promoted to compile time for the configurations the notebooks use
+//   0 generic; 1 every state component is observed (n_obs == D); 2 = 1 + a dynamic policy with two latent
+//   states (DynamicPolicy.ipynb: state_size = 2).  The per-component predicates and the latent loops vanish.
+template <int KIND, int ENV, int NOISE, int SPEC>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_rollout(const RolloutParams P) {
   constexpr int D = (KIND == MTGP_EVAL_SR) ? 0 : EnvDim<ENV>::D;
   constexpr int DR = D > 0 ? D : 1;
-  const int n_obs = FULLOBS ? D : P.n_obs;  // compile-time in the usual case: no per-component predicates
+  constexpr bool FULLOBS = SPEC >= 1;
+  constexpr bool FIXED_LATENT = (KIND == MTGP_EVAL_STATIC) || (KIND == MTGP_EVAL_DYNAMIC && SPEC == 2);
+  const int n_obs = FULLOBS ? D : P.n_obs;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const int slot = blockIdx.x * kWarpsPerCta + wic;
@@ -154,7 +159,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
       for (int i = lane; i < n; i += 32) {
         const uint2 c = prog_s[soff + i];
         dst[i] = mtgp_expand_instr(c, scratch);
-        if (KIND == MTGP_EVAL_DYNAMIC && t == P.state_size) {
+        if (KIND == MTGP_EVAL_DYNAMIC && t == P.state_size) {  // the readout tree
           // does the readout read an observation or the control slot?  (conservative: unused operand fields count)
           const uint32_t xk = (c.x >> 4) & 3u, yk = (c.x >> 6) & 3u, xs = (c.x >> 16) & 0xFFu, ys = c.x >> 24;
           const bool rx = xk == OK_MEM && ((int)xs < n_obs || (int)xs == P.slot_u);
@@ -172,14 +177,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
   const bool readout_sees_y = (KIND == MTGP_EVAL_DYNAMIC) && (__any_sync(0xFFFFFFFFu, readout_reads_y) != 0);
 
   const float* ts = P.ts;
-  const int K = P.K, NL = P.n_latent;
+  const int K = P.K;
+  const int NL = FIXED_LATENT ? (KIND == MTGP_EVAL_STATIC ? 0 : 2) : P.n_latent;
   // shared-space addresses of the latent-state slots of this lane (component j is 128 bytes further)
   const mtgp_saddr a_state = lbytes + 128u * (uint32_t)P.slot_state, a_out = lbytes + 128u * (uint32_t)P.slot_out,
                    a_lat = lbytes + 128u * (uint32_t)P.slot_lat;
   const float t0 = ts[0], t1 = ts[K - 1];
   const float dts = (K > 1) ? ts[1] - ts[0] : 0.0f;  // ts[1]-ts[0], acrobot.py:82
   const mtgp_saddr wide_s = mtgp_saddr_of(wide);
-  const mtgp_saddr prog_readout = wide_s + 32u * (uint32_t)woff[(KIND == MTGP_EVAL_DYNAMIC) ? P.state_size : 0];
+  const mtgp_saddr prog_readout = wide_s + 32u * (uint32_t)woff[(KIND == MTGP_EVAL_DYNAMIC) ? NL : 0];
   float fit_sum = 0.0f;
   unsigned int my_steps = 0;  // Euler steps integrated by this lane (< 2^32: max_steps is capped at 2^22 per solve)
 
@@ -387,7 +393,7 @@ size_t rollout_smem(const RolloutParams& rp) {
   return 16 * kWarpsPerCta + (size_t)kWarpsPerCta * per_warp;
 }
 
-template <int KIND, int ENV, int NOISE, bool FULLOBS>
+template <int KIND, int ENV, int NOISE, int SPEC>
 int launch_one(RolloutParams rp, int tmp_base, int n_tmp, int wide_cap, int want_fast, cudaStream_t stream) {
   rp.slots_per_warp = tmp_base + n_tmp + 1;
   rp.wide_cap = wide_cap;
@@ -398,7 +404,7 @@ int launch_one(RolloutParams rp, int tmp_base, int n_tmp, int wide_cap, int want
     mtgp_set_error("rollout needs %zu bytes of shared memory per CTA: over the 227 KB limit", smem);
     return MTGP_ERR_UNSUPPORTED;
   }
-  auto kern = k_rollout<KIND, ENV, NOISE, FULLOBS>;
+  auto kern = k_rollout<KIND, ENV, NOISE, SPEC>;
   MTGP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned blocks = (unsigned)((rp.P + kWarpsPerCta - 1) / kWarpsPerCta);
   kern<<<blocks, kWarpsPerCta * 32, smem, stream>>>(rp);
@@ -436,16 +442,19 @@ int launch_kind_env(RolloutParams rp, int tmp_base, int bound, void* noise_ws, c
   int rc;
   constexpr int ENVD = (KIND == MTGP_EVAL_SR) ? 0 : EnvDim<ENV>::D;
   const bool full_obs = (KIND != MTGP_EVAL_SR) && rp.n_obs == ENVD;
-#define LAUNCH2(NZ)                                                                                  \
-  if (full_obs) {                                                                                      \
-    rc = launch_one<KIND, ENV, NZ, true>(rp, tmp_base, rp.fast_tmp, rp.fast_instr, 1, stream);                \
-    if (rc == MTGP_OK && !all_fast) rc = launch_one<KIND, ENV, NZ, true>(rp, tmp_base, bound, worst_instr, 0, stream); \
-  } else {                                                                                             \
-    rc = launch_one<KIND, ENV, NZ, false>(rp, tmp_base, rp.fast_tmp, rp.fast_instr, 1, stream);               \
-    if (rc == MTGP_OK && !all_fast) rc = launch_one<KIND, ENV, NZ, false>(rp, tmp_base, bound, worst_instr, 0, stream); \
+  const int spec = !full_obs ? 0 : ((KIND == MTGP_EVAL_DYNAMIC && rp.state_size == 2) ? 2 : 1);
+#define LAUNCH1(NZ, SPEC)                                                                             \
+  {                                                                                                   \
+    rc = launch_one<KIND, ENV, NZ, SPEC>(rp, tmp_base, rp.fast_tmp, rp.fast_instr, 1, stream);        \
+    if (rc == MTGP_OK && !all_fast) rc = launch_one<KIND, ENV, NZ, SPEC>(rp, tmp_base, bound, worst_instr, 0, stream); \
   }
+#define LAUNCH2(NZ)                                                                                   \
+  if constexpr (KIND == MTGP_EVAL_SR) LAUNCH1(NZ, 0)                                                  \
+  else if constexpr (KIND == MTGP_EVAL_STATIC) { if (spec) LAUNCH1(NZ, 1) else LAUNCH1(NZ, 0) }       \
+  else { if (spec == 2) LAUNCH1(NZ, 2) else if (spec == 1) LAUNCH1(NZ, 1) else LAUNCH1(NZ, 0) }
   if (noise == 0) { LAUNCH2(0) } else if (noise == 1) { LAUNCH2(1) } else { LAUNCH2(2) }
 #undef LAUNCH2
+#undef LAUNCH1
   return rc;
 }
 
