@@ -166,10 +166,10 @@ __device__ __forceinline__ void sincos_contract(float x, float& s, float& c) {
 
 // ---- environments --------------------------------------------------------------------------------
 template <int ENV>
-struct EnvDim { static constexpr int D = 1; };
-template <> struct EnvDim<MTGP_ENV_ACROBOT> { static constexpr int D = 4; };
-template <> struct EnvDim<MTGP_ENV_HARMONIC> { static constexpr int D = 2; };
-template <> struct EnvDim<MTGP_ENV_REACTOR> { static constexpr int D = 3; };
+struct EnvDim { static constexpr int D = 1, NT = 0; };  // D state components, NT targets (acrobot.py:11, harmonic_oscillator.py:12, reactor.py:11)
+template <> struct EnvDim<MTGP_ENV_ACROBOT> { static constexpr int D = 4, NT = 0; };
+template <> struct EnvDim<MTGP_ENV_HARMONIC> { static constexpr int D = 2, NT = 1; };
+template <> struct EnvDim<MTGP_ENV_REACTOR> { static constexpr int D = 3, NT = 1; };
 
 template <int ENV>
 struct Env {

@@ -179,9 +179,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
   const float* ts = P.ts;
   const int K = P.K;
   const int NL = FIXED_LATENT ? (KIND == MTGP_EVAL_STATIC ? 0 : 2) : P.n_latent;
+  // slot map of the data vector (mtgp_rollout_slot_map); compile-time for SPEC == 2: [y(D) | a(2) | u | targets | out(2) | state(2)]
+  constexpr bool FIXED_SLOTS = (KIND == MTGP_EVAL_DYNAMIC && SPEC == 2);
+  constexpr int NT = (KIND == MTGP_EVAL_SR) ? 0 : EnvDim<ENV>::NT;
+  const int slot_lat = FIXED_SLOTS ? D : P.slot_lat, slot_u = FIXED_SLOTS ? D + 2 : P.slot_u,
+            slot_target = FIXED_SLOTS ? D + 3 : P.slot_target, slot_out = FIXED_SLOTS ? D + 3 + NT : P.slot_out,
+            slot_state = FIXED_SLOTS ? D + 5 + NT : P.slot_state;
   // shared-space addresses of the latent-state slots of this lane (component j is 128 bytes further)
-  const mtgp_saddr a_state = lbytes + 128u * (uint32_t)P.slot_state, a_out = lbytes + 128u * (uint32_t)P.slot_out,
-                   a_lat = lbytes + 128u * (uint32_t)P.slot_lat;
+  const mtgp_saddr a_state = lbytes + 128u * (uint32_t)slot_state, a_out = lbytes + 128u * (uint32_t)slot_out,
+                   a_lat = lbytes + 128u * (uint32_t)slot_lat;
   const float t0 = ts[0], t1 = ts[K - 1];
   const float dts = (K > 1) ? ts[1] - ts[0] : 0.0f;  // ts[1]-ts[0], acrobot.py:82
   const mtgp_saddr wide_s = mtgp_saddr_of(wide);
@@ -196,7 +202,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
     Env<ENV> env;
     if (KIND != MTGP_EVAL_SR) env.init(P, bb);
     if (KIND != MTGP_EVAL_SR)
-      for (int i = 0; i < P.n_targets; i++) lb[(P.slot_target + i) * 32] = P.targets[bb * P.n_targets + i];
+      for (int i = 0; i < P.n_targets; i++) lb[(slot_target + i) * 32] = P.targets[bb * P.n_targets + i];
     const float* nz_base = (NOISE == 1) ? P.noise + (size_t)bb * 4 : nullptr;
     const int nzs = P.B * 4;  // floats per table row
 
@@ -212,9 +218,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
       }
       for (int j = 0; j < NL; j++) {
         const float v = (KIND == MTGP_EVAL_SR) ? P.x0[bb * NL + j] : 0.0f;  // a0 = 0 (dynamic_evaluate.py:89)
-        lb[(P.slot_state + j) * 32] = v;
-        lb[(P.slot_lat + j) * 32] = v;
-        lb[(P.slot_out + j) * 32] = v;
+        lb[(slot_state + j) * 32] = v;
+        lb[(slot_lat + j) * 32] = v;
+        lb[(slot_out + j) * 32] = v;
       }
       if (KIND != MTGP_EVAL_SR) { env.sum = 0.0f; env.sum0 = 0.0f; env.fs = -1; }
       float sr_total = 0.0f;
@@ -222,7 +228,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
       {
         bool bad = false;
         if (KIND != MTGP_EVAL_SR) bad = env.bad_state(x);
-        for (int j = 0; j < NL; j++) bad |= !mtgp_isfinitef(lb[(P.slot_state + j) * 32]);
+        for (int j = 0; j < NL; j++) bad |= !mtgp_isfinitef(lb[(slot_state + j) * 32]);
         ev_old_bad = bad;  // Event: cond_fn at (t0, y0)
       }
       bool alive = true;
@@ -253,7 +259,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
 #pragma unroll
               for (int i = 0; i < D; i++)
                 if (i < n_obs) lb[i * 32] = 0.0f;
-              lb[P.slot_u * 32] = 0.0f;
+              lb[slot_u * 32] = 0.0f;
             }
             u = mtgp_interpret_wide(prog_readout, lbytes);  // feedforward :107 / dynamic readout :113
             float dx[DR];
@@ -264,7 +270,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
 #pragma unroll
               for (int i = 0; i < D; i++)
                 if (i < n_obs) lb[i * 32] = y[i];
-              lb[P.slot_u * 32] = u;
+              lb[slot_u * 32] = u;
             }
           }
           for (int j = 0; j < NL; j++) {  // latent trees: state equation (:116) / SR vector field
@@ -309,7 +315,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
 #pragma unroll
               for (int i = 0; i < D; i++)
                 if (i < n_obs) lb[i * 32] = ys[i];
-              if (KIND == MTGP_EVAL_DYNAMIC) lb[P.slot_u * 32] = 0.0f;  // zeros(control_size) (dynamic_evaluate.py:101)
+              if (KIND == MTGP_EVAL_DYNAMIC) lb[slot_u * 32] = 0.0f;  // zeros(control_size) (dynamic_evaluate.py:101)
             }
             const float uk = mtgp_interpret_wide(prog_readout, lbytes);
             const float qk = (ENV == MTGP_ENV_ACROBOT) ? tk / dts : 0.0f;
@@ -442,7 +448,13 @@ int launch_kind_env(RolloutParams rp, int tmp_base, int bound, void* noise_ws, c
   int rc;
   constexpr int ENVD = (KIND == MTGP_EVAL_SR) ? 0 : EnvDim<ENV>::D;
   const bool full_obs = (KIND != MTGP_EVAL_SR) && rp.n_obs == ENVD;
-  const int spec = !full_obs ? 0 : ((KIND == MTGP_EVAL_DYNAMIC && rp.state_size == 2) ? 2 : 1);
+  int spec = !full_obs ? 0 : ((KIND == MTGP_EVAL_DYNAMIC && rp.state_size == 2) ? 2 : 1);
+  if (spec == 2) {  // the kernel's compile-time slot map must be the launch's
+    constexpr int NT = (KIND == MTGP_EVAL_SR) ? 0 : EnvDim<ENV>::NT;
+    if (rp.slot_lat != ENVD || rp.slot_u != ENVD + 2 || rp.slot_target != ENVD + 3 || rp.slot_out != ENVD + 3 + NT ||
+        rp.slot_state != ENVD + 5 + NT || rp.n_latent != 2)
+      spec = 1;
+  }
 #define LAUNCH1(NZ, SPEC)                                                                             \
   {                                                                                                   \
     rc = launch_one<KIND, ENV, NZ, SPEC>(rp, tmp_base, rp.fast_tmp, rp.fast_instr, 1, stream);        \
