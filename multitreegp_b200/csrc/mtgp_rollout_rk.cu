@@ -37,7 +37,9 @@ __constant__ float DP_CMID[7] = {(float)(6025192743.0 / 30085553152.0 / 2), 0.0f
 constexpr int kRkWarps = 1;  // one warp per CTA: the adaptive workloads are small populations, fine-grained CTAs balance the SMs
 constexpr int kRkArrays = 12;  // Y, Y1, YI, F0, KS[0..6], SV
 
-template <int KIND, int ENV, bool NOISE>
+// SPEC as in k_rollout: 0 generic; 2 = every state component observed and the latent count known (static: 0,
+// dynamic: 2), so that D + n_latent, the solver-array offsets and the component loops are compile-time.
+template <int KIND, int ENV, bool NOISE, int SPEC>
 __global__ void __launch_bounds__(kRkWarps * 32) k_rollout_rk(const RolloutParams P) {
   constexpr int D = (KIND == MTGP_EVAL_SR) ? 0 : EnvDim<ENV>::D;
   constexpr int DR = D > 0 ? D : 1;
@@ -87,12 +89,14 @@ __global__ void __launch_bounds__(kRkWarps * 32) k_rollout_rk(const RolloutParam
   __syncwarp();
 
   const float* ts = P.ts;
-  const int K = P.K, NL = P.n_latent, DT = D + NL;
+  constexpr bool FIXED = (SPEC == 2) && (KIND != MTGP_EVAL_SR);
+  const int n_obs = FIXED ? D : P.n_obs;
+  const int K = P.K, NL = FIXED ? (KIND == MTGP_EVAL_STATIC ? 0 : 2) : P.n_latent, DT = D + NL;
   const float t0 = ts[0], t1 = ts[K - 1];
   const float dts = (K > 1) ? ts[1] - ts[0] : 0.0f;
   const bool dopri = P.solver == MTGP_SOLVER_DOPRI5, pid = P.controller == MTGP_CONTROLLER_PID;
   const mtgp_saddr wide_s = mtgp_saddr_of(wide);
-  const mtgp_saddr prog_readout = wide_s + 32u * (uint32_t)woff[(KIND == MTGP_EVAL_DYNAMIC) ? P.state_size : 0];
+  const mtgp_saddr prog_readout = wide_s + 32u * (uint32_t)woff[(KIND == MTGP_EVAL_DYNAMIC) ? NL : 0];
   // solver arrays in the value file: component i of array a is slot slot_rk + a*DT + i
   float* const Y = lb + (size_t)(P.slot_rk + 0 * DT) * 32;
   float* const Y1 = lb + (size_t)(P.slot_rk + 1 * DT) * 32;
@@ -119,15 +123,15 @@ __global__ void __launch_bounds__(kRkWarps * 32) k_rollout_rk(const RolloutParam
       if (KIND != MTGP_EVAL_SR) {
 #pragma unroll
         for (int i = 0; i < D; i++) x[i] = src[i * 32];
-        env.template f_obs<NOISE ? 2 : 0>(t, x, y, P.n_obs, P.obs_noise, P.partitionable, nullptr, 0);
+        env.template f_obs<NOISE ? 2 : 0>(t, x, y, n_obs, P.obs_noise, P.partitionable, nullptr, 0);
         if (KIND == MTGP_EVAL_STATIC) {
 #pragma unroll
           for (int i = 0; i < D; i++)
-            if (i < P.n_obs) lb[i * 32] = y[i];
+            if (i < n_obs) lb[i * 32] = y[i];
         } else {
 #pragma unroll
           for (int i = 0; i < D; i++)
-            if (i < P.n_obs) lb[i * 32] = 0.0f;
+            if (i < n_obs) lb[i * 32] = 0.0f;
           lb[P.slot_u * 32] = 0.0f;
         }
         const float u = mtgp_interpret_wide(prog_readout, lbytes);
@@ -140,7 +144,7 @@ __global__ void __launch_bounds__(kRkWarps * 32) k_rollout_rk(const RolloutParam
         if (KIND == MTGP_EVAL_DYNAMIC) {
 #pragma unroll
           for (int i = 0; i < D; i++)
-            if (i < P.n_obs) lb[i * 32] = y[i];
+            if (i < n_obs) lb[i * 32] = y[i];
           lb[P.slot_u * 32] = u;
         }
       }
@@ -202,10 +206,10 @@ __global__ void __launch_bounds__(kRkWarps * 32) k_rollout_rk(const RolloutParam
             lb[(P.slot_lat + j) * 32] = lat;
             if (doit && P.act_o && lane_valid && pass == 0) P.act_o[(((size_t)ind * P.B + b) * K + kk) * NL + j] = lat;
           }
-          env.template f_obs<NOISE ? 2 : 0>(tk, xs, ys, P.n_obs, P.obs_noise, P.partitionable, nullptr, 0);
+          env.template f_obs<NOISE ? 2 : 0>(tk, xs, ys, n_obs, P.obs_noise, P.partitionable, nullptr, 0);
 #pragma unroll
           for (int i = 0; i < D; i++)
-            if (i < P.n_obs) lb[i * 32] = ys[i];
+            if (i < n_obs) lb[i * 32] = ys[i];
           if (KIND == MTGP_EVAL_DYNAMIC) lb[P.slot_u * 32] = 0.0f;
           const float uk = mtgp_interpret_wide(prog_readout, lbytes);
           const float qk = (ENV == MTGP_ENV_ACROBOT) ? tk / dts : 0.0f;
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(kRkWarps * 32) k_rollout_rk(const RolloutParam
               if (P.ys_o)
 #pragma unroll
                 for (int i = 0; i < D; i++)
-                  if (i < P.n_obs) P.ys_o[o * P.n_obs + i] = ys[i];
+                  if (i < n_obs) P.ys_o[o * n_obs + i] = ys[i];
               if (P.us_o) P.us_o[o] = uk;
             }
           }
@@ -399,15 +403,24 @@ int launch_rk(RolloutParams rp, cudaStream_t stream) {
     return MTGP_ERR_UNSUPPORTED;
   }
   const unsigned blocks = (unsigned)((rp.P + kRkWarps - 1) / kRkWarps);
-  if (rp.obs_noise != 0.0f && KIND != MTGP_EVAL_SR) {
-    auto kern = k_rollout_rk<KIND, ENV, true>;
-    MTGP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<blocks, kRkWarps * 32, smem, stream>>>(rp);
-  } else {
-    auto kern = k_rollout_rk<KIND, ENV, false>;
-    MTGP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<blocks, kRkWarps * 32, smem, stream>>>(rp);
+  constexpr int ENVD = (KIND == MTGP_EVAL_SR) ? 0 : EnvDim<ENV>::D;
+  const bool fixed = (KIND != MTGP_EVAL_SR) && rp.n_obs == ENVD &&
+                     (KIND == MTGP_EVAL_STATIC ? rp.n_latent == 0 : rp.n_latent == 2);
+  const bool noise = rp.obs_noise != 0.0f && KIND != MTGP_EVAL_SR;
+#define RK_LAUNCH(NZ, SPEC)                                                                             \
+  {                                                                                                     \
+    auto kern = k_rollout_rk<KIND, ENV, NZ, SPEC>;                                                      \
+    MTGP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<blocks, kRkWarps * 32, smem, stream>>>(rp);                                                  \
   }
+  if constexpr (KIND == MTGP_EVAL_SR) {
+    RK_LAUNCH(false, 0)
+  } else if (fixed) {
+    if (noise) RK_LAUNCH(true, 2) else RK_LAUNCH(false, 2)
+  } else {
+    if (noise) RK_LAUNCH(true, 0) else RK_LAUNCH(false, 0)
+  }
+#undef RK_LAUNCH
   return mtgp_check_launch("k_rollout_rk");
 }
 
