@@ -192,6 +192,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
   const float dts = (K > 1) ? ts[1] - ts[0] : 0.0f;  // ts[1]-ts[0], acrobot.py:82
   const mtgp_saddr wide_s = mtgp_saddr_of(wide);
   const mtgp_saddr prog_readout = wide_s + 32u * (uint32_t)woff[(KIND == MTGP_EVAL_DYNAMIC) ? NL : 0];
+  mtgp_saddr prog_lat[2] = {wide_s, wide_s};  // FIXED_SLOTS: the two state-equation programs
+  if (FIXED_SLOTS) {
+    prog_lat[0] = wide_s + 32u * (uint32_t)woff[0];
+    prog_lat[1] = wide_s + 32u * (uint32_t)woff[1];
+  }
   float fit_sum = 0.0f;
   unsigned int my_steps = 0;  // Euler steps integrated by this lane (< 2^32: max_steps is capped at 2^22 per solve)
 
@@ -235,6 +240,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
       float tprev = t0, tnext = t0 + P.dt0;
       tnext = tnext < t1 ? tnext : t1;
       int steps = 0, k = 0;
+      const float* nz_step = nz_base;  // noise-table row of the current step
       unsigned int lane_steps = 0;  // steps this lane integrated before its event fired
       float ts_k = ts[0];  // ts[k], reloaded only when k advances
       // One iteration = one Euler step while any lane is still integrating, then the save points that
@@ -250,7 +256,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
           if (KIND != MTGP_EVAL_SR) {
             float y[DR];
             env.template f_obs<NOISE>(tprev, x, y, n_obs, P.obs_noise, P.partitionable,
-                                      nz_base + (size_t)steps * nzs, nzs);
+                                      nz_step, nzs);
             if (KIND == MTGP_EVAL_STATIC) {
 #pragma unroll
               for (int i = 0; i < D; i++)
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
             }
           }
           for (int j = 0; j < NL; j++) {  // latent trees: state equation (:116) / SR vector field
-            const float f = mtgp_interpret_wide(wide_s + 32u * (uint32_t)woff[j], lbytes);
+            const float f = mtgp_interpret_wide(FIXED_SLOTS ? prog_lat[j & 1] : wide_s + 32u * (uint32_t)woff[j], lbytes);
             mtgp_sts_f32(a_out + 128u * j, mtgp_lds_f32(a_state + 128u * j) + dt * f);
           }
           new_tprev = tnext < t1 ? tnext : t1;
@@ -361,6 +367,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
           tprev = new_tprev;
           tnext = new_tnext;
           steps++;
+          if (NOISE == 1) nz_step += nzs;
         }
       }
       if (pass == 0 && lane_valid) my_steps += lane_steps;
