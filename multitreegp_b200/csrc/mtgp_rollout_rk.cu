@@ -35,12 +35,15 @@ __constant__ float DP_CMID[7] = {(float)(6025192743.0 / 30085553152.0 / 2), 0.0f
                                  (float)(11237099.0 / 235043384.0 / 2)};
 
 constexpr int kRkWarps = 1;  // one warp per CTA: the adaptive workloads are small populations, fine-grained CTAs balance the SMs
-constexpr int kRkArrays = 12;  // Y, Y1, YI, F0, KS[0..6], SV
+// 12 solver arrays per lane: Y, Y1, YI, F0, KS[0..6], SV
 
 // SPEC as in k_rollout: 0 generic; 2 = every state component observed and the latent count known (static: 0,
 // dynamic: 2), so that D + n_latent, the solver-array offsets and the component loops are compile-time.
 template <int KIND, int ENV, bool NOISE, int SPEC>
-__global__ void __launch_bounds__(kRkWarps * 32) k_rollout_rk(const RolloutParams P) {
+#ifndef MTGP_RK_MIN_CTAS
+#define MTGP_RK_MIN_CTAS 20  // 96 registers: measured best on the DynamicPolicy notebook configuration
+#endif
+__global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(const RolloutParams P) {
   constexpr int D = (KIND == MTGP_EVAL_SR) ? 0 : EnvDim<ENV>::D;
   constexpr int DR = D > 0 ? D : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
