@@ -118,3 +118,13 @@ def test_product_never_imports_the_oracle():
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
             assert not re.search(r"#include\s+[\"<][^\">]*oracle", src), f"{f} includes oracle sources"
             assert "libmtgp_oracle" not in src and "pyoracle" not in src, f"{f} loads the oracle"
+
+
+def test_evaluation_driver_elite_numpy_path():
+    """EvaluationDriver.elite on host arrays is the reference's argsort(fitness)[:elite_size] per sub-population
+    (reproduction.py:82), stable; the device path (mtgp_select) is compared with it in the GPU suite."""
+    from multitreegp_b200.strategy_eval import EvaluationDriver
+    drv = EvaluationDriver(1, 4, fitness_function=None, num_populations=2)
+    f = np.array([[3.0, 1.0, 1.0, -0.0], [np.nan, 2.0, 0.0, 2.0]], np.float32)
+    np.testing.assert_array_equal(drv.elite(f, 3), [[3, 1, 2], [2, 1, 3]])
+    assert drv.elite(f, 3).dtype == np.int32
