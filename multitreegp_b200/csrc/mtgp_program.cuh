@@ -213,8 +213,8 @@ __host__ __device__ MTGP_COMPACT_INLINE Vec<R> mtgp_interpret(const uint2* __res
 //   ADD: c1 = 1, fy = 0         x*1 + y          SUB : c1 = 1, fy = sign   x*1 + (-y)
 //   RSUB: c1 = -1, fy = 0       x*(-1) + y       MUL : MP = ~0             x*y + (-0.0)
 //   LOAD: ADD with y = imm = -0.0                (all exact: one rounding, same bits as the plain op)
-// and the result is ALWAYS stored (to a scratch slot when nobody needs it), so there is no
-// predicate for it.  Everything else (div, max, min, transcendental, ...) takes a switch.
+// A result that a later instruction reads from the value file is stored by its producer (W_FAST_ST); the
+// slow operators always store (to a scratch slot when nobody needs the value).
 struct __align__(16) mtgp_wide_instr {
   uint4 a;  // .x = x byte offset | y byte offset << 16 (slot * 128)
             // .y = store byte offset | op << 16  (op: W_END, W_FAST, or a slow opcode)
@@ -222,9 +222,10 @@ struct __align__(16) mtgp_wide_instr {
   uint4 b;  // .x = MY: ~0 -> y from memory, 0 -> y = immediate      .y = c1: float bits of +1 / -1
             // .z = MP: ~0 -> multiply          .w = fy: 0 or 0x80000000
 };
+// W_FAST: fma path, result only needed by the next instruction (no store); W_FAST_ST: fma path + store
 enum mtgp_wop : uint32_t {
-  W_END = 0, W_FAST = 1, W_DIV = 2, W_RDIV = 3, W_MAX = 4, W_MIN = 5, W_SIN = 6, W_COS = 7, W_EXP = 8, W_LOG = 9,
-  W_SQRT = 10, W_TANH = 11, W_NEG = 12, W_ABS = 13, W_SQUARE = 14, W_LOADI = 15
+  W_END = 0, W_FAST = 1, W_FAST_ST = 2, W_DIV = 3, W_RDIV = 4, W_MAX = 5, W_MIN = 6, W_SIN = 7, W_COS = 8, W_EXP = 9,
+  W_LOG = 10, W_SQRT = 11, W_TANH = 12, W_NEG = 13, W_ABS = 14, W_SQUARE = 15, W_LOADI = 16
 };
 
 // compact -> wide.  `scratch_slot` receives the results nobody reads.
@@ -262,6 +263,7 @@ __host__ __device__ __forceinline__ mtgp_wide_instr mtgp_expand_instr(uint2 c, u
     uint32_t t = xk; xk = yk; yk = t;
     t = xs; xs = ys; ys = t;
   }
+  if (wop == W_FAST && st != MTGP_NO_SLOT) wop = W_FAST_ST;
   // after canonicalisation x is the accumulator or memory, y is memory or the immediate
   w.a.x = ((xk == OK_MEM ? xs : 0u) * 128u) | (((yk == OK_MEM ? ys : 0u) * 128u) << 16);
   w.a.y = ((st != MTGP_NO_SLOT ? st : scratch_slot) * 128u) | (wop << 16);
@@ -345,12 +347,13 @@ static __host__ __device__ MTGP_INTERP_INLINE float mtgp_interpret_wide(mtgp_sad
     prog += 32;
     a = mtgp_lds_v4(prog);
     b = mtgp_lds_v4(prog + 16);
-    if (ctl < ((W_FAST + 1u) << 16)) {
+    if (ctl < (W_FAST_ST << 16)) {
       acc = fmaf(mtgp_u2f(xb), mtgp_u2f(pb), mtgp_u2f(qb));
     } else {
-      acc = mtgp_wide_slow_op(ctl >> 16, mtgp_u2f(xb), mtgp_u2f(yb));
+      if (ctl < ((W_FAST_ST + 1u) << 16)) acc = fmaf(mtgp_u2f(xb), mtgp_u2f(pb), mtgp_u2f(qb));
+      else acc = mtgp_wide_slow_op(ctl >> 16, mtgp_u2f(xb), mtgp_u2f(yb));
+      mtgp_sts_f32(st, acc);
     }
-    mtgp_sts_f32(st, acc);
   }
   return acc;
 }
