@@ -71,7 +71,7 @@ Workspace carve(void* ws, int P, int T, int N, int n_points_padded, int n_vars, 
   w.bc.flags = c.take<uint8_t>(trees);
   w.prog = c.take<uint2>(trees * (size_t)mtgp_lstride(N));
   w.meta = c.take<uint32_t>(trees);
-  w.order = c.take<int32_t>((size_t)P);
+  w.order = c.take<int32_t>((size_t)P + 2);  // + the two slot counters of the persistent rollout launches
   w.Xt = c.take<float>((size_t)n_points_padded * (n_vars > 0 ? n_vars : 0));
   w.Yt = c.take<float>((size_t)n_points_padded * T);
   w.noise = noise_bytes ? c.take<unsigned char>(noise_bytes) : nullptr;

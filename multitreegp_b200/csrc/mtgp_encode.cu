@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(1024) k_cost_order(const uint32_t* __restrict_
   }
   __syncthreads();
   for (int i = threadIdx.x; i < P; i += blockDim.x) order[atomicAdd(&bin_start[cost_bin(i)], 1)] = i;
+  if (threadIdx.x < 2) order[P + threadIdx.x] = 0;  // slot counters of the persistent rollout launches
 }
 }  // namespace
 

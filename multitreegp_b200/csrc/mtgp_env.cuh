@@ -20,6 +20,7 @@ struct RolloutParams {
   const uint32_t* meta;
   const int32_t* live;
   const int32_t* order;  // schedule slot -> individual, costliest first (k_cost_order); NULL = identity
+  int* next_slot;        // persistent warps draw their next schedule slot from this counter (NULL: one slot per warp)
   int lstride;
   int P, T;
   int B, K, n_obs, n_targets, n_params, state_size, max_steps;

@@ -35,7 +35,7 @@ struct mtgp_programs {
   int lstride;           // instructions reserved per tree (even)
   int tmp_base;          // first temporary slot
   int n_tmp;             // temporary slots provisioned per warp
-  int32_t* order;        // [P] scratch for the cost-ordered schedule of the rollout kernels (may be NULL)
+  int32_t* order;        // [P + 2] scratch: cost-ordered schedule + two zeroed slot counters (may be NULL)
 };
 
 int mtgp_launch_rollout(const mtgp_programs& progs, const int32_t* live, int P, int T, int N,

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
   const int n_obs = FULLOBS ? D : P.n_obs;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
-  const int slot = blockIdx.x * kWarpsPerCta + wic;
+  const int slot0 = blockIdx.x * kWarpsPerCta + wic;
 
   // shared memory: [mbarriers][per warp: compact programs | tree offsets | wide programs | value file]
   const size_t per_warp = (size_t)P.prog_words_per_warp * sizeof(uint2) + kMaxTrees * sizeof(int) +
@@ -107,26 +107,38 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
   mtgp_wide_instr* wide = reinterpret_cast<mtgp_wide_instr*>(woff + kMaxTrees);
   float* vf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(wide) +
                                        (size_t)P.wide_cap * sizeof(mtgp_wide_instr));
-  if (slot >= P.P) return;  // whole warp leaves together (no block-wide barrier below)
+  // Persistent warps: every warp draws schedule slots (costliest individual first) from a global counter
+  // until the population is exhausted -- no CTA turnover between individuals.
+  uint64_t* bar = bars + 2 * wic;
+  if (lane == 0) mbar_init(bar, 1);
+  __syncwarp();
+  uint32_t bar_phase = 0;
+  bool first_round = true;
+  for (;;) {
+  int slot = slot0;  // the first individual comes with the launch; later ones from the counter
+  if (!first_round) {
+    if (!P.next_slot) return;
+    if (lane == 0) slot = (int)(gridDim.x * kWarpsPerCta) + atomicAdd(P.next_slot, 1);
+    slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
+  }
+  first_round = false;
+  if (slot >= P.P) return;  // whole warp leaves together (no block-wide barrier anywhere)
   const int ind = P.order ? P.order[slot] : slot;
 
   // which launch owns this individual: by the temporaries and instructions its programs need
-  int total_instr = 0;
   {
-    int need = 0;
+    int need = 0, total_instr = 0;
     for (int t = 0; t < P.T; t++) {
       const uint32_t m = P.meta[(size_t)ind * P.T + t];
       need = max(need, (int)(m >> 16));
       total_instr += (int)(m & 0xFFFFu) + 1;
     }
     const bool fast = (need <= P.fast_tmp) && (total_instr <= P.fast_instr);
-    if (fast != (P.want_fast != 0)) return;
+    if (fast != (P.want_fast != 0)) continue;
   }
 
   // ---- stage this individual's programs: cp.async.bulk -> shared, completion on an mbarrier ----
-  uint64_t* bar = bars + 2 * wic;
   if (lane == 0) {
-    mbar_init(bar, 1);
     uint32_t total = 0;
     for (int t = 0; t < P.T; t++) {
       const uint32_t n = P.meta[(size_t)ind * P.T + t] & 0xFFFFu;
@@ -147,7 +159,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
   float* lb = vf + lane;  // lane base of the value file (R = 1)
   const mtgp_saddr lbytes = mtgp_saddr_of(lb);
   for (int s = 0; s < P.slots_per_warp; s++) lb[s * 32] = 0.0f;
-  mbar_wait(bar, 0);
+  mbar_wait(bar, bar_phase);
+  bar_phase ^= 1u;
   bool readout_reads_y = false;
   // ---- pre-decode: compact (8 B) -> wide (32 B) instructions, once per individual -------------
   {
@@ -398,6 +411,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
     P.fitness[ind] = f;
     if (P.steps_done) atomicAdd(P.steps_done, warp_steps);
   }
+  __syncwarp();  // the value file and the program area are reused by the next individual
+  }  // persistent loop
+}
+
+int sm_count() {
+  static int n = 0;  // one device model per process
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
 }
 
 size_t rollout_smem(const RolloutParams& rp) {
@@ -419,7 +444,15 @@ int launch_one(RolloutParams rp, int tmp_base, int n_tmp, int wide_cap, int want
   }
   auto kern = k_rollout<KIND, ENV, NOISE, SPEC>;
   MTGP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const unsigned blocks = (unsigned)((rp.P + kWarpsPerCta - 1) / kWarpsPerCta);
+  unsigned blocks = (unsigned)((rp.P + kWarpsPerCta - 1) / kWarpsPerCta);
+  rp.next_slot = nullptr;
+#ifndef MTGP_NO_PERSISTENT
+  if (rp.order && blocks > (unsigned)(sm_count() * MTGP_ROLLOUT_MIN_CTAS)) {  // persistent: as many CTAs as can be resident, each warp loops over schedule slots
+    rp.next_slot = const_cast<int*>(rp.order) + rp.P + (want_fast ? 0 : 1);
+    const unsigned resident = (unsigned)(sm_count() * MTGP_ROLLOUT_MIN_CTAS);
+    blocks = blocks < resident ? blocks : resident;
+  }
+#endif
   kern<<<blocks, kWarpsPerCta * 32, smem, stream>>>(rp);
   return mtgp_check_launch("k_rollout");
 }
