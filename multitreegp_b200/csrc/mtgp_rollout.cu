@@ -115,303 +115,303 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
   uint32_t bar_phase = 0;
   bool first_round = true;
   for (;;) {
-  int slot = slot0;  // the first individual comes with the launch; later ones from the counter
-  if (!first_round) {
-    if (!P.next_slot) return;
-    if (lane == 0) slot = (int)(gridDim.x * kWarpsPerCta) + atomicAdd(P.next_slot, 1);
-    slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
-  }
-  first_round = false;
-  if (slot >= P.P) return;  // whole warp leaves together (no block-wide barrier anywhere)
-  const int ind = P.order ? P.order[slot] : slot;
+    int slot = slot0;  // the first individual comes with the launch; later ones from the counter
+    if (!first_round) {
+      if (!P.next_slot) return;
+      if (lane == 0) slot = (int)(gridDim.x * kWarpsPerCta) + atomicAdd(P.next_slot, 1);
+      slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
+    }
+    first_round = false;
+    if (slot >= P.P) return;  // whole warp leaves together (no block-wide barrier anywhere)
+    const int ind = P.order ? P.order[slot] : slot;
 
-  // which launch owns this individual: by the temporaries and instructions its programs need
-  {
-    int need = 0, total_instr = 0;
-    for (int t = 0; t < P.T; t++) {
-      const uint32_t m = P.meta[(size_t)ind * P.T + t];
-      need = max(need, (int)(m >> 16));
-      total_instr += (int)(m & 0xFFFFu) + 1;
+    // which launch owns this individual: by the temporaries and instructions its programs need
+    {
+      int need = 0, total_instr = 0;
+      for (int t = 0; t < P.T; t++) {
+        const uint32_t m = P.meta[(size_t)ind * P.T + t];
+        need = max(need, (int)(m >> 16));
+        total_instr += (int)(m & 0xFFFFu) + 1;
+      }
+      const bool fast = (need <= P.fast_tmp) && (total_instr <= P.fast_instr);
+      if (fast != (P.want_fast != 0)) continue;
     }
-    const bool fast = (need <= P.fast_tmp) && (total_instr <= P.fast_instr);
-    if (fast != (P.want_fast != 0)) continue;
-  }
 
-  // ---- stage this individual's programs: cp.async.bulk -> shared, completion on an mbarrier ----
-  if (lane == 0) {
-    uint32_t total = 0;
-    for (int t = 0; t < P.T; t++) {
-      const uint32_t n = P.meta[(size_t)ind * P.T + t] & 0xFFFFu;
-      total += ((n + 2u) & ~1u) * 8u;
+    // ---- stage this individual's programs: cp.async.bulk -> shared, completion on an mbarrier ----
+    if (lane == 0) {
+      uint32_t total = 0;
+      for (int t = 0; t < P.T; t++) {
+        const uint32_t n = P.meta[(size_t)ind * P.T + t] & 0xFFFFu;
+        total += ((n + 2u) & ~1u) * 8u;
+      }
+      mbar_expect_tx(bar, total);
+      int off = 0;
+      uint32_t soff = 0;  // compact programs are staged back to back (16-byte granules)
+      for (int t = 0; t < P.T; t++) {
+        const uint32_t n = P.meta[(size_t)ind * P.T + t] & 0xFFFFu;
+        bulk_g2s(prog_s + soff, P.prog + ((size_t)ind * P.T + t) * P.lstride, ((n + 2u) & ~1u) * 8u, bar);
+        soff += (n + 2u) & ~1u;
+        woff[t] = off;
+        off += (int)n + 1;
+      }
     }
-    mbar_expect_tx(bar, total);
-    int off = 0;
-    uint32_t soff = 0;  // compact programs are staged back to back (16-byte granules)
-    for (int t = 0; t < P.T; t++) {
-      const uint32_t n = P.meta[(size_t)ind * P.T + t] & 0xFFFFu;
-      bulk_g2s(prog_s + soff, P.prog + ((size_t)ind * P.T + t) * P.lstride, ((n + 2u) & ~1u) * 8u, bar);
-      soff += (n + 2u) & ~1u;
-      woff[t] = off;
-      off += (int)n + 1;
-    }
-  }
-  __syncwarp();
-  float* lb = vf + lane;  // lane base of the value file (R = 1)
-  const mtgp_saddr lbytes = mtgp_saddr_of(lb);
-  for (int s = 0; s < P.slots_per_warp; s++) lb[s * 32] = 0.0f;
-  mbar_wait(bar, bar_phase);
-  bar_phase ^= 1u;
-  bool readout_reads_y = false;
-  // ---- pre-decode: compact (8 B) -> wide (32 B) instructions, once per individual -------------
-  {
-    const uint32_t scratch = (uint32_t)P.slots_per_warp - 1u;
-    uint32_t soff = 0;
-    for (int t = 0; t < P.T; t++) {
-      const int n = (int)(P.meta[(size_t)ind * P.T + t] & 0xFFFFu) + 1;  // including X_END
-      mtgp_wide_instr* dst = wide + woff[t];
-      for (int i = lane; i < n; i += 32) {
-        const uint2 c = prog_s[soff + i];
-        dst[i] = mtgp_expand_instr(c, scratch);
-        if (KIND == MTGP_EVAL_DYNAMIC && t == P.state_size) {  // the readout tree
-          // does the readout read an observation or the control slot?  (conservative: unused operand fields count)
-          const uint32_t xk = (c.x >> 4) & 3u, yk = (c.x >> 6) & 3u, xs = (c.x >> 16) & 0xFFu, ys = c.x >> 24;
-          const bool rx = xk == OK_MEM && ((int)xs < n_obs || (int)xs == P.slot_u);
-          const bool ry = yk == OK_MEM && ((int)ys < n_obs || (int)ys == P.slot_u);
-          readout_reads_y |= (rx || ry) && (c.x & 15u) != X_END;
+    __syncwarp();
+    float* lb = vf + lane;  // lane base of the value file (R = 1)
+    const mtgp_saddr lbytes = mtgp_saddr_of(lb);
+    for (int s = 0; s < P.slots_per_warp; s++) lb[s * 32] = 0.0f;
+    mbar_wait(bar, bar_phase);
+    bar_phase ^= 1u;
+    bool readout_reads_y = false;
+    // ---- pre-decode: compact (8 B) -> wide (32 B) instructions, once per individual -------------
+    {
+      const uint32_t scratch = (uint32_t)P.slots_per_warp - 1u;
+      uint32_t soff = 0;
+      for (int t = 0; t < P.T; t++) {
+        const int n = (int)(P.meta[(size_t)ind * P.T + t] & 0xFFFFu) + 1;  // including X_END
+        mtgp_wide_instr* dst = wide + woff[t];
+        for (int i = lane; i < n; i += 32) {
+          const uint2 c = prog_s[soff + i];
+          dst[i] = mtgp_expand_instr(c, scratch);
+          if (KIND == MTGP_EVAL_DYNAMIC && t == P.state_size) {  // the readout tree
+            // does the readout read an observation or the control slot?  (conservative: unused operand fields count)
+            const uint32_t xk = (c.x >> 4) & 3u, yk = (c.x >> 6) & 3u, xs = (c.x >> 16) & 0xFFu, ys = c.x >> 24;
+            const bool rx = xk == OK_MEM && ((int)xs < n_obs || (int)xs == P.slot_u);
+            const bool ry = yk == OK_MEM && ((int)ys < n_obs || (int)ys == P.slot_u);
+            readout_reads_y |= (rx || ry) && (c.x & 15u) != X_END;
+          }
         }
+        soff += ((uint32_t)n + 1u) & ~1u;
       }
-      soff += ((uint32_t)n + 1u) & ~1u;
     }
-  }
-  __syncwarp();
-  // The dynamic readout sees zeros for the observations and the control inside the step
-  // (dynamic_evaluate.py:113) and the saved observations in the post-pass (:100-101).  With the
-  // notebooks' variable lists it reads neither (only the latent state), and the slots need no care.
-  const bool readout_sees_y = (KIND == MTGP_EVAL_DYNAMIC) && (__any_sync(0xFFFFFFFFu, readout_reads_y) != 0);
+    __syncwarp();
+    // The dynamic readout sees zeros for the observations and the control inside the step
+    // (dynamic_evaluate.py:113) and the saved observations in the post-pass (:100-101).  With the
+    // notebooks' variable lists it reads neither (only the latent state), and the slots need no care.
+    const bool readout_sees_y = (KIND == MTGP_EVAL_DYNAMIC) && (__any_sync(0xFFFFFFFFu, readout_reads_y) != 0);
 
-  const float* ts = P.ts;
-  const int K = P.K;
-  const int NL = FIXED_LATENT ? (KIND == MTGP_EVAL_STATIC ? 0 : 2) : P.n_latent;
-  // slot map of the data vector (mtgp_rollout_slot_map); compile-time for SPEC == 2: [y(D) | a(2) | u | targets | out(2) | state(2)]
-  constexpr bool FIXED_SLOTS = (KIND == MTGP_EVAL_DYNAMIC && SPEC == 2);
-  constexpr int NT = (KIND == MTGP_EVAL_SR) ? 0 : EnvDim<ENV>::NT;
-  const int slot_lat = FIXED_SLOTS ? D : P.slot_lat, slot_u = FIXED_SLOTS ? D + 2 : P.slot_u,
-            slot_target = FIXED_SLOTS ? D + 3 : P.slot_target, slot_out = FIXED_SLOTS ? D + 3 + NT : P.slot_out,
-            slot_state = FIXED_SLOTS ? D + 5 + NT : P.slot_state;
-  // shared-space addresses of the latent-state slots of this lane (component j is 128 bytes further)
-  const mtgp_saddr a_state = lbytes + 128u * (uint32_t)slot_state, a_out = lbytes + 128u * (uint32_t)slot_out,
-                   a_lat = lbytes + 128u * (uint32_t)slot_lat;
-  const float t0 = ts[0], t1 = ts[K - 1];
-  const float dts = (K > 1) ? ts[1] - ts[0] : 0.0f;  // ts[1]-ts[0], acrobot.py:82
-  const mtgp_saddr wide_s = mtgp_saddr_of(wide);
-  const mtgp_saddr prog_readout = wide_s + 32u * (uint32_t)woff[(KIND == MTGP_EVAL_DYNAMIC) ? NL : 0];
-  mtgp_saddr prog_lat[2] = {wide_s, wide_s};  // FIXED_SLOTS: the two state-equation programs
-  if (FIXED_SLOTS) {
-    prog_lat[0] = wide_s + 32u * (uint32_t)woff[0];
-    prog_lat[1] = wide_s + 32u * (uint32_t)woff[1];
-  }
-  float fit_sum = 0.0f;
-  unsigned int my_steps = 0;  // Euler steps integrated by this lane (< 2^32: max_steps is capped at 2^22 per solve)
+    const float* ts = P.ts;
+    const int K = P.K;
+    const int NL = FIXED_LATENT ? (KIND == MTGP_EVAL_STATIC ? 0 : 2) : P.n_latent;
+    // slot map of the data vector (mtgp_rollout_slot_map); compile-time for SPEC == 2: [y(D) | a(2) | u | targets | out(2) | state(2)]
+    constexpr bool FIXED_SLOTS = (KIND == MTGP_EVAL_DYNAMIC && SPEC == 2);
+    constexpr int NT = (KIND == MTGP_EVAL_SR) ? 0 : EnvDim<ENV>::NT;
+    const int slot_lat = FIXED_SLOTS ? D : P.slot_lat, slot_u = FIXED_SLOTS ? D + 2 : P.slot_u,
+              slot_target = FIXED_SLOTS ? D + 3 : P.slot_target, slot_out = FIXED_SLOTS ? D + 3 + NT : P.slot_out,
+              slot_state = FIXED_SLOTS ? D + 5 + NT : P.slot_state;
+    // shared-space addresses of the latent-state slots of this lane (component j is 128 bytes further)
+    const mtgp_saddr a_state = lbytes + 128u * (uint32_t)slot_state, a_out = lbytes + 128u * (uint32_t)slot_out,
+                     a_lat = lbytes + 128u * (uint32_t)slot_lat;
+    const float t0 = ts[0], t1 = ts[K - 1];
+    const float dts = (K > 1) ? ts[1] - ts[0] : 0.0f;  // ts[1]-ts[0], acrobot.py:82
+    const mtgp_saddr wide_s = mtgp_saddr_of(wide);
+    const mtgp_saddr prog_readout = wide_s + 32u * (uint32_t)woff[(KIND == MTGP_EVAL_DYNAMIC) ? NL : 0];
+    mtgp_saddr prog_lat[2] = {wide_s, wide_s};  // FIXED_SLOTS: the two state-equation programs
+    if (FIXED_SLOTS) {
+      prog_lat[0] = wide_s + 32u * (uint32_t)woff[0];
+      prog_lat[1] = wide_s + 32u * (uint32_t)woff[1];
+    }
+    float fit_sum = 0.0f;
+    unsigned int my_steps = 0;  // Euler steps integrated by this lane (< 2^32: max_steps is capped at 2^22 per solve)
 
-  for (int b0 = 0; b0 < P.B; b0 += 32) {  // B > 32: the warp takes 32 trajectories at a time
-    const int b = b0 + lane;
-    const bool lane_valid = b < P.B;
-    const int bb = lane_valid ? b : P.B - 1;  // idle lanes shadow a valid trajectory
-    Env<ENV> env;
-    if (KIND != MTGP_EVAL_SR) env.init(P, bb);
-    if (KIND != MTGP_EVAL_SR)
-      for (int i = 0; i < P.n_targets; i++) lb[(slot_target + i) * 32] = P.targets[bb * P.n_targets + i];
-    const float* nz_base = (NOISE == 1) ? P.noise + (size_t)bb * 4 : nullptr;
-    const int nzs = P.B * 4;  // floats per table row
+    for (int b0 = 0; b0 < P.B; b0 += 32) {  // B > 32: the warp takes 32 trajectories at a time
+      const int b = b0 + lane;
+      const bool lane_valid = b < P.B;
+      const int bb = lane_valid ? b : P.B - 1;  // idle lanes shadow a valid trajectory
+      Env<ENV> env;
+      if (KIND != MTGP_EVAL_SR) env.init(P, bb);
+      if (KIND != MTGP_EVAL_SR)
+        for (int i = 0; i < P.n_targets; i++) lb[(slot_target + i) * 32] = P.targets[bb * P.n_targets + i];
+      const float* nz_base = (NOISE == 1) ? P.noise + (size_t)bb * 4 : nullptr;
+      const int nzs = P.B * 4;  // floats per table row
 
-    int fs_known = -1;
-    bool viol = false;
-    float traj_fitness = 0.0f;
-    for (int pass = 0; pass < 2; pass++) {
-      // ---------------- one trajectory solve ----------------
-      float x[DR], x1[DR];
-      if (KIND != MTGP_EVAL_SR) {
+      int fs_known = -1;
+      bool viol = false;
+      float traj_fitness = 0.0f;
+      for (int pass = 0; pass < 2; pass++) {
+        // ---------------- one trajectory solve ----------------
+        float x[DR], x1[DR];
+        if (KIND != MTGP_EVAL_SR) {
 #pragma unroll
-        for (int i = 0; i < D; i++) { x[i] = P.x0[bb * D + i]; x1[i] = x[i]; }
-      }
-      for (int j = 0; j < NL; j++) {
-        const float v = (KIND == MTGP_EVAL_SR) ? P.x0[bb * NL + j] : 0.0f;  // a0 = 0 (dynamic_evaluate.py:89)
-        lb[(slot_state + j) * 32] = v;
-        lb[(slot_lat + j) * 32] = v;
-        lb[(slot_out + j) * 32] = v;
-      }
-      if (KIND != MTGP_EVAL_SR) { env.sum = 0.0f; env.sum0 = 0.0f; env.fs = -1; }
-      float sr_total = 0.0f;
-      bool ev_old_bad;
-      {
-        bool bad = false;
-        if (KIND != MTGP_EVAL_SR) bad = env.bad_state(x);
-        for (int j = 0; j < NL; j++) bad |= !mtgp_isfinitef(lb[(slot_state + j) * 32]);
-        ev_old_bad = bad;  // Event: cond_fn at (t0, y0)
-      }
-      bool alive = true;
-      float tprev = t0, tnext = t0 + P.dt0;
-      tnext = tnext < t1 ? tnext : t1;
-      int steps = 0, k = 0;
-      const float* nz_step = nz_base;  // noise-table row of the current step
-      unsigned int lane_steps = 0;  // steps this lane integrated before its event fired
-      float ts_k = ts[0];  // ts[k], reloaded only when k advances
-      // One iteration = one Euler step while any lane is still integrating, then the save points that
-      // step covers.  Once the solve is over (t1 reached, max_steps, or every lane's event fired) the
-      // remaining save points are emitted from the inf pre-fill of SaveAt -- by the same code.
-      while (k < K) {
-        const bool stepping = (tprev < t1) && (steps < P.max_steps) &&
-                              (__ballot_sync(0xFFFFFFFFu, alive && lane_valid) != 0u);
-        float save_until = mtgp_inff(), new_tprev = tprev, new_tnext = tnext;
-        if (stepping) {
-          const float dt = tnext - tprev;
-          float u = 0.0f;
-          if (KIND != MTGP_EVAL_SR) {
-            float y[DR];
-            env.template f_obs<NOISE>(tprev, x, y, n_obs, P.obs_noise, P.partitionable,
-                                      nz_step, nzs);
-            if (KIND == MTGP_EVAL_STATIC) {
-#pragma unroll
-              for (int i = 0; i < D; i++)
-                if (i < n_obs) lb[i * 32] = y[i];
-            } else if (readout_sees_y) {
-#pragma unroll
-              for (int i = 0; i < D; i++)
-                if (i < n_obs) lb[i * 32] = 0.0f;
-              lb[slot_u * 32] = 0.0f;
-            }
-            u = mtgp_interpret_wide(prog_readout, lbytes);  // feedforward :107 / dynamic readout :113
-            float dx[DR];
-            env.drift(x, u, dx);
-#pragma unroll
-            for (int i = 0; i < D; i++) x1[i] = x[i] + dt * dx[i];
-            if (KIND == MTGP_EVAL_DYNAMIC) {
-#pragma unroll
-              for (int i = 0; i < D; i++)
-                if (i < n_obs) lb[i * 32] = y[i];
-              lb[slot_u * 32] = u;
-            }
-          }
-          for (int j = 0; j < NL; j++) {  // latent trees: state equation (:116) / SR vector field
-            const float f = mtgp_interpret_wide(FIXED_SLOTS ? prog_lat[j & 1] : wide_s + 32u * (uint32_t)woff[j], lbytes);
-            mtgp_sts_f32(a_out + 128u * j, mtgp_lds_f32(a_state + 128u * j) + dt * f);
-          }
-          new_tprev = tnext < t1 ? tnext : t1;
-          new_tnext = tnext + P.dt0;
-          new_tnext = (new_tnext > t1 - 1e-6f) ? t1 : new_tnext;  // _clip_to_end
-          save_until = tnext;
+          for (int i = 0; i < D; i++) { x[i] = P.x0[bb * D + i]; x1[i] = x[i]; }
         }
-        const bool live_save = stepping && alive;
-        // ---- SaveAt(ts): dense (linear) output for every ts[k] <= tnext ----
-        while (k < K && ts_k <= save_until) {
-          const float tk = ts_k;
-          const float coeff = (tprev == tnext) ? 0.0f : (tk - tprev) / (tnext - tprev);
-          float xs[DR];
-          if (KIND != MTGP_EVAL_SR) {
-#pragma unroll
-            for (int i = 0; i < D; i++) xs[i] = live_save ? x[i] + coeff * (x1[i] - x[i]) : mtgp_inff();
-          }
-          float row = 0.0f;
-          for (int j = 0; j < NL; j++) {
-            const float a0 = mtgp_lds_f32(a_state + 128u * j), a1 = mtgp_lds_f32(a_out + 128u * j);
-            const float lat = live_save ? a0 + coeff * (a1 - a0) : mtgp_inff();
-            if (KIND == MTGP_EVAL_SR) {
-              const float e = lat - P.ys_true[((size_t)bb * K + k) * NL + j];
-              row = row + e * e;
-              if (P.xs_o && lane_valid && pass == 0) P.xs_o[(((size_t)ind * P.B + b) * K + k) * NL + j] = lat;
-            } else {
-              mtgp_sts_f32(a_lat + 128u * j, lat);
-              if (P.act_o && lane_valid && pass == 0) P.act_o[(((size_t)ind * P.B + b) * K + k) * NL + j] = lat;
-            }
-          }
-          if (KIND == MTGP_EVAL_SR) {
-            sr_total = sr_total + row;
-          } else {
-            float ys[DR];
-            env.template f_obs<NOISE>(tk, xs, ys, n_obs, P.obs_noise, P.partitionable,
-                                      nz_base + (size_t)(P.cap_steps + k) * nzs, nzs);
-            if (KIND == MTGP_EVAL_STATIC || readout_sees_y) {
-#pragma unroll
-              for (int i = 0; i < D; i++)
-                if (i < n_obs) lb[i * 32] = ys[i];
-              if (KIND == MTGP_EVAL_DYNAMIC) lb[slot_u * 32] = 0.0f;  // zeros(control_size) (dynamic_evaluate.py:101)
-            }
-            const float uk = mtgp_interpret_wide(prog_readout, lbytes);
-            const float qk = (ENV == MTGP_ENV_ACROBOT) ? tk / dts : 0.0f;
-            if (ENV == MTGP_ENV_ACROBOT && qk > (float)(k + 1)) viol = true;
-            env.cost_add(k, qk, xs, uk, fs_known);
-            if (lane_valid && pass == 0 && (P.xs_o || P.ys_o || P.us_o)) {
-              const size_t o = ((size_t)ind * P.B + b) * K + k;
-              if (P.xs_o)
-#pragma unroll
-                for (int i = 0; i < D; i++) P.xs_o[o * D + i] = xs[i];
-              if (P.ys_o)
+        for (int j = 0; j < NL; j++) {
+          const float v = (KIND == MTGP_EVAL_SR) ? P.x0[bb * NL + j] : 0.0f;  // a0 = 0 (dynamic_evaluate.py:89)
+          lb[(slot_state + j) * 32] = v;
+          lb[(slot_lat + j) * 32] = v;
+          lb[(slot_out + j) * 32] = v;
+        }
+        if (KIND != MTGP_EVAL_SR) { env.sum = 0.0f; env.sum0 = 0.0f; env.fs = -1; }
+        float sr_total = 0.0f;
+        bool ev_old_bad;
+        {
+          bool bad = false;
+          if (KIND != MTGP_EVAL_SR) bad = env.bad_state(x);
+          for (int j = 0; j < NL; j++) bad |= !mtgp_isfinitef(lb[(slot_state + j) * 32]);
+          ev_old_bad = bad;  // Event: cond_fn at (t0, y0)
+        }
+        bool alive = true;
+        float tprev = t0, tnext = t0 + P.dt0;
+        tnext = tnext < t1 ? tnext : t1;
+        int steps = 0, k = 0;
+        const float* nz_step = nz_base;  // noise-table row of the current step
+        unsigned int lane_steps = 0;  // steps this lane integrated before its event fired
+        float ts_k = ts[0];  // ts[k], reloaded only when k advances
+        // One iteration = one Euler step while any lane is still integrating, then the save points that
+        // step covers.  Once the solve is over (t1 reached, max_steps, or every lane's event fired) the
+        // remaining save points are emitted from the inf pre-fill of SaveAt -- by the same code.
+        while (k < K) {
+          const bool stepping = (tprev < t1) && (steps < P.max_steps) &&
+                                (__ballot_sync(0xFFFFFFFFu, alive && lane_valid) != 0u);
+          float save_until = mtgp_inff(), new_tprev = tprev, new_tnext = tnext;
+          if (stepping) {
+            const float dt = tnext - tprev;
+            float u = 0.0f;
+            if (KIND != MTGP_EVAL_SR) {
+              float y[DR];
+              env.template f_obs<NOISE>(tprev, x, y, n_obs, P.obs_noise, P.partitionable,
+                                        nz_step, nzs);
+              if (KIND == MTGP_EVAL_STATIC) {
 #pragma unroll
                 for (int i = 0; i < D; i++)
-                  if (i < n_obs) P.ys_o[o * n_obs + i] = ys[i];
-              if (P.us_o) P.us_o[o] = uk;
+                  if (i < n_obs) lb[i * 32] = y[i];
+              } else if (readout_sees_y) {
+#pragma unroll
+                for (int i = 0; i < D; i++)
+                  if (i < n_obs) lb[i * 32] = 0.0f;
+                lb[slot_u * 32] = 0.0f;
+              }
+              u = mtgp_interpret_wide(prog_readout, lbytes);  // feedforward :107 / dynamic readout :113
+              float dx[DR];
+              env.drift(x, u, dx);
+#pragma unroll
+              for (int i = 0; i < D; i++) x1[i] = x[i] + dt * dx[i];
+              if (KIND == MTGP_EVAL_DYNAMIC) {
+#pragma unroll
+                for (int i = 0; i < D; i++)
+                  if (i < n_obs) lb[i * 32] = y[i];
+                lb[slot_u * 32] = u;
+              }
             }
+            for (int j = 0; j < NL; j++) {  // latent trees: state equation (:116) / SR vector field
+              const float f = mtgp_interpret_wide(FIXED_SLOTS ? prog_lat[j & 1] : wide_s + 32u * (uint32_t)woff[j], lbytes);
+              mtgp_sts_f32(a_out + 128u * j, mtgp_lds_f32(a_state + 128u * j) + dt * f);
+            }
+            new_tprev = tnext < t1 ? tnext : t1;
+            new_tnext = tnext + P.dt0;
+            new_tnext = (new_tnext > t1 - 1e-6f) ? t1 : new_tnext;  // _clip_to_end
+            save_until = tnext;
           }
-          k++;
-          ts_k = ts[k < K ? k : K - 1];
-        }
-        if (stepping) {
-          // ---- Event(cond_fn): sign change of cond_fn evaluated at (tnext, y1) ----
-          bool bad = false;
-          if (KIND != MTGP_EVAL_SR) bad = env.bad_state(x1);
-          for (int j = 0; j < NL; j++) bad |= !mtgp_isfinitef(mtgp_lds_f32(a_out + 128u * j));
-          const bool fired = (bad != ev_old_bad);
-          // ---- commit ----
-          if (alive) {
-            ev_old_bad = bad;
-            lane_steps++;
+          const bool live_save = stepping && alive;
+          // ---- SaveAt(ts): dense (linear) output for every ts[k] <= tnext ----
+          while (k < K && ts_k <= save_until) {
+            const float tk = ts_k;
+            const float coeff = (tprev == tnext) ? 0.0f : (tk - tprev) / (tnext - tprev);
+            float xs[DR];
             if (KIND != MTGP_EVAL_SR) {
 #pragma unroll
-              for (int i = 0; i < D; i++) x[i] = x1[i];
+              for (int i = 0; i < D; i++) xs[i] = live_save ? x[i] + coeff * (x1[i] - x[i]) : mtgp_inff();
             }
-          }
-          for (int j = 0; j < NL; j++) {
-            const float cur = mtgp_lds_f32(a_state + 128u * j);
-            const float nv = alive ? mtgp_lds_f32(a_out + 128u * j) : cur;
-            mtgp_sts_f32(a_state + 128u * j, nv);
-            mtgp_sts_f32(a_lat + 128u * j, nv);
-          }
-          if (alive && fired) alive = false;
-          tprev = new_tprev;
-          tnext = new_tnext;
-          steps++;
-          if (NOISE == 1) nz_step += nzs;
-        }
-      }
-      if (pass == 0 && lane_valid) my_steps += lane_steps;
-      traj_fitness = (KIND == MTGP_EVAL_SR) ? sr_total / (float)K : env.cost_finish(K, fs_known);
-      // Acrobot with a ts grid for which the running-prefix cost is not exact (ts[k]/dts > k+1
-      // somewhere): redo the solve with first_success known.  Warp-uniform decision.
-      if (ENV != MTGP_ENV_ACROBOT || pass == 1) break;
-      if (__ballot_sync(0xFFFFFFFFu, viol) == 0u) break;
-      fs_known = env.fs < 0 ? 0 : env.fs;
-    }
-    if (lane_valid) {
-      if (P.tf_o) P.tf_o[(size_t)ind * P.B + b] = traj_fitness;
-      fit_sum = fit_sum + (mtgp_isfinitef(traj_fitness) ? traj_fitness : P.max_fitness);
-    }
-  }
-  // mean over B (fixed shuffle tree), clip, parsimony
+            float row = 0.0f;
+            for (int j = 0; j < NL; j++) {
+              const float a0 = mtgp_lds_f32(a_state + 128u * j), a1 = mtgp_lds_f32(a_out + 128u * j);
+              const float lat = live_save ? a0 + coeff * (a1 - a0) : mtgp_inff();
+              if (KIND == MTGP_EVAL_SR) {
+                const float e = lat - P.ys_true[((size_t)bb * K + k) * NL + j];
+                row = row + e * e;
+                if (P.xs_o && lane_valid && pass == 0) P.xs_o[(((size_t)ind * P.B + b) * K + k) * NL + j] = lat;
+              } else {
+                mtgp_sts_f32(a_lat + 128u * j, lat);
+                if (P.act_o && lane_valid && pass == 0) P.act_o[(((size_t)ind * P.B + b) * K + k) * NL + j] = lat;
+              }
+            }
+            if (KIND == MTGP_EVAL_SR) {
+              sr_total = sr_total + row;
+            } else {
+              float ys[DR];
+              env.template f_obs<NOISE>(tk, xs, ys, n_obs, P.obs_noise, P.partitionable,
+                                        nz_base + (size_t)(P.cap_steps + k) * nzs, nzs);
+              if (KIND == MTGP_EVAL_STATIC || readout_sees_y) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) fit_sum = fit_sum + __shfl_xor_sync(0xFFFFFFFFu, fit_sum, o);
-  unsigned long long warp_steps = my_steps;
-  for (int o = 16; o > 0; o >>= 1) warp_steps += __shfl_xor_sync(0xFFFFFFFFu, warp_steps, o);
-  if (lane == 0) {
-    float f = clip_jnp(fit_sum / (float)P.B, 0.0f, P.max_fitness);
-    if (P.live) {
-      int cnt = 0;
-      for (int t = 0; t < P.T; t++) cnt += P.live[(size_t)ind * P.T + t];
-      f = f + P.size_parsimony * (float)cnt;
+                for (int i = 0; i < D; i++)
+                  if (i < n_obs) lb[i * 32] = ys[i];
+                if (KIND == MTGP_EVAL_DYNAMIC) lb[slot_u * 32] = 0.0f;  // zeros(control_size) (dynamic_evaluate.py:101)
+              }
+              const float uk = mtgp_interpret_wide(prog_readout, lbytes);
+              const float qk = (ENV == MTGP_ENV_ACROBOT) ? tk / dts : 0.0f;
+              if (ENV == MTGP_ENV_ACROBOT && qk > (float)(k + 1)) viol = true;
+              env.cost_add(k, qk, xs, uk, fs_known);
+              if (lane_valid && pass == 0 && (P.xs_o || P.ys_o || P.us_o)) {
+                const size_t o = ((size_t)ind * P.B + b) * K + k;
+                if (P.xs_o)
+#pragma unroll
+                  for (int i = 0; i < D; i++) P.xs_o[o * D + i] = xs[i];
+                if (P.ys_o)
+#pragma unroll
+                  for (int i = 0; i < D; i++)
+                    if (i < n_obs) P.ys_o[o * n_obs + i] = ys[i];
+                if (P.us_o) P.us_o[o] = uk;
+              }
+            }
+            k++;
+            ts_k = ts[k < K ? k : K - 1];
+          }
+          if (stepping) {
+            // ---- Event(cond_fn): sign change of cond_fn evaluated at (tnext, y1) ----
+            bool bad = false;
+            if (KIND != MTGP_EVAL_SR) bad = env.bad_state(x1);
+            for (int j = 0; j < NL; j++) bad |= !mtgp_isfinitef(mtgp_lds_f32(a_out + 128u * j));
+            const bool fired = (bad != ev_old_bad);
+            // ---- commit ----
+            if (alive) {
+              ev_old_bad = bad;
+              lane_steps++;
+              if (KIND != MTGP_EVAL_SR) {
+#pragma unroll
+                for (int i = 0; i < D; i++) x[i] = x1[i];
+              }
+            }
+            for (int j = 0; j < NL; j++) {
+              const float cur = mtgp_lds_f32(a_state + 128u * j);
+              const float nv = alive ? mtgp_lds_f32(a_out + 128u * j) : cur;
+              mtgp_sts_f32(a_state + 128u * j, nv);
+              mtgp_sts_f32(a_lat + 128u * j, nv);
+            }
+            if (alive && fired) alive = false;
+            tprev = new_tprev;
+            tnext = new_tnext;
+            steps++;
+            if (NOISE == 1) nz_step += nzs;
+          }
+        }
+        if (pass == 0 && lane_valid) my_steps += lane_steps;
+        traj_fitness = (KIND == MTGP_EVAL_SR) ? sr_total / (float)K : env.cost_finish(K, fs_known);
+        // Acrobot with a ts grid for which the running-prefix cost is not exact (ts[k]/dts > k+1
+        // somewhere): redo the solve with first_success known.  Warp-uniform decision.
+        if (ENV != MTGP_ENV_ACROBOT || pass == 1) break;
+        if (__ballot_sync(0xFFFFFFFFu, viol) == 0u) break;
+        fs_known = env.fs < 0 ? 0 : env.fs;
+      }
+      if (lane_valid) {
+        if (P.tf_o) P.tf_o[(size_t)ind * P.B + b] = traj_fitness;
+        fit_sum = fit_sum + (mtgp_isfinitef(traj_fitness) ? traj_fitness : P.max_fitness);
+      }
     }
-    P.fitness[ind] = f;
-    if (P.steps_done) atomicAdd(P.steps_done, warp_steps);
-  }
-  __syncwarp();  // the value file and the program area are reused by the next individual
+    // mean over B (fixed shuffle tree), clip, parsimony
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) fit_sum = fit_sum + __shfl_xor_sync(0xFFFFFFFFu, fit_sum, o);
+    unsigned long long warp_steps = my_steps;
+    for (int o = 16; o > 0; o >>= 1) warp_steps += __shfl_xor_sync(0xFFFFFFFFu, warp_steps, o);
+    if (lane == 0) {
+      float f = clip_jnp(fit_sum / (float)P.B, 0.0f, P.max_fitness);
+      if (P.live) {
+        int cnt = 0;
+        for (int t = 0; t < P.T; t++) cnt += P.live[(size_t)ind * P.T + t];
+        f = f + P.size_parsimony * (float)cnt;
+      }
+      P.fitness[ind] = f;
+      if (P.steps_done) atomicAdd(P.steps_done, warp_steps);
+    }
+    __syncwarp();  // the value file and the program area are reused by the next individual
   }  // persistent loop
 }
 
