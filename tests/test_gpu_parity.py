@@ -141,6 +141,27 @@ def test_dynamic_readout_that_reads_observations(engine, oracle, env_name, solve
     assert int(gpu["steps"][0]) == ref["steps"]
 
 
+def test_populations_larger_than_the_resident_warps(engine, oracle):
+    """More individuals than the 148 x 32 resident one-warp CTAs: the rollout warps become persistent and draw
+    further schedule slots from a counter.  Every kind / instantiation, bit-exact against the oracle."""
+    rng = np.random.default_rng(99)
+    P = 6000
+    lib, pop, data = util.sr_case(rng, P, B=4, T_end=1.0)
+    ref = oracle.rollout_population(pop, lib.table(), data)
+    gpu = _gpu_rollout(engine, lib, pop, data, count_steps=True)
+    _assert_fitness(gpu["fitness"], ref["fitness"], 1e5)
+    assert int(gpu["steps"][0]) == ref["steps"]
+    for env_name, kind, S in (("harmonic", abi.EVAL_STATIC, 2), ("reactor", abi.EVAL_DYNAMIC, 3),
+                              ("acrobot", abi.EVAL_DYNAMIC, 2)):
+        grid = dict(T_end=0.4, dt_save=0.04, dt0=0.002) if env_name == "reactor" else dict(T_end=2.0, dt_save=0.2, dt0=0.05)
+        lib, pop, data = util.control_case(env_name, kind, rng, P=P, B=4, obs_noise=0.1, state_size=S,
+                                           param_mode="Constant" if env_name == "acrobot" else "Different", **grid)
+        ref = oracle.rollout_population(pop, lib.table(), data)
+        gpu = _gpu_rollout(engine, lib, pop, data, count_steps=True)
+        _assert_fitness(gpu["fitness"], ref["fitness"], 1e4)
+        assert int(gpu["steps"][0]) == ref["steps"], env_name
+
+
 def test_inline_noise_generator_matches_the_table(engine, oracle, monkeypatch):
     """The rollout kernel normally reads the observation noise from a table computed once per
     evaluation; when the table would be too large it generates the noise in-kernel.  Same bits."""
