@@ -192,11 +192,12 @@ def cpu_sample_size(w, target_s, n_threads=0):
     """How many individuals the oracle evaluates in about target_s seconds on this host."""
     from oracle import pyoracle as po
     po.build()
-    probe = w["pop"][:32]
     n_threads = n_threads or host_threads()
+    n_probe = max(32, 8 * n_threads)  # several individuals per thread, or the probe only measures imbalance
+    probe = w["pop"][:n_probe]
     t = time.perf_counter(); po.rollout_population(probe, w["lib"].table(), w["data"], n_threads)
     dt = time.perf_counter() - t
-    n = int(min(w["pop"].shape[0], max(32, 32 * target_s / max(dt, 1e-4))))
+    n = int(min(w["pop"].shape[0], max(32, n_probe * target_s / max(dt, 1e-4))))
     return max(32, n - n % 8)
 
 
