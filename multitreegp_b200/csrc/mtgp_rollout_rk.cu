@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
   constexpr int DR = D > 0 ? D : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
-  const int slot = blockIdx.x * kRkWarps + wic;
+  const int slot0 = blockIdx.x * kRkWarps + wic;
   const size_t per_warp = (size_t)P.prog_words_per_warp * sizeof(uint2) + kMaxTrees * sizeof(int) +
                           (size_t)P.wide_cap * sizeof(mtgp_wide_instr) + (size_t)P.slots_per_warp * 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
@@ -58,342 +58,357 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
   mtgp_wide_instr* wide = reinterpret_cast<mtgp_wide_instr*>(woff + kMaxTrees);
   float* vf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(wide) +
                                        (size_t)P.wide_cap * sizeof(mtgp_wide_instr));
-  if (slot >= P.P) return;
-  const int ind = P.order ? P.order[slot] : slot;
-
-  // ---- stage + pre-decode the programs (same as K2) ----
+  // persistent warps, as in k_rollout: the first individual comes with the launch, later ones from the counter
   uint64_t* bar = bars + 2 * wic;
-  if (lane == 0) {
-    mbar_init(bar, 1);
-    uint32_t total = 0;
-    for (int t = 0; t < P.T; t++) total += (((P.meta[(size_t)ind * P.T + t] & 0xFFFFu) + 2u) & ~1u) * 8u;
-    mbar_expect_tx(bar, total);
-    int off = 0;
-    for (int t = 0; t < P.T; t++) {
-      const uint32_t n = P.meta[(size_t)ind * P.T + t] & 0xFFFFu;
-      bulk_g2s(prog_s + (size_t)t * P.lstride, P.prog + ((size_t)ind * P.T + t) * P.lstride, ((n + 2u) & ~1u) * 8u, bar);
-      woff[t] = off;
-      off += (int)n + 1;
-    }
-  }
+  if (lane == 0) mbar_init(bar, 1);
   __syncwarp();
-  float* lb = vf + lane;
-  const mtgp_saddr lbytes = mtgp_saddr_of(lb);
-  for (int s = 0; s < P.slots_per_warp; s++) lb[s * 32] = 0.0f;
-  mbar_wait(bar, 0);
-  {
-    const uint32_t scratch = (uint32_t)P.slots_per_warp - 1u;
-    for (int t = 0; t < P.T; t++) {
-      const int n = (int)(P.meta[(size_t)ind * P.T + t] & 0xFFFFu) + 1;
-      mtgp_wide_instr* dst = wide + woff[t];
-      for (int i = lane; i < n; i += 32) dst[i] = mtgp_expand_instr(prog_s[(size_t)t * P.lstride + i], scratch);
+  uint32_t bar_phase = 0;
+  bool first_round = true;
+  for (;;) {
+    int slot = slot0;
+    if (!first_round) {
+      if (!P.next_slot) return;
+      if (lane == 0) slot = (int)(gridDim.x * kRkWarps) + atomicAdd(P.next_slot, 1);
+      slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
     }
-  }
-  __syncwarp();
+    first_round = false;
+    if (slot >= P.P) return;
+    const int ind = P.order ? P.order[slot] : slot;
 
-  const float* ts = P.ts;
-  constexpr bool FIXED = (SPEC == 2) && (KIND != MTGP_EVAL_SR);
-  const int n_obs = FIXED ? D : P.n_obs;
-  const int K = P.K, NL = FIXED ? (KIND == MTGP_EVAL_STATIC ? 0 : 2) : P.n_latent, DT = D + NL;
-  const float t0 = ts[0], t1 = ts[K - 1];
-  const float dts = (K > 1) ? ts[1] - ts[0] : 0.0f;
-  const bool dopri = P.solver == MTGP_SOLVER_DOPRI5, pid = P.controller == MTGP_CONTROLLER_PID;
-  const mtgp_saddr wide_s = mtgp_saddr_of(wide);
-  const mtgp_saddr prog_readout = wide_s + 32u * (uint32_t)woff[(KIND == MTGP_EVAL_DYNAMIC) ? NL : 0];
-  // solver arrays in the value file: component i of array a is slot slot_rk + a*DT + i
-  float* const Y = lb + (size_t)(P.slot_rk + 0 * DT) * 32;
-  float* const Y1 = lb + (size_t)(P.slot_rk + 1 * DT) * 32;
-  float* const YI = lb + (size_t)(P.slot_rk + 2 * DT) * 32;
-  float* const F0 = lb + (size_t)(P.slot_rk + 3 * DT) * 32;
-  float* const KS = lb + (size_t)(P.slot_rk + 4 * DT) * 32;  // KS[st][i] at (st*DT + i)*32
-  float* const SV = lb + (size_t)(P.slot_rk + 11 * DT) * 32; // state at a save point
-  float fit_sum = 0.0f;
-  unsigned int my_steps = 0;
-
-  for (int b0 = 0; b0 < P.B; b0 += 32) {
-    const int b = b0 + lane;
-    const bool lane_valid = b < P.B;
-    const int bb = lane_valid ? b : P.B - 1;
-    Env<ENV> env;
-    if (KIND != MTGP_EVAL_SR) env.init(P, bb);
-    if (KIND != MTGP_EVAL_SR)
-      for (int i = 0; i < P.n_targets; i++) lb[(P.slot_target + i) * 32] = P.targets[bb * P.n_targets + i];
-
-    // vector field of the evaluator at (t, src): writes dst[i] = scale * f_i  (i < DT)
-    auto vector_field = [&](float t, const float* src, float* dst, float scale, float* raw) {
-      float x[DR], y[DR], dx[DR];
-      for (int j = 0; j < NL; j++) lb[(P.slot_lat + j) * 32] = src[(D + j) * 32];
-      if (KIND != MTGP_EVAL_SR) {
-#pragma unroll
-        for (int i = 0; i < D; i++) x[i] = src[i * 32];
-        env.template f_obs<NOISE ? 2 : 0>(t, x, y, n_obs, P.obs_noise, P.partitionable, nullptr, 0);
-        if (KIND == MTGP_EVAL_STATIC) {
-#pragma unroll
-          for (int i = 0; i < D; i++)
-            if (i < n_obs) lb[i * 32] = y[i];
-        } else {
-#pragma unroll
-          for (int i = 0; i < D; i++)
-            if (i < n_obs) lb[i * 32] = 0.0f;
-          lb[P.slot_u * 32] = 0.0f;
-        }
-        const float u = mtgp_interpret_wide(prog_readout, lbytes);
-        env.drift(x, u, dx);
-#pragma unroll
-        for (int i = 0; i < D; i++) {
-          dst[i * 32] = scale * dx[i];
-          if (raw) raw[i * 32] = dx[i];
-        }
-        if (KIND == MTGP_EVAL_DYNAMIC) {
-#pragma unroll
-          for (int i = 0; i < D; i++)
-            if (i < n_obs) lb[i * 32] = y[i];
-          lb[P.slot_u * 32] = u;
-        }
+    // ---- stage + pre-decode the programs (same as K2) ----
+    if (lane == 0) {
+      uint32_t total = 0;
+      for (int t = 0; t < P.T; t++) total += (((P.meta[(size_t)ind * P.T + t] & 0xFFFFu) + 2u) & ~1u) * 8u;
+      mbar_expect_tx(bar, total);
+      int off = 0;
+      for (int t = 0; t < P.T; t++) {
+        const uint32_t n = P.meta[(size_t)ind * P.T + t] & 0xFFFFu;
+        bulk_g2s(prog_s + (size_t)t * P.lstride, P.prog + ((size_t)ind * P.T + t) * P.lstride, ((n + 2u) & ~1u) * 8u, bar);
+        woff[t] = off;
+        off += (int)n + 1;
       }
-      for (int j = 0; j < NL; j++) {
-        const float f = mtgp_interpret_wide(wide_s + 32u * (uint32_t)woff[j], lbytes);
-        dst[(D + j) * 32] = scale * f;
-        if (raw) raw[(D + j) * 32] = f;
+    }
+    __syncwarp();
+    float* lb = vf + lane;
+    const mtgp_saddr lbytes = mtgp_saddr_of(lb);
+    for (int s = 0; s < P.slots_per_warp; s++) lb[s * 32] = 0.0f;
+    mbar_wait(bar, bar_phase);
+    bar_phase ^= 1u;
+    {
+      const uint32_t scratch = (uint32_t)P.slots_per_warp - 1u;
+      for (int t = 0; t < P.T; t++) {
+        const int n = (int)(P.meta[(size_t)ind * P.T + t] & 0xFFFFu) + 1;
+        mtgp_wide_instr* dst = wide + woff[t];
+        for (int i = lane; i < n; i += 32) dst[i] = mtgp_expand_instr(prog_s[(size_t)t * P.lstride + i], scratch);
       }
-    };
-    auto bad_state = [&](const float* src) {
-      bool bad = false;
-      if (KIND != MTGP_EVAL_SR) {
-        float x[DR];
-#pragma unroll
-        for (int i = 0; i < D; i++) x[i] = src[i * 32];
-        bad = env.bad_state(x);
-      }
-      for (int j = 0; j < NL; j++) bad |= !mtgp_isfinitef(src[(D + j) * 32]);
-      return bad;
-    };
+    }
+    __syncwarp();
 
-    int fs_known = -1;
-    bool viol = false;
-    float traj_fitness = 0.0f;
-    for (int pass = 0; pass < 2; pass++) {
-      if (KIND != MTGP_EVAL_SR) {
-#pragma unroll
-        for (int i = 0; i < D; i++) Y[i * 32] = P.x0[bb * D + i];
-      }
-      for (int j = 0; j < NL; j++) Y[(D + j) * 32] = (KIND == MTGP_EVAL_SR) ? P.x0[bb * NL + j] : 0.0f;
-      if (KIND != MTGP_EVAL_SR) { env.sum = 0.0f; env.sum0 = 0.0f; env.fs = -1; }
-      float sr_total = 0.0f;
-      bool ev_old_bad = bad_state(Y);
-      bool active = true, fsal_valid = false, at_dtmin = false;  // fsal_valid: F0 holds f(tprev, Y)
-      float tprev = t0, tnext = t0 + P.dt0;
-      tnext = tnext < t1 ? tnext : t1;
-      float prev_inv = 1.0f, prev_prev_inv = 1.0f;
-      int num_steps = 0, k = 0;
+    const float* ts = P.ts;
+    constexpr bool FIXED = (SPEC == 2) && (KIND != MTGP_EVAL_SR);
+    const int n_obs = FIXED ? D : P.n_obs;
+    const int K = P.K, NL = FIXED ? (KIND == MTGP_EVAL_STATIC ? 0 : 2) : P.n_latent, DT = D + NL;
+    const float t0 = ts[0], t1 = ts[K - 1];
+    const float dts = (K > 1) ? ts[1] - ts[0] : 0.0f;
+    const bool dopri = P.solver == MTGP_SOLVER_DOPRI5, pid = P.controller == MTGP_CONTROLLER_PID;
+    const mtgp_saddr wide_s = mtgp_saddr_of(wide);
+    const mtgp_saddr prog_readout = wide_s + 32u * (uint32_t)woff[(KIND == MTGP_EVAL_DYNAMIC) ? NL : 0];
+    // solver arrays in the value file: component i of array a is slot slot_rk + a*DT + i
+    float* const Y = lb + (size_t)(P.slot_rk + 0 * DT) * 32;
+    float* const Y1 = lb + (size_t)(P.slot_rk + 1 * DT) * 32;
+    float* const YI = lb + (size_t)(P.slot_rk + 2 * DT) * 32;
+    float* const F0 = lb + (size_t)(P.slot_rk + 3 * DT) * 32;
+    float* const KS = lb + (size_t)(P.slot_rk + 4 * DT) * 32;  // KS[st][i] at (st*DT + i)*32
+    float* const SV = lb + (size_t)(P.slot_rk + 11 * DT) * 32; // state at a save point
+    float fit_sum = 0.0f;
+    unsigned int my_steps = 0;
 
-      // one save point of the post-pass for the lanes with `doit`; xs/lat hold the saved state
-      auto save_point = [&](bool doit, const float* sv /* DT components at sv[i*32] */) {
-        const int kk = k < K ? k : K - 1;
-        const float tk = ts[kk];
-        if (KIND == MTGP_EVAL_SR) {
-          float row = 0.0f;
-          for (int j = 0; j < NL; j++) {
-            const float lat = sv[j * 32];
-            const float e = lat - P.ys_true[((size_t)bb * K + kk) * NL + j];
-            row = row + e * e;
-            if (doit && P.xs_o && lane_valid && pass == 0) P.xs_o[(((size_t)ind * P.B + b) * K + kk) * NL + j] = lat;
+    for (int b0 = 0; b0 < P.B; b0 += 32) {
+      const int b = b0 + lane;
+      const bool lane_valid = b < P.B;
+      const int bb = lane_valid ? b : P.B - 1;
+      Env<ENV> env;
+      if (KIND != MTGP_EVAL_SR) env.init(P, bb);
+      if (KIND != MTGP_EVAL_SR)
+        for (int i = 0; i < P.n_targets; i++) lb[(P.slot_target + i) * 32] = P.targets[bb * P.n_targets + i];
+
+      // vector field of the evaluator at (t, src): writes dst[i] = scale * f_i  (i < DT)
+      auto vector_field = [&](float t, const float* src, float* dst, float scale, float* raw) {
+        float x[DR], y[DR], dx[DR];
+        for (int j = 0; j < NL; j++) lb[(P.slot_lat + j) * 32] = src[(D + j) * 32];
+        if (KIND != MTGP_EVAL_SR) {
+#pragma unroll
+          for (int i = 0; i < D; i++) x[i] = src[i * 32];
+          env.template f_obs<NOISE ? 2 : 0>(t, x, y, n_obs, P.obs_noise, P.partitionable, nullptr, 0);
+          if (KIND == MTGP_EVAL_STATIC) {
+#pragma unroll
+            for (int i = 0; i < D; i++)
+              if (i < n_obs) lb[i * 32] = y[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < D; i++)
+              if (i < n_obs) lb[i * 32] = 0.0f;
+            lb[P.slot_u * 32] = 0.0f;
           }
-          if (doit) sr_total = sr_total + row;
-        } else {
-          float xs[DR], ys[DR];
+          const float u = mtgp_interpret_wide(prog_readout, lbytes);
+          env.drift(x, u, dx);
 #pragma unroll
-          for (int i = 0; i < D; i++) xs[i] = sv[i * 32];
-          for (int j = 0; j < NL; j++) {
-            const float lat = sv[(D + j) * 32];
-            lb[(P.slot_lat + j) * 32] = lat;
-            if (doit && P.act_o && lane_valid && pass == 0) P.act_o[(((size_t)ind * P.B + b) * K + kk) * NL + j] = lat;
+          for (int i = 0; i < D; i++) {
+            dst[i * 32] = scale * dx[i];
+            if (raw) raw[i * 32] = dx[i];
           }
-          env.template f_obs<NOISE ? 2 : 0>(tk, xs, ys, n_obs, P.obs_noise, P.partitionable, nullptr, 0);
+          if (KIND == MTGP_EVAL_DYNAMIC) {
 #pragma unroll
-          for (int i = 0; i < D; i++)
-            if (i < n_obs) lb[i * 32] = ys[i];
-          if (KIND == MTGP_EVAL_DYNAMIC) lb[P.slot_u * 32] = 0.0f;
-          const float uk = mtgp_interpret_wide(prog_readout, lbytes);
-          const float qk = (ENV == MTGP_ENV_ACROBOT) ? tk / dts : 0.0f;
-          if (doit) {
-            if (ENV == MTGP_ENV_ACROBOT && qk > (float)(kk + 1)) viol = true;
-            env.cost_add(kk, qk, xs, uk, fs_known);
-            if (lane_valid && pass == 0 && (P.xs_o || P.ys_o || P.us_o)) {
-              const size_t o = ((size_t)ind * P.B + b) * K + kk;
-              if (P.xs_o)
-#pragma unroll
-                for (int i = 0; i < D; i++) P.xs_o[o * D + i] = xs[i];
-              if (P.ys_o)
-#pragma unroll
-                for (int i = 0; i < D; i++)
-                  if (i < n_obs) P.ys_o[o * n_obs + i] = ys[i];
-              if (P.us_o) P.us_o[o] = uk;
-            }
+            for (int i = 0; i < D; i++)
+              if (i < n_obs) lb[i * 32] = y[i];
+            lb[P.slot_u * 32] = u;
           }
+        }
+        for (int j = 0; j < NL; j++) {
+          const float f = mtgp_interpret_wide(wide_s + 32u * (uint32_t)woff[j], lbytes);
+          dst[(D + j) * 32] = scale * f;
+          if (raw) raw[(D + j) * 32] = f;
         }
       };
-
-      // One iteration = one attempted step of every lane that is still integrating, followed by the
-      // save points that step covers (per lane).  When no lane integrates any more, the remaining save
-      // points of every lane are drained from the inf pre-fill of SaveAt -- through the same code.
-      while (true) {
-        const bool stepping = __ballot_sync(0xFFFFFFFFu, active && lane_valid) != 0u;
-        if (!stepping && __ballot_sync(0xFFFFFFFFu, k < K) == 0u) break;
-        const float dt = tnext - tprev;
-        bool keep = true, nan_err = false;
-        float new_tprev = tprev, new_tnext = tnext;
-        if (stepping) {
-          // ---- stages (Euler: one; Dopri5: seven, the first one reused under FSAL) ----
-          const int n_stages = dopri ? 7 : 1;
-          const bool need_f0 = !dopri || (__ballot_sync(0xFFFFFFFFu, !fsal_valid) != 0u);
-          for (int st = 0; st < n_stages; st++) {
-            const float* src = Y;
-            float tst = tprev;
-            if (st > 0) {
-              for (int i = 0; i < DT; i++) {
-                float acc = 0.0f;
-                for (int j = 0; j < st; j++) {
-                  const float term = DP_A[st - 1][j] * KS[(j * DT + i) * 32];
-                  acc = (j == 0) ? term : acc + term;
-                }
-                YI[i * 32] = Y[i * 32] + acc;
-              }
-              if (st == 6)
-                for (int i = 0; i < DT; i++) Y1[i * 32] = YI[i * 32];
-              const float cst = DP_C[st - 1];
-              tst = (cst == 1.0f) ? tnext : tprev + cst * dt;
-              src = YI;
-            }
-            if (st == 0 && !need_f0) {
-              for (int i = 0; i < DT; i++) KS[i * 32] = dt * F0[i * 32];  // FSAL / same point after a rejection
-            } else {
-              // unscaled copies: stage 0 -> F0; the last stage overwrites YI (dead by then) and becomes
-              // the next step's F0 when this step is accepted
-              float* raw = dopri ? (st == 0 ? F0 : (st == 6 ? YI : nullptr)) : nullptr;
-              vector_field(tst, src, KS + (size_t)st * DT * 32, dt, raw);
-            }
-          }
-          fsal_valid = true;
-          if (!dopri)
-            for (int i = 0; i < DT; i++) Y1[i * 32] = Y[i * 32] + KS[i * 32];
-          // ---- step-size controller ----
-          if (!pid) {
-            new_tprev = tnext;
-            new_tnext = tnext + P.dt0;
-          } else {
-            float sumsq = 0.0f;
-            for (int i = 0; i < DT; i++) {
-              float yerr = 0.0f;
-              for (int j = 0; j < 7; j++) {
-                const float term = DP_BERR[j] * KS[(j * DT + i) * 32];
-                yerr = (j == 0) ? term : yerr + term;
-              }
-              const float ym = mtgp_maximumf(mtgp_absf(Y[i * 32]), mtgp_absf(Y1[i * 32]));
-              const float sc = yerr / (P.atol + ym * P.rtol);
-              sumsq = sumsq + sc * sc;
-            }
-            const float scaled_error = mtgp_sqrtf(sumsq / (float)DT);
-            keep = (scaled_error < 1.0f) || at_dtmin;
-            const float inv_err = (scaled_error == 0.0f) ? mtgp_inff() : 1.0f / scaled_error;
-            const float factor1 = (P.coeff1 == 0.0f) ? 1.0f : mtgp_expf(P.coeff1 * mtgp_logf(inv_err));
-            const float factor2 = (P.coeff2 == 0.0f) ? 1.0f : mtgp_expf(P.coeff2 * mtgp_logf(prev_inv));
-            const float factor3 = (P.coeff3 == 0.0f) ? 1.0f : mtgp_expf(P.coeff3 * mtgp_logf(prev_prev_inv));
-            const float fmin = keep ? 1.0f : P.factormin;
-            float factor = ((P.safety * factor1) * factor2) * factor3;
-            factor = clip_jnp(factor, fmin, P.factormax);
-            float ndt = dt * factor;
-            if (P.dtmin > 0.0f) {
-              at_dtmin = (ndt <= P.dtmin);
-              ndt = (ndt != ndt) ? ndt : (ndt > P.dtmin ? ndt : P.dtmin);
-            }
-            new_tprev = keep ? tnext : tprev;
-            new_tnext = new_tprev + ndt;
-            if (keep && active) { prev_prev_inv = prev_inv; prev_inv = inv_err; }
-            nan_err = (scaled_error != scaled_error);
-          }
-          new_tprev = new_tprev < t1 ? new_tprev : t1;
-          {
-            const bool clip = new_tnext > t1 - 1e-6f;
-            const float tclip = keep ? t1 : new_tprev + 0.5f * (t1 - new_tprev);
-            new_tnext = clip ? tclip : new_tnext;
-          }
+      auto bad_state = [&](const float* src) {
+        bool bad = false;
+        if (KIND != MTGP_EVAL_SR) {
+          float x[DR];
+#pragma unroll
+          for (int i = 0; i < D; i++) x[i] = src[i * 32];
+          bad = env.bad_state(x);
         }
-        const bool commit = stepping && active && keep && !nan_err;
-        // ---- SaveAt(ts): every lane has its own pending save points ----
-        while (true) {
+        for (int j = 0; j < NL; j++) bad |= !mtgp_isfinitef(src[(D + j) * 32]);
+        return bad;
+      };
+
+      int fs_known = -1;
+      bool viol = false;
+      float traj_fitness = 0.0f;
+      for (int pass = 0; pass < 2; pass++) {
+        if (KIND != MTGP_EVAL_SR) {
+#pragma unroll
+          for (int i = 0; i < D; i++) Y[i * 32] = P.x0[bb * D + i];
+        }
+        for (int j = 0; j < NL; j++) Y[(D + j) * 32] = (KIND == MTGP_EVAL_SR) ? P.x0[bb * NL + j] : 0.0f;
+        if (KIND != MTGP_EVAL_SR) { env.sum = 0.0f; env.sum0 = 0.0f; env.fs = -1; }
+        float sr_total = 0.0f;
+        bool ev_old_bad = bad_state(Y);
+        bool active = true, fsal_valid = false, at_dtmin = false;  // fsal_valid: F0 holds f(tprev, Y)
+        float tprev = t0, tnext = t0 + P.dt0;
+        tnext = tnext < t1 ? tnext : t1;
+        float prev_inv = 1.0f, prev_prev_inv = 1.0f;
+        int num_steps = 0, k = 0;
+
+        // one save point of the post-pass for the lanes with `doit`; xs/lat hold the saved state
+        auto save_point = [&](bool doit, const float* sv /* DT components at sv[i*32] */) {
           const int kk = k < K ? k : K - 1;
           const float tk = ts[kk];
-          const bool pending = (k < K) && (stepping ? (commit && tk <= tnext) : true);
-          if (__ballot_sync(0xFFFFFFFFu, pending) == 0u) break;
-          const float th = (tprev == tnext) ? 0.0f : (tk - tprev) / (tnext - tprev);
-          for (int i = 0; i < DT; i++) {
-            const float y0 = Y[i * 32], y1 = Y1[i * 32];
-            float v;
-            if (!dopri) {
-              v = y0 + th * (y1 - y0);
-            } else {
-              float acc = 0.0f;
-              for (int j = 0; j < 7; j++) {
-                const float term = DP_CMID[j] * KS[(j * DT + i) * 32];
-                acc = (j == 0) ? term : acc + term;
-              }
-              const float ymid = y0 + acc;
-              const float f0 = KS[i * 32], f1 = KS[(6 * DT + i) * 32];
-              const float a = ((2.0f * (f1 - f0)) - (8.0f * (y1 + y0))) + (16.0f * ymid);
-              const float bq = ((((5.0f * f0) - (3.0f * f1)) + (18.0f * y0)) + (14.0f * y1)) - (32.0f * ymid);
-              const float cq = ((((f1 - (4.0f * f0)) - (11.0f * y0)) - (5.0f * y1))) + (16.0f * ymid);
-              v = ((((a * th + bq) * th + cq) * th + f0) * th) + y0;
+          if (KIND == MTGP_EVAL_SR) {
+            float row = 0.0f;
+            for (int j = 0; j < NL; j++) {
+              const float lat = sv[j * 32];
+              const float e = lat - P.ys_true[((size_t)bb * K + kk) * NL + j];
+              row = row + e * e;
+              if (doit && P.xs_o && lane_valid && pass == 0) P.xs_o[(((size_t)ind * P.B + b) * K + kk) * NL + j] = lat;
             }
-            SV[i * 32] = stepping ? v : mtgp_inff();  // drained save points keep the inf pre-fill
-          }
-          save_point(pending, SV);
-          if (pending) k++;
-        }
-        if (stepping) {
-          // ---- Event + commit ----
-          const bool bad = bad_state(Y1);
-          const bool fired = (bad != ev_old_bad);
-          if (commit) {
-            ev_old_bad = bad;
-            my_steps += (pass == 0 && lane_valid) ? 1u : 0u;
-            for (int i = 0; i < DT; i++) {
-              Y[i * 32] = Y1[i * 32];
-              if (dopri) F0[i * 32] = YI[i * 32];  // unscaled f at (tnext, y1)
-            }
-          }
-          if (active) {
-            num_steps++;
-            tprev = new_tprev;
-            tnext = new_tnext;
-            if ((commit && fired) || nan_err || !(tprev < t1) || num_steps >= P.max_steps) active = false;
-          }
-        }
-      }
-      traj_fitness = (KIND == MTGP_EVAL_SR) ? sr_total / (float)K : env.cost_finish(K, fs_known);
-      if (ENV != MTGP_ENV_ACROBOT || pass == 1) break;
-      if (__ballot_sync(0xFFFFFFFFu, viol) == 0u) break;
-      fs_known = env.fs < 0 ? 0 : env.fs;
-    }
-    if (lane_valid) {
-      if (P.tf_o) P.tf_o[(size_t)ind * P.B + b] = traj_fitness;
-      fit_sum = fit_sum + (mtgp_isfinitef(traj_fitness) ? traj_fitness : P.max_fitness);
-    }
-  }
+            if (doit) sr_total = sr_total + row;
+          } else {
+            float xs[DR], ys[DR];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) fit_sum = fit_sum + __shfl_xor_sync(0xFFFFFFFFu, fit_sum, o);
-  unsigned long long warp_steps = my_steps;
-  for (int o = 16; o > 0; o >>= 1) warp_steps += __shfl_xor_sync(0xFFFFFFFFu, warp_steps, o);
-  if (lane == 0) {
-    float f = clip_jnp(fit_sum / (float)P.B, 0.0f, P.max_fitness);
-    if (P.live) {
-      int cnt = 0;
-      for (int t = 0; t < P.T; t++) cnt += P.live[(size_t)ind * P.T + t];
-      f = f + P.size_parsimony * (float)cnt;
+            for (int i = 0; i < D; i++) xs[i] = sv[i * 32];
+            for (int j = 0; j < NL; j++) {
+              const float lat = sv[(D + j) * 32];
+              lb[(P.slot_lat + j) * 32] = lat;
+              if (doit && P.act_o && lane_valid && pass == 0) P.act_o[(((size_t)ind * P.B + b) * K + kk) * NL + j] = lat;
+            }
+            env.template f_obs<NOISE ? 2 : 0>(tk, xs, ys, n_obs, P.obs_noise, P.partitionable, nullptr, 0);
+#pragma unroll
+            for (int i = 0; i < D; i++)
+              if (i < n_obs) lb[i * 32] = ys[i];
+            if (KIND == MTGP_EVAL_DYNAMIC) lb[P.slot_u * 32] = 0.0f;
+            const float uk = mtgp_interpret_wide(prog_readout, lbytes);
+            const float qk = (ENV == MTGP_ENV_ACROBOT) ? tk / dts : 0.0f;
+            if (doit) {
+              if (ENV == MTGP_ENV_ACROBOT && qk > (float)(kk + 1)) viol = true;
+              env.cost_add(kk, qk, xs, uk, fs_known);
+              if (lane_valid && pass == 0 && (P.xs_o || P.ys_o || P.us_o)) {
+                const size_t o = ((size_t)ind * P.B + b) * K + kk;
+                if (P.xs_o)
+#pragma unroll
+                  for (int i = 0; i < D; i++) P.xs_o[o * D + i] = xs[i];
+                if (P.ys_o)
+#pragma unroll
+                  for (int i = 0; i < D; i++)
+                    if (i < n_obs) P.ys_o[o * n_obs + i] = ys[i];
+                if (P.us_o) P.us_o[o] = uk;
+              }
+            }
+          }
+        };
+
+        // One iteration = one attempted step of every lane that is still integrating, followed by the
+        // save points that step covers (per lane).  When no lane integrates any more, the remaining save
+        // points of every lane are drained from the inf pre-fill of SaveAt -- through the same code.
+        while (true) {
+          const bool stepping = __ballot_sync(0xFFFFFFFFu, active && lane_valid) != 0u;
+          if (!stepping && __ballot_sync(0xFFFFFFFFu, k < K) == 0u) break;
+          const float dt = tnext - tprev;
+          bool keep = true, nan_err = false;
+          float new_tprev = tprev, new_tnext = tnext;
+          if (stepping) {
+            // ---- stages (Euler: one; Dopri5: seven, the first one reused under FSAL) ----
+            const int n_stages = dopri ? 7 : 1;
+            const bool need_f0 = !dopri || (__ballot_sync(0xFFFFFFFFu, !fsal_valid) != 0u);
+            for (int st = 0; st < n_stages; st++) {
+              const float* src = Y;
+              float tst = tprev;
+              if (st > 0) {
+                for (int i = 0; i < DT; i++) {
+                  float acc = 0.0f;
+                  for (int j = 0; j < st; j++) {
+                    const float term = DP_A[st - 1][j] * KS[(j * DT + i) * 32];
+                    acc = (j == 0) ? term : acc + term;
+                  }
+                  YI[i * 32] = Y[i * 32] + acc;
+                }
+                if (st == 6)
+                  for (int i = 0; i < DT; i++) Y1[i * 32] = YI[i * 32];
+                const float cst = DP_C[st - 1];
+                tst = (cst == 1.0f) ? tnext : tprev + cst * dt;
+                src = YI;
+              }
+              if (st == 0 && !need_f0) {
+                for (int i = 0; i < DT; i++) KS[i * 32] = dt * F0[i * 32];  // FSAL / same point after a rejection
+              } else {
+                // unscaled copies: stage 0 -> F0; the last stage overwrites YI (dead by then) and becomes
+                // the next step's F0 when this step is accepted
+                float* raw = dopri ? (st == 0 ? F0 : (st == 6 ? YI : nullptr)) : nullptr;
+                vector_field(tst, src, KS + (size_t)st * DT * 32, dt, raw);
+              }
+            }
+            fsal_valid = true;
+            if (!dopri)
+              for (int i = 0; i < DT; i++) Y1[i * 32] = Y[i * 32] + KS[i * 32];
+            // ---- step-size controller ----
+            if (!pid) {
+              new_tprev = tnext;
+              new_tnext = tnext + P.dt0;
+            } else {
+              float sumsq = 0.0f;
+              for (int i = 0; i < DT; i++) {
+                float yerr = 0.0f;
+                for (int j = 0; j < 7; j++) {
+                  const float term = DP_BERR[j] * KS[(j * DT + i) * 32];
+                  yerr = (j == 0) ? term : yerr + term;
+                }
+                const float ym = mtgp_maximumf(mtgp_absf(Y[i * 32]), mtgp_absf(Y1[i * 32]));
+                const float sc = yerr / (P.atol + ym * P.rtol);
+                sumsq = sumsq + sc * sc;
+              }
+              const float scaled_error = mtgp_sqrtf(sumsq / (float)DT);
+              keep = (scaled_error < 1.0f) || at_dtmin;
+              const float inv_err = (scaled_error == 0.0f) ? mtgp_inff() : 1.0f / scaled_error;
+              const float factor1 = (P.coeff1 == 0.0f) ? 1.0f : mtgp_expf(P.coeff1 * mtgp_logf(inv_err));
+              const float factor2 = (P.coeff2 == 0.0f) ? 1.0f : mtgp_expf(P.coeff2 * mtgp_logf(prev_inv));
+              const float factor3 = (P.coeff3 == 0.0f) ? 1.0f : mtgp_expf(P.coeff3 * mtgp_logf(prev_prev_inv));
+              const float fmin = keep ? 1.0f : P.factormin;
+              float factor = ((P.safety * factor1) * factor2) * factor3;
+              factor = clip_jnp(factor, fmin, P.factormax);
+              float ndt = dt * factor;
+              if (P.dtmin > 0.0f) {
+                at_dtmin = (ndt <= P.dtmin);
+                ndt = (ndt != ndt) ? ndt : (ndt > P.dtmin ? ndt : P.dtmin);
+              }
+              new_tprev = keep ? tnext : tprev;
+              new_tnext = new_tprev + ndt;
+              if (keep && active) { prev_prev_inv = prev_inv; prev_inv = inv_err; }
+              nan_err = (scaled_error != scaled_error);
+            }
+            new_tprev = new_tprev < t1 ? new_tprev : t1;
+            {
+              const bool clip = new_tnext > t1 - 1e-6f;
+              const float tclip = keep ? t1 : new_tprev + 0.5f * (t1 - new_tprev);
+              new_tnext = clip ? tclip : new_tnext;
+            }
+          }
+          const bool commit = stepping && active && keep && !nan_err;
+          // ---- SaveAt(ts): every lane has its own pending save points ----
+          while (true) {
+            const int kk = k < K ? k : K - 1;
+            const float tk = ts[kk];
+            const bool pending = (k < K) && (stepping ? (commit && tk <= tnext) : true);
+            if (__ballot_sync(0xFFFFFFFFu, pending) == 0u) break;
+            const float th = (tprev == tnext) ? 0.0f : (tk - tprev) / (tnext - tprev);
+            for (int i = 0; i < DT; i++) {
+              const float y0 = Y[i * 32], y1 = Y1[i * 32];
+              float v;
+              if (!dopri) {
+                v = y0 + th * (y1 - y0);
+              } else {
+                float acc = 0.0f;
+                for (int j = 0; j < 7; j++) {
+                  const float term = DP_CMID[j] * KS[(j * DT + i) * 32];
+                  acc = (j == 0) ? term : acc + term;
+                }
+                const float ymid = y0 + acc;
+                const float f0 = KS[i * 32], f1 = KS[(6 * DT + i) * 32];
+                const float a = ((2.0f * (f1 - f0)) - (8.0f * (y1 + y0))) + (16.0f * ymid);
+                const float bq = ((((5.0f * f0) - (3.0f * f1)) + (18.0f * y0)) + (14.0f * y1)) - (32.0f * ymid);
+                const float cq = ((((f1 - (4.0f * f0)) - (11.0f * y0)) - (5.0f * y1))) + (16.0f * ymid);
+                v = ((((a * th + bq) * th + cq) * th + f0) * th) + y0;
+              }
+              SV[i * 32] = stepping ? v : mtgp_inff();  // drained save points keep the inf pre-fill
+            }
+            save_point(pending, SV);
+            if (pending) k++;
+          }
+          if (stepping) {
+            // ---- Event + commit ----
+            const bool bad = bad_state(Y1);
+            const bool fired = (bad != ev_old_bad);
+            if (commit) {
+              ev_old_bad = bad;
+              my_steps += (pass == 0 && lane_valid) ? 1u : 0u;
+              for (int i = 0; i < DT; i++) {
+                Y[i * 32] = Y1[i * 32];
+                if (dopri) F0[i * 32] = YI[i * 32];  // unscaled f at (tnext, y1)
+              }
+            }
+            if (active) {
+              num_steps++;
+              tprev = new_tprev;
+              tnext = new_tnext;
+              if ((commit && fired) || nan_err || !(tprev < t1) || num_steps >= P.max_steps) active = false;
+            }
+          }
+        }
+        traj_fitness = (KIND == MTGP_EVAL_SR) ? sr_total / (float)K : env.cost_finish(K, fs_known);
+        if (ENV != MTGP_ENV_ACROBOT || pass == 1) break;
+        if (__ballot_sync(0xFFFFFFFFu, viol) == 0u) break;
+        fs_known = env.fs < 0 ? 0 : env.fs;
+      }
+      if (lane_valid) {
+        if (P.tf_o) P.tf_o[(size_t)ind * P.B + b] = traj_fitness;
+        fit_sum = fit_sum + (mtgp_isfinitef(traj_fitness) ? traj_fitness : P.max_fitness);
+      }
     }
-    P.fitness[ind] = f;
-    if (P.steps_done) atomicAdd(P.steps_done, warp_steps);
-  }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) fit_sum = fit_sum + __shfl_xor_sync(0xFFFFFFFFu, fit_sum, o);
+    unsigned long long warp_steps = my_steps;
+    for (int o = 16; o > 0; o >>= 1) warp_steps += __shfl_xor_sync(0xFFFFFFFFu, warp_steps, o);
+    if (lane == 0) {
+      float f = clip_jnp(fit_sum / (float)P.B, 0.0f, P.max_fitness);
+      if (P.live) {
+        int cnt = 0;
+        for (int t = 0; t < P.T; t++) cnt += P.live[(size_t)ind * P.T + t];
+        f = f + P.size_parsimony * (float)cnt;
+      }
+      P.fitness[ind] = f;
+      if (P.steps_done) atomicAdd(P.steps_done, warp_steps);
+    }
+    __syncwarp();  // the value file and the program area are reused by the next individual
+  }  // persistent loop
 }
 
 template <int KIND, int ENV>
@@ -405,7 +420,22 @@ int launch_rk(RolloutParams rp, cudaStream_t stream) {
     mtgp_set_error("adaptive rollout needs %zu bytes of shared memory per CTA: over the 227 KB limit", smem);
     return MTGP_ERR_UNSUPPORTED;
   }
-  const unsigned blocks = (unsigned)((rp.P + kRkWarps - 1) / kRkWarps);
+  unsigned blocks = (unsigned)((rp.P + kRkWarps - 1) / kRkWarps);
+  rp.next_slot = nullptr;
+  {
+    int dev = 0, n_sm = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+    const size_t per_cta = smem + 1024;  // + the per-CTA reservation
+    size_t fit = ((size_t)228 * 1024) / per_cta;
+    if (fit > MTGP_RK_MIN_CTAS) fit = MTGP_RK_MIN_CTAS;
+    if (fit < 1) fit = 1;
+    const unsigned resident = (unsigned)(n_sm * fit);
+    if (rp.order && blocks > resident) {
+      rp.next_slot = const_cast<int*>(rp.order) + rp.P;
+      blocks = resident;
+    }
+  }
   constexpr int ENVD = (KIND == MTGP_EVAL_SR) ? 0 : EnvDim<ENV>::D;
   const bool fixed = (KIND != MTGP_EVAL_SR) && rp.n_obs == ENVD &&
                      (KIND == MTGP_EVAL_STATIC ? rp.n_latent == 0 : rp.n_latent == 2);

@@ -160,6 +160,14 @@ def test_populations_larger_than_the_resident_warps(engine, oracle):
         gpu = _gpu_rollout(engine, lib, pop, data, count_steps=True)
         _assert_fitness(gpu["fitness"], ref["fitness"], 1e4)
         assert int(gpu["steps"][0]) == ref["steps"], env_name
+    # the adaptive kernel keeps at most 20 one-warp CTAs per SM resident: 4 000 individuals make it persistent too
+    lib, pop, data = util.control_case("acrobot", abi.EVAL_DYNAMIC, rng, P=4000, B=4, obs_noise=0.1, max_steps=1000,
+                                       T_end=2.0, dt_save=0.2, dt0=0.05)
+    util.with_solver(data, **util.DOPRI_PID)
+    ref = oracle.rollout_population(pop, lib.table(), data)
+    gpu = _gpu_rollout(engine, lib, pop, data, count_steps=True)
+    _assert_fitness(gpu["fitness"], ref["fitness"], 1e4)
+    assert int(gpu["steps"][0]) == ref["steps"]
 
 
 def test_inline_noise_generator_matches_the_table(engine, oracle, monkeypatch):
