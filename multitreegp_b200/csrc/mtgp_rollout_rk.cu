@@ -40,6 +40,13 @@ constexpr int kRkWarps = 1;  // one warp per CTA: the adaptive workloads are sma
 // SPEC as in k_rollout: 0 generic; 2 = every state component observed and the latent count known (static: 0,
 // dynamic: 2), so that D + n_latent, the solver-array offsets and the component loops are compile-time.
 template <int KIND, int ENV, bool NOISE, int SPEC>
+// the solver's component loops stay rolled: the kernel's hot loop is far larger than the instruction cache,
+// and code size costs more than loop overhead here
+#ifdef MTGP_RK_UNROLL
+#define MTGP_RK_LOOP
+#else
+#define MTGP_RK_LOOP _Pragma("unroll 1")
+#endif
 #ifndef MTGP_RK_MIN_CTAS
 #define MTGP_RK_MIN_CTAS 20  // 96 registers: measured best on the DynamicPolicy notebook configuration
 #endif
@@ -264,8 +271,10 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
               const float* src = Y;
               float tst = tprev;
               if (st > 0) {
+                MTGP_RK_LOOP
                 for (int i = 0; i < DT; i++) {
                   float acc = 0.0f;
+                  MTGP_RK_LOOP
                   for (int j = 0; j < st; j++) {
                     const float term = DP_A[st - 1][j] * KS[(j * DT + i) * 32];
                     acc = (j == 0) ? term : acc + term;
@@ -296,6 +305,7 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
               new_tnext = tnext + P.dt0;
             } else {
               float sumsq = 0.0f;
+              MTGP_RK_LOOP
               for (int i = 0; i < DT; i++) {
                 float yerr = 0.0f;
                 for (int j = 0; j < 7; j++) {
