@@ -111,19 +111,36 @@ __device__ __forceinline__ float bits_to_normal(uint32_t bits) {
   return 1.41421356f * mtgp_erfinvf(u);
 }
 
-// normal(fold_in(key, bits(t)), (n,)) for n <= 4
-template <int NMAXOBS>
+// Single out-of-line copies for the in-kernel noise generator (the adaptive kernel's hot loop is far larger
+// than the instruction cache: five inlined threefry blocks and four erfinv polynomials are 1 000 instructions).
+static __device__ __noinline__ uint2 threefry2x32_ool(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1) {
+  uint32_t o0, o1;
+  threefry2x32(k0, k1, x0, x1, o0, o1);
+  return make_uint2(o0, o1);
+}
+static __device__ __noinline__ float bits_to_normal_ool(uint32_t bits) { return bits_to_normal(bits); }
+
+// normal(fold_in(key, bits(t)), (n,)) for n <= 4.  OOL: call the out-of-line helpers (same bits).
+template <int NMAXOBS, bool OOL = false>
 __device__ __forceinline__ void obs_normal(uint32_t key0, uint32_t key1, float t, int n, int partitionable,
                                            float* out) {
+  auto tf = [](uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t& o0, uint32_t& o1) {
+    if (OOL) {
+      const uint2 r = threefry2x32_ool(k0, k1, x0, x1);
+      o0 = r.x; o1 = r.y;
+    } else {
+      threefry2x32(k0, k1, x0, x1, o0, o1);
+    }
+  };
   uint32_t f0, f1;
-  threefry2x32(key0, key1, 0u, __float_as_uint(t), f0, f1);
+  tf(key0, key1, 0u, __float_as_uint(t), f0, f1);
   uint32_t bits[NMAXOBS];
   if (partitionable) {
 #pragma unroll
     for (int i = 0; i < NMAXOBS; i++) {
       if (i < n) {
         uint32_t o0, o1;
-        threefry2x32(f0, f1, 0u, (uint32_t)i, o0, o1);
+        tf(f0, f1, 0u, (uint32_t)i, o0, o1);
         bits[i] = o0 ^ o1;
       }
     }
@@ -134,7 +151,7 @@ __device__ __forceinline__ void obs_normal(uint32_t key0, uint32_t key1, float t
       if (i < half) {
         uint32_t o0, o1;
         const uint32_t c1 = (half + i < n) ? (uint32_t)(half + i) : 0u;
-        threefry2x32(f0, f1, (uint32_t)i, c1, o0, o1);
+        tf(f0, f1, (uint32_t)i, c1, o0, o1);
 #pragma unroll
         for (int j = 0; j < NMAXOBS; j++) {
           if (j == i) bits[j] = o0;
@@ -145,7 +162,7 @@ __device__ __forceinline__ void obs_normal(uint32_t key0, uint32_t key1, float t
   }
 #pragma unroll
   for (int i = 0; i < NMAXOBS; i++)
-    if (i < n) out[i] = bits_to_normal(bits[i]);
+    if (i < n) out[i] = OOL ? bits_to_normal_ool(bits[i]) : bits_to_normal(bits[i]);
 }
 
 __device__ __forceinline__ float clip_jnp(float v, float lo, float hi) {
@@ -207,10 +224,11 @@ struct Env {
 
   // EnvironmentBase.f_obs (control_environment_base.py:43-48) + Acrobot.f_obs (acrobot.py:29-32)
   // normal(fold_in(key, bits(t)), (n_obs,)) @ W, W = obs_noise * eye (reactor.py:43 scales it)
+  template <bool OOL = false>
   __device__ __forceinline__ void noise_term(float t, int n_obs, float obs_noise, int partitionable,
                                              float* out) const {
     float nrm[D];
-    obs_normal<D>(key0, key1, t, n_obs, partitionable, nrm);
+    obs_normal<D, OOL>(key0, key1, t, n_obs, partitionable, nrm);
 #pragma unroll
     for (int i = 0; i < D; i++) {
       if (i < n_obs) {
@@ -229,12 +247,12 @@ struct Env {
     }
   }
 
-  // out-of-line copy for the in-kernel generator: ~700 instructions that must not be replicated at
-  // every observation site
+  // out-of-line copy for the in-kernel generator (must not be replicated at every observation site), itself
+  // built from single copies of threefry and erfinv
   struct Noise4 { float v[4]; };
   __device__ __noinline__ Noise4 noise_term_ool(float t, int n_obs, float obs_noise, int partitionable) const {
     float nt[D];
-    noise_term(t, n_obs, obs_noise, partitionable, nt);
+    noise_term<true>(t, n_obs, obs_noise, partitionable, nt);
     Noise4 r;
 #pragma unroll
     for (int i = 0; i < 4; i++) r.v[i] = (i < D) ? nt[i < D ? i : 0] : 0.0f;

@@ -350,6 +350,7 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
             const bool pending = (k < K) && (stepping ? (commit && tk <= tnext) : true);
             if (__ballot_sync(0xFFFFFFFFu, pending) == 0u) break;
             const float th = (tprev == tnext) ? 0.0f : (tk - tprev) / (tnext - tprev);
+            MTGP_RK_LOOP
             for (int i = 0; i < DT; i++) {
               const float y0 = Y[i * 32], y1 = Y1[i * 32];
               float v;
