@@ -28,7 +28,7 @@
 
 using namespace mtgp_dev;
 
-int mtgp_launch_rollout_rk(RolloutParams rp, int kind, int env_id, cudaStream_t stream);
+int mtgp_launch_rollout_rk(RolloutParams rp, int kind, int env_id, int tmp_base, int bound, cudaStream_t stream);
 
 namespace {
 
@@ -596,7 +596,7 @@ int mtgp_launch_rollout(const mtgp_programs& progs, const int32_t* live, int P, 
   rp.prog_words_per_warp = T * progs.lstride;
   const int bound = progs.n_tmp;
   if (d.solver != MTGP_SOLVER_EULER || d.controller != MTGP_CONTROLLER_CONSTANT) {
-    // Dopri5 and/or PIDController: the general kernel, provisioned for the worst case in one launch
+    // Dopri5 and/or PIDController: the general kernel (same two provisioning classes)
     rp.solver = d.solver;
     rp.controller = d.controller;
     rp.rtol = d.rtol; rp.atol = d.atol; rp.dtmin = d.dtmin;
@@ -612,7 +612,7 @@ int mtgp_launch_rollout(const mtgp_programs& progs, const int32_t* live, int P, 
     rp.slot_rk = n_data;
     rp.slots_per_warp = progs.tmp_base + bound + 1;
     rp.wide_cap = T * progs.lstride;
-    return mtgp_launch_rollout_rk(rp, d.kind, d.env_id, stream);
+    return mtgp_launch_rollout_rk(rp, d.kind, d.env_id, progs.tmp_base, bound, stream);
   }
 #define DISPATCH(KIND, ENV) return launch_kind_env<KIND, ENV>(rp, progs.tmp_base, bound, noise_ws, stream)
   if (d.kind == MTGP_EVAL_SR) DISPATCH(MTGP_EVAL_SR, MTGP_ENV_NONE);

@@ -82,15 +82,29 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
     if (slot >= P.P) return;
     const int ind = P.order ? P.order[slot] : slot;
 
-    // ---- stage + pre-decode the programs (same as K2) ----
+    // which launch owns this individual (as in k_rollout): small programs run with a small footprint
+    {
+      int need = 0, total_instr = 0;
+      for (int t = 0; t < P.T; t++) {
+        const uint32_t m = P.meta[(size_t)ind * P.T + t];
+        need = max(need, (int)(m >> 16));
+        total_instr += (int)(m & 0xFFFFu) + 1;
+      }
+      const bool fast = (need <= P.fast_tmp) && (total_instr <= P.fast_instr);
+      if (fast != (P.want_fast != 0)) continue;
+    }
+
+    // ---- stage (back to back) + pre-decode the programs (same as K2) ----
     if (lane == 0) {
       uint32_t total = 0;
       for (int t = 0; t < P.T; t++) total += (((P.meta[(size_t)ind * P.T + t] & 0xFFFFu) + 2u) & ~1u) * 8u;
       mbar_expect_tx(bar, total);
       int off = 0;
+      uint32_t soff = 0;
       for (int t = 0; t < P.T; t++) {
         const uint32_t n = P.meta[(size_t)ind * P.T + t] & 0xFFFFu;
-        bulk_g2s(prog_s + (size_t)t * P.lstride, P.prog + ((size_t)ind * P.T + t) * P.lstride, ((n + 2u) & ~1u) * 8u, bar);
+        bulk_g2s(prog_s + soff, P.prog + ((size_t)ind * P.T + t) * P.lstride, ((n + 2u) & ~1u) * 8u, bar);
+        soff += (n + 2u) & ~1u;
         woff[t] = off;
         off += (int)n + 1;
       }
@@ -103,10 +117,12 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
     bar_phase ^= 1u;
     {
       const uint32_t scratch = (uint32_t)P.slots_per_warp - 1u;
+      uint32_t soff = 0;
       for (int t = 0; t < P.T; t++) {
         const int n = (int)(P.meta[(size_t)ind * P.T + t] & 0xFFFFu) + 1;
         mtgp_wide_instr* dst = wide + woff[t];
-        for (int i = lane; i < n; i += 32) dst[i] = mtgp_expand_instr(prog_s[(size_t)t * P.lstride + i], scratch);
+        for (int i = lane; i < n; i += 32) dst[i] = mtgp_expand_instr(prog_s[soff + i], scratch);
+        soff += ((uint32_t)n + 1u) & ~1u;
       }
     }
     __syncwarp();
@@ -422,8 +438,18 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
   }  // persistent loop
 }
 
+// Two provisioning classes as in the fixed-step kernel: individuals whose programs need at most kFastTmp
+// temporaries and kFastInstr instructions run with a small shared-memory footprint (more resident warps), the
+// rest in a second launch provisioned for the worst case.  Each launch skips the other's individuals.
+constexpr int kFastTmp = 8;
+constexpr int kFastInstr = 64;
+
 template <int KIND, int ENV>
-int launch_rk(RolloutParams rp, cudaStream_t stream) {
+int launch_rk_class(RolloutParams rp, int tmp_base, int n_tmp, int wide_cap, int want_fast, cudaStream_t stream) {
+  rp.slots_per_warp = tmp_base + n_tmp + 1;
+  rp.wide_cap = wide_cap;
+  rp.prog_words_per_warp = (wide_cap + rp.T + 1) & ~1;  // sum over trees of (n + 2) & ~1 <= instructions + T
+  rp.want_fast = want_fast;
   const size_t per_warp = (size_t)rp.prog_words_per_warp * sizeof(uint2) + kMaxTrees * sizeof(int) +
                           (size_t)rp.wide_cap * sizeof(mtgp_wide_instr) + (size_t)rp.slots_per_warp * 128;
   const size_t smem = 16 * kRkWarps + (size_t)kRkWarps * per_warp;
@@ -442,8 +468,8 @@ int launch_rk(RolloutParams rp, cudaStream_t stream) {
     if (fit > MTGP_RK_MIN_CTAS) fit = MTGP_RK_MIN_CTAS;
     if (fit < 1) fit = 1;
     const unsigned resident = (unsigned)(n_sm * fit);
-    if (rp.order && blocks > resident) {
-      rp.next_slot = const_cast<int*>(rp.order) + rp.P;
+    if (rp.order && blocks > resident) {  // persistent warps (see k_rollout)
+      rp.next_slot = const_cast<int*>(rp.order) + rp.P + (want_fast ? 0 : 1);
       blocks = resident;
     }
   }
@@ -468,10 +494,21 @@ int launch_rk(RolloutParams rp, cudaStream_t stream) {
   return mtgp_check_launch("k_rollout_rk");
 }
 
+template <int KIND, int ENV>
+int launch_rk(RolloutParams rp, int tmp_base, int bound, cudaStream_t stream) {
+  const int worst_instr = rp.T * rp.lstride;
+  const bool all_fast = (bound <= kFastTmp) && (worst_instr <= kFastInstr);
+  rp.fast_tmp = all_fast ? bound : kFastTmp;
+  rp.fast_instr = all_fast ? worst_instr : kFastInstr;
+  int rc = launch_rk_class<KIND, ENV>(rp, tmp_base, rp.fast_tmp, rp.fast_instr, 1, stream);
+  if (rc == MTGP_OK && !all_fast) rc = launch_rk_class<KIND, ENV>(rp, tmp_base, bound, worst_instr, 0, stream);
+  return rc;
+}
+
 }  // namespace
 
-int mtgp_launch_rollout_rk(RolloutParams rp, int kind, int env_id, cudaStream_t stream) {
-#define DISPATCH(KIND, ENV) return launch_rk<KIND, ENV>(rp, stream)
+int mtgp_launch_rollout_rk(RolloutParams rp, int kind, int env_id, int tmp_base, int bound, cudaStream_t stream) {
+#define DISPATCH(KIND, ENV) return launch_rk<KIND, ENV>(rp, tmp_base, bound, stream)
   if (kind == MTGP_EVAL_SR) DISPATCH(MTGP_EVAL_SR, MTGP_ENV_NONE);
   if (kind == MTGP_EVAL_STATIC) {
     if (env_id == MTGP_ENV_ACROBOT) DISPATCH(MTGP_EVAL_STATIC, MTGP_ENV_ACROBOT);

@@ -267,18 +267,29 @@ def test_configuration_corners(engine, oracle):
     lib = util.control_library(env, abi.EVAL_DYNAMIC, state_size=2, ops=util.OPS_SR)
     cases.append((lib, sample_population(rng, 10, lib, 7, 127, full=True),
                   util.control_data(env, abi.EVAL_DYNAMIC, rng, 8, 2.0, 0.2, 0.05, 2, "Different")))
+    # the same size without division, small coefficients: finite trajectories through the worst-case launch
+    env = HarmonicOscillator(0.0, 0.05)
+    lib = util.control_library(env, abi.EVAL_DYNAMIC, state_size=2, ops=util.OPS_CONTROL)
+    big = sample_population(rng, 12, lib, 7, 127, full=True)
+    big[..., 3] *= 0.3
+    cases.append((lib, big, util.control_data(env, abi.EVAL_DYNAMIC, rng, 8, 2.0, 0.2, 0.05, 2, "Different")))
     # max_nodes 255 with ordinary (sparse) trees, static policy, noise on
     env = HarmonicOscillator(0.0, 0.05)
     lib = util.control_library(env, abi.EVAL_STATIC, ops=util.OPS_ALL)
     cases.append((lib, sample_population(rng, 40, lib, 8, 255),
                   util.control_data(env, abi.EVAL_STATIC, rng, 8, 3.0, 0.2, 0.05, 0, "Different")))
-    for lib, pop, data in cases:
-        ref = oracle.rollout_population(pop, lib.table(), data, trajectories=True)
-        gpu = _gpu_rollout(engine, lib, pop, data, trajectories=True, count_steps=True)
-        for k in ("xs", "ys", "us", "traj_fitness"):
-            assert util.same_or_both_nan(gpu[k], ref[k]).all(), k
-        _assert_fitness(gpu["fitness"], ref["fitness"], 1e4)
-        assert int(gpu["steps"][0]) == ref["steps"]
+    for adaptive in (False, True):  # the fixed-step kernel, then the same corners through the adaptive one
+        for lib, pop, data in cases:
+            if adaptive:
+                util.with_solver(data, max_steps=400, **util.DOPRI_PID)
+            ref = oracle.rollout_population(pop, lib.table(), data, trajectories=True)
+            gpu = _gpu_rollout(engine, lib, pop, data, trajectories=True, count_steps=True)
+            for k in ("xs", "ys", "us", "traj_fitness"):
+                assert util.same_or_both_nan(gpu[k], ref[k]).all(), (k, adaptive)
+            _assert_fitness(gpu["fitness"], ref["fitness"], 1e4)
+            assert int(gpu["steps"][0]) == ref["steps"]
+            if pop is big:
+                assert (ref["fitness"] < 1e4).any()  # the big-tree case is not just the penalty
     # SR with three trees (a 3-dimensional system)
     from multitreegp_b200.node_library import NodeLibrary
     from multitreegp_b200.rollout_data import RolloutData
