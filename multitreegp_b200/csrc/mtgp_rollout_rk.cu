@@ -48,7 +48,7 @@ template <int KIND, int ENV, bool NOISE, int SPEC>
 #define MTGP_RK_LOOP _Pragma("unroll 1")
 #endif
 #ifndef MTGP_RK_MIN_CTAS
-#define MTGP_RK_MIN_CTAS 20  // 96 registers: measured best on the DynamicPolicy notebook configuration
+#define MTGP_RK_MIN_CTAS 16  // 122 registers, no spills; shared memory allows 15 resident CTAs for the fast class
 #endif
 __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(const RolloutParams P) {
   constexpr int D = (KIND == MTGP_EVAL_SR) ? 0 : EnvDim<ENV>::D;
