@@ -86,7 +86,9 @@ __global__ void __launch_bounds__(256) k_noise_table(const RolloutParams P, cons
 // SPEC: launch-time facts promoted to compile time for the configurations the notebooks use
 //   0 generic; 1 every state component is observed (n_obs == D); 2 = 1 + a dynamic policy with two latent
 //   states (DynamicPolicy.ipynb: state_size = 2).  The per-component predicates and the latent loops vanish.
-template <int KIND, int ENV, int NOISE, int SPEC>
+// TRAJ_OUT: the evaluate_candidate outputs (xs, ys, us, activities, per-trajectory fitness) are requested.
+// Population evaluation never asks for them, and without their code the hot loop is 120 instructions shorter.
+template <int KIND, int ENV, int NOISE, int SPEC, bool TRAJ_OUT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_rollout(const RolloutParams P) {
   constexpr int D = (KIND == MTGP_EVAL_SR) ? 0 : EnvDim<ENV>::D;
   constexpr int DR = D > 0 ? D : 1;
@@ -318,10 +320,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
               if (KIND == MTGP_EVAL_SR) {
                 const float e = lat - P.ys_true[((size_t)bb * K + k) * NL + j];
                 row = row + e * e;
-                if (P.xs_o && lane_valid && pass == 0) P.xs_o[(((size_t)ind * P.B + b) * K + k) * NL + j] = lat;
+                if (TRAJ_OUT && P.xs_o && lane_valid && pass == 0) P.xs_o[(((size_t)ind * P.B + b) * K + k) * NL + j] = lat;
               } else {
                 mtgp_sts_f32(a_lat + 128u * j, lat);
-                if (P.act_o && lane_valid && pass == 0) P.act_o[(((size_t)ind * P.B + b) * K + k) * NL + j] = lat;
+                if (TRAJ_OUT && P.act_o && lane_valid && pass == 0) P.act_o[(((size_t)ind * P.B + b) * K + k) * NL + j] = lat;
               }
             }
             if (KIND == MTGP_EVAL_SR) {
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
               const float qk = (ENV == MTGP_ENV_ACROBOT) ? tk / dts : 0.0f;
               if (ENV == MTGP_ENV_ACROBOT && qk > (float)(k + 1)) viol = true;
               env.cost_add(k, qk, xs, uk, fs_known);
-              if (lane_valid && pass == 0 && (P.xs_o || P.ys_o || P.us_o)) {
+              if (TRAJ_OUT && lane_valid && pass == 0 && (P.xs_o || P.ys_o || P.us_o)) {
                 const size_t o = ((size_t)ind * P.B + b) * K + k;
                 if (P.xs_o)
 #pragma unroll
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
         fs_known = env.fs < 0 ? 0 : env.fs;
       }
       if (lane_valid) {
-        if (P.tf_o) P.tf_o[(size_t)ind * P.B + b] = traj_fitness;
+        if (TRAJ_OUT && P.tf_o) P.tf_o[(size_t)ind * P.B + b] = traj_fitness;
         fit_sum = fit_sum + (mtgp_isfinitef(traj_fitness) ? traj_fitness : P.max_fitness);
       }
     }
@@ -431,7 +433,7 @@ size_t rollout_smem(const RolloutParams& rp) {
   return 16 * kWarpsPerCta + (size_t)kWarpsPerCta * per_warp;
 }
 
-template <int KIND, int ENV, int NOISE, int SPEC>
+template <int KIND, int ENV, int NOISE, int SPEC, bool TRAJ_OUT>
 int launch_one(RolloutParams rp, int tmp_base, int n_tmp, int wide_cap, int want_fast, cudaStream_t stream) {
   rp.slots_per_warp = tmp_base + n_tmp + 1;
   rp.wide_cap = wide_cap;
@@ -442,7 +444,7 @@ int launch_one(RolloutParams rp, int tmp_base, int n_tmp, int wide_cap, int want
     mtgp_set_error("rollout needs %zu bytes of shared memory per CTA: over the 227 KB limit", smem);
     return MTGP_ERR_UNSUPPORTED;
   }
-  auto kern = k_rollout<KIND, ENV, NOISE, SPEC>;
+  auto kern = k_rollout<KIND, ENV, NOISE, SPEC, TRAJ_OUT>;
   MTGP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   unsigned blocks = (unsigned)((rp.P + kWarpsPerCta - 1) / kWarpsPerCta);
   rp.next_slot = nullptr;
@@ -495,11 +497,14 @@ int launch_kind_env(RolloutParams rp, int tmp_base, int bound, void* noise_ws, c
         rp.slot_state != ENVD + 5 + NT || rp.n_latent != 2)
       spec = 1;
   }
-#define LAUNCH1(NZ, SPEC)                                                                             \
+  const bool traj_out = rp.xs_o || rp.ys_o || rp.us_o || rp.act_o || rp.tf_o;
+#define LAUNCH1T(NZ, SPEC, TR)                                                                        \
   {                                                                                                   \
-    rc = launch_one<KIND, ENV, NZ, SPEC>(rp, tmp_base, rp.fast_tmp, rp.fast_instr, 1, stream);        \
-    if (rc == MTGP_OK && !all_fast) rc = launch_one<KIND, ENV, NZ, SPEC>(rp, tmp_base, bound, worst_instr, 0, stream); \
+    rc = launch_one<KIND, ENV, NZ, SPEC, TR>(rp, tmp_base, rp.fast_tmp, rp.fast_instr, 1, stream);    \
+    if (rc == MTGP_OK && !all_fast)                                                                   \
+      rc = launch_one<KIND, ENV, NZ, SPEC, TR>(rp, tmp_base, bound, worst_instr, 0, stream);          \
   }
+#define LAUNCH1(NZ, SPEC) { if (traj_out) LAUNCH1T(NZ, SPEC, true) else LAUNCH1T(NZ, SPEC, false) }
 #define LAUNCH2(NZ)                                                                                   \
   if constexpr (KIND == MTGP_EVAL_SR) LAUNCH1(NZ, 0)                                                  \
   else if constexpr (KIND == MTGP_EVAL_STATIC) { if (spec) LAUNCH1(NZ, 1) else LAUNCH1(NZ, 0) }       \
@@ -507,6 +512,7 @@ int launch_kind_env(RolloutParams rp, int tmp_base, int bound, void* noise_ws, c
   if (noise == 0) { LAUNCH2(0) } else if (noise == 1) { LAUNCH2(1) } else { LAUNCH2(2) }
 #undef LAUNCH2
 #undef LAUNCH1
+#undef LAUNCH1T
   return rc;
 }
 
