@@ -70,3 +70,35 @@ def test_sr_data_tuple_and_unbound_evaluator():
     ev.bind([("+", 2, 0.5), ("*", 2, 0.5)], [["x0", "x1"]], [2])
     t = ev._table()
     assert t.n_ids == 2 + 2 + 2
+
+
+def test_environment_classes_mirror_the_reference_constructors():
+    """acrobot.py:7-27, harmonic_oscillator.py:8-56, reactor.py:7-65: sizes, initial-state bounds, parameter pytrees."""
+    rng = np.random.default_rng(4)
+    ts = np.arange(0, 2, 0.2, dtype=np.float32)
+    acro = Acrobot(0.0, 0.1)
+    assert (acro.n_var, acro.n_control, acro.n_targets, acro.n_obs) == (4, 1, 0, 4)
+    x0, targets = acro.sample_init_states(64, rng)
+    assert x0.shape == (64, 4) and x0.dtype == np.float32 and np.abs(x0).max() <= 0.1   # U(-0.1, 0.1) (acrobot.py:18-22)
+    assert targets.shape == (64, 0)                                                     # zero-size target is legal
+    p = acro.sample_params(8, "Constant", ts, rng)
+    assert len(p) == 4 and all(np.all(a == 1.0) and a.shape == (8,) for a in p)         # l1 = l2 = m1 = m2 = 1
+    assert Acrobot(0.0, 0.0, n_obs=2).n_obs == 2                                        # partial observation
+
+    ho = HarmonicOscillator(0.0, 0.0)
+    assert (ho.n_var, ho.n_control, ho.n_targets) == (2, 1, 1)
+    om, ze = ho.sample_params(16, "Constant", ts, rng)
+    assert np.all(om == 1.0) and np.all(ze == 0.0)
+    om, ze = ho.sample_params(256, "Different", ts, rng)
+    assert 0.0 <= om.min() and om.max() <= 2.0 and 0.0 <= ze.min() and ze.max() <= 1.5
+    with pytest.raises(NotImplementedError):
+        ho.sample_params(4, "Switch", ts, rng)      # time-varying parameters: out of scope, refused loudly
+    x0, targets = ho.sample_init_states(32, rng)
+    assert x0.shape == (32, 2) and targets.shape == (32, 1) and np.abs(targets).max() <= 3.0
+
+    cstr = StirredTankReactor(0.0, 0.0)
+    assert (cstr.n_var, cstr.n_control, cstr.n_targets) == (3, 1, 1)
+    p = cstr.sample_params(8, "Constant", ts, rng)
+    assert len(p) == 8 and all(a.shape == (8,) for a in p)
+    for env in (acro, ho, cstr):
+        assert env.n_params == len(env.sample_params(2, "Constant", ts, rng))
