@@ -200,7 +200,9 @@ MTGP_API int mtgp_decode(mtgp_bytecode in, int P, int T, int N, float* trees_out
 /* Lowering pass, exposed for tests and tools: level-1 bytecode -> executable accumulator-machine
  * programs (multitreegp_b200/csrc/mtgp_program.cuh).  prog_out [device] is [P*T, stride] 8-byte
  * instructions with stride = mtgp_program_stride(N); meta_out [device] uint32[P*T] holds
- * n_instructions | n_temporaries << 16.  tmp_base = first value-file slot free for temporaries. */
+ * n_instructions (bits 0-9) | n_threaded_instructions << 10 (bits 10-21, the rollout kernels'
+ * expanded form incl. header and END) | n_temporaries << 22.  tmp_base = first value-file slot free
+ * for temporaries. */
 MTGP_API int mtgp_lower(mtgp_bytecode bc, int P, int T, int N, const mtgp_node_table* table, int tmp_base,
                         void* prog_out, uint32_t* meta_out, void* stream);
 MTGP_API int mtgp_program_stride(int N);

@@ -14,7 +14,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libmtgp_b200.so")
 SOURCES = ["mtgp_api.cu", "mtgp_encode.cu", "mtgp_rollout.cu", "mtgp_rollout_rk.cu", "mtgp_pointwise.cu",
            "mtgp_select.cu"]
-HEADERS = ["mtgp_internal.cuh", "mtgp_program.cuh", "mtgp_env.cuh", "mtgp_lower.cuh", "../../include/mtgp.h", "../../include/mtgp_math.h"]
+HEADERS = ["mtgp_internal.cuh", "mtgp_program.cuh", "mtgp_threaded.cuh", "mtgp_env.cuh", "mtgp_lower.cuh", "../../include/mtgp.h", "../../include/mtgp_math.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

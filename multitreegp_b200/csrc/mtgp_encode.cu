@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(1024) k_cost_order(const uint32_t* __restrict_
   __syncthreads();
   auto cost_bin = [&](int ind) {
     int c = 0;
-    for (int t = 0; t < T; t++) c += (int)(meta[(size_t)ind * T + t] & 0xFFFFu) + 1;
+    for (int t = 0; t < T; t++) c += (int)MTGP_META_N(meta[(size_t)ind * T + t]) + 1;
     return kCostBins - 1 - min(c, kCostBins - 1);  // bin 0 = costliest
   };
   for (int i = threadIdx.x; i < P; i += blockDim.x) atomicAdd(&bin_start[cost_bin(i)], 1);

@@ -23,6 +23,7 @@ struct RolloutParams {
   int* next_slot;        // persistent warps draw their next schedule slot from this counter (NULL: one slot per warp)
   int lstride;
   int P, T;
+  int kind;  // MTGP_EVAL_*
   int B, K, n_obs, n_targets, n_params, state_size, max_steps;
   float dt0, max_fitness, obs_noise, size_parsimony;
   int partitionable;
@@ -33,7 +34,7 @@ struct RolloutParams {
   unsigned long long* steps_done;
   const float* noise;  // [cap_steps + K, n_obs, B] precomputed observation noise (NOISE == 1), see k_noise_table
   int cap_steps;       // rows of the step part of the noise table
-  int fast_tmp, fast_instr, want_fast;  // launch class: programs within / beyond the fast provisioning
+  int fast_tmp, fast_th, want_fast;  // launch class: programs within / beyond the fast provisioning (temporaries, threaded instructions)
   int n_latent;        // state kept in the value file: SR -> T, DYNAMIC -> state_size, STATIC -> 0
   int slot_lat;        // data-vector slot of latent component 0
   int slot_u;          // data-vector slot of the control (control evaluators)
@@ -41,14 +42,20 @@ struct RolloutParams {
   int slot_out;        // n_latent slots: y1 of the latent state
   int slot_state;      // n_latent slots: master copy of the latent state
   int slots_per_warp;      // data + latent copies + temporaries + 1 scratch slot
-  int prog_words_per_warp; // compact staging area (uint2)
-  int wide_cap;            // pre-decoded instructions provisioned per warp
+  int th_cap;              // threaded-code instructions provisioned per warp (also bounds the compact staging area)
   // general Runge-Kutta path (mtgp_rollout_rk.cu): Dopri5 and/or PIDController
   int solver, controller;
   float rtol, atol, dtmin, safety, factormin, factormax, coeff1, coeff2, coeff3;
   int slot_rk;             // first of the 12 * (D + n_latent) slots: Y, Y1, YI, F0, KS[7], SV
 };
 constexpr int kMaxTrees = 32;
+// launch classes of the rollout kernels: programs with at most kFastTmp temporaries and kFastTh threaded
+// instructions per individual run with a small shared-memory footprint
+constexpr int kFastTmp = 8;
+constexpr int kFastTh = 96;
+// worst case of the threaded form: every compact instruction expands to MTGP_TH_MAX_EXPAND, plus the header
+// and the ST per tree; the dynamic policy's readout is expanded twice
+__host__ __device__ inline int mtgp_worst_threaded(int T, int lstride) { return (T + 1) * (MTGP_TH_MAX_EXPAND * lstride + 2); }
 
 // ---- PTX helpers: mbarrier + 1-D bulk async copy (TMA) ------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -77,6 +84,106 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
+}
+
+// ---- per-warp shared memory of the rollout kernels ---------------------------------------------------
+//   [compact programs, staged by cp.async.bulk | tree offsets | threaded-code programs | value file]
+struct WarpArea {
+  uint2* prog_s;     // th_cap compact instructions (sum over trees of (n + 2) & ~1 <= sum of n_threaded)
+  int* woff;         // woff[t] = index of tree t's header in `th`
+  mtgp_tinstr* th;   // th_cap threaded instructions
+  float* vf;         // slots_per_warp * 32 floats; slot s of lane l at vf[s * 32 + l]
+};
+__host__ __device__ __forceinline__ size_t warp_area_bytes(int th_cap, int slots_per_warp) {
+  return (size_t)th_cap * sizeof(uint2) + kMaxTrees * sizeof(int) + (size_t)th_cap * sizeof(mtgp_tinstr) +
+         (size_t)slots_per_warp * 128;
+}
+__device__ __forceinline__ WarpArea warp_area(const RolloutParams& P, unsigned char* wbase) {
+  WarpArea w;
+  w.prog_s = reinterpret_cast<uint2*>(wbase);
+  w.woff = reinterpret_cast<int*>(wbase + (size_t)P.th_cap * sizeof(uint2));
+  w.th = reinterpret_cast<mtgp_tinstr*>(w.woff + kMaxTrees);
+  w.vf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(w.th) + (size_t)P.th_cap * sizeof(mtgp_tinstr));
+  return w;
+}
+
+// Threaded instructions an individual needs in shared memory (program layout below): every tree once,
+// the dynamic policy's readout a second time (stand-alone copy for the save points), one ST per tree.
+__device__ __forceinline__ int individual_th_need(const RolloutParams& P, int ind) {
+  int total = 0;
+  for (int t = 0; t < P.T; t++) total += (int)MTGP_META_TH(P.meta[(size_t)ind * P.T + t]) + 1;
+  if (P.kind == MTGP_EVAL_DYNAMIC) total += (int)MTGP_META_TH(P.meta[(size_t)ind * P.T + P.state_size]);
+  return total;
+}
+// Which launch owns an individual: by the temporaries and threaded instructions its programs need.
+__device__ __forceinline__ bool individual_is_fast(const RolloutParams& P, int ind) {
+  int need = 0;
+  for (int t = 0; t < P.T; t++) need = max(need, (int)MTGP_META_TMP(P.meta[(size_t)ind * P.T + t]));
+  return (need <= P.fast_tmp) && (individual_th_need(P, ind) <= P.fast_th);
+}
+
+// Stage the individual's compact programs (cp.async.bulk + mbarrier) and zero the value file.
+__device__ __forceinline__ void warp_stage_programs(const RolloutParams& P, int ind, int lane, uint64_t* bar,
+                                                    uint32_t& bar_phase, const WarpArea& w) {
+  if (lane == 0) {
+    uint32_t total = 0;
+    for (int t = 0; t < P.T; t++) total += ((MTGP_META_N(P.meta[(size_t)ind * P.T + t]) + 2u) & ~1u) * 8u;
+    mbar_expect_tx(bar, total);
+    uint32_t soff = 0;  // compact programs are staged back to back (16-byte granules)
+    for (int t = 0; t < P.T; t++) {
+      const uint32_t n = MTGP_META_N(P.meta[(size_t)ind * P.T + t]);
+      bulk_g2s(w.prog_s + soff, P.prog + ((size_t)ind * P.T + t) * P.lstride, ((n + 2u) & ~1u) * 8u, bar);
+      soff += (n + 2u) & ~1u;
+    }
+  }
+  __syncwarp();
+  float* lb = w.vf + lane;
+  for (int s = 0; s < P.slots_per_warp; s++) lb[s * 32] = 0.0f;
+  mbar_wait(bar, bar_phase);
+  bar_phase ^= 1u;
+}
+
+// Offset of tree t's compact program in the staging area.
+__device__ __forceinline__ uint32_t compact_offset(const RolloutParams& P, int ind, int t) {
+  uint32_t soff = 0;
+  for (int q = 0; q < t; q++) soff += (MTGP_META_N(P.meta[(size_t)ind * P.T + q]) + 2u) & ~1u;
+  return soff;
+}
+
+#define MTGP_NO_STORE 0xFFFFFFFFu
+// One threaded program = a CHAIN of trees run by a single interpreter call: tree `first + i` (i < count) is
+// expanded in turn; its value is stored to value-file slot `store_slot0 + i` (when store_slot0 >= 0) by giving
+// its last instruction the ..._ST form (or an ST instruction).  The value of the last tree is also the call's
+// result.  Writes [header]...[END] at dst, returns the instruction count.  Called by ONE lane.
+__device__ __forceinline__ int th_build_chain(const RolloutParams& P, int ind, const WarpArea& w, mtgp_tinstr* dst,
+                                              int first, int count, int store_slot0, int readout_tree = -1,
+                                              int readout_store = -1) {
+  int m = 1;
+  auto append = [&](int t, int store_slot) {
+    const uint32_t soff = compact_offset(P, ind, t);
+    const int n = (int)MTGP_META_N(P.meta[(size_t)ind * P.T + t]);  // without X_END
+    for (int i = 0; i < n; i++) m += mtgp_th_expand(w.prog_s[soff + i], dst + m);
+    if (n == 0) {  // (the lowering pass always emits at least a load)
+      dst[m].next = TH_LOAD_I; dst[m].a = 0; dst[m].b = 0; dst[m].c = 0;
+      m++;
+    }
+    if (store_slot >= 0) {
+      mtgp_tinstr& last = dst[m - 1];
+      if (last.next < TH_ST && (last.next & 1u) == 0u) {  // arithmetic / load without a store: fuse it
+        last.next += 1u;
+        last.c = (uint32_t)store_slot * 128u;
+      } else {
+        dst[m].next = TH_ST; dst[m].a = 0; dst[m].b = 0; dst[m].c = (uint32_t)store_slot * 128u;
+        m++;
+      }
+    }
+  };
+  if (readout_tree >= 0) append(readout_tree, readout_store);
+  for (int i = 0; i < count; i++) append(first + i, store_slot0 >= 0 ? store_slot0 + i : -1);
+  dst[m].next = TH_END; dst[m].a = 0; dst[m].b = 0; dst[m].c = 0;
+  m++;
+  mtgp_th_link(dst, m - 1);
+  return m;
 }
 
 // ---- jax.random on the device (THIRD-PARTY semantics; same as the oracle) -----
@@ -163,6 +270,28 @@ __device__ __forceinline__ void obs_normal(uint32_t key0, uint32_t key1, float t
 #pragma unroll
   for (int i = 0; i < NMAXOBS; i++)
     if (i < n) out[i] = OOL ? bits_to_normal_ool(bits[i]) : bits_to_normal(bits[i]);
+}
+
+// !isfinite(v) as ONE compare: |v| <= FLT_MAX is false for NaN and for +-inf
+__device__ __forceinline__ bool nonfinite_cmp(float v) { return !(fabsf(v) <= 3.40282347e38f); }
+
+// C @ x for C = eye(D)[:n_obs] and FINITE x, bit-identical to the literal dot product
+//     y_i = ((1|0)*x_0 + (1|0)*x_1) + ...        (control_environment_base.py:46)
+// every off-diagonal term is a zero with the sign of x_j, so y_i = x_i unless x_i is a zero, and a sum of
+// zeros is -0 only if every term is -0:  y_i = x_i + z,  z = -0 if all x_j carry a sign bit, else +0.
+template <int D>
+__device__ __forceinline__ float obs_zero_term(const float* x) {
+  uint32_t m = 0x80000000u;
+#pragma unroll
+  for (int j = 0; j < D; j++) m &= __float_as_uint(x[j]);
+  return __uint_as_float(m);
+}
+
+// Acrobot.f_obs angle wrap (acrobot.py:31): jnp.remainder(o + pi, 2 pi) - pi.  t = o + pi.
+// |t| < 2 pi: fmod returns t itself; a negative remainder gets the divisor added (python sign rule).
+__device__ __forceinline__ float wrap_in_range(float t) {
+  const float r = (t < 0.0f) ? t + 6.28318548f : t;
+  return r - 3.14159274f;
 }
 
 __device__ __forceinline__ float clip_jnp(float v, float lo, float hi) {
@@ -261,7 +390,8 @@ struct Env {
 
   // NOISE: 0 none, 1 = noise term read from the precomputed table row `nz` (element stride `nzs`),
   //        2 = generated inline.  All three give the same bits.
-  template <int NOISE>
+  // FINITE_X: the caller guarantees (warp-uniformly) that every component of x is finite
+  template <int NOISE, bool FINITE_X = false>
   __device__ __forceinline__ void f_obs(float t, const float* x, float* y, int n_obs, float obs_noise,
                                         int partitionable, const float* nz, int nzs) const {
     float nt[D];
@@ -276,14 +406,19 @@ struct Env {
 #pragma unroll
       for (int i = 0; i < D; i++) nt[i] = t4[i < 4 ? i : 3];
     }
+    const float z = FINITE_X ? obs_zero_term<D>(x) : 0.0f;
 #pragma unroll
     for (int i = 0; i < D; i++) {
       if (i < n_obs) {
         float acc = 0.0f;
+        if (FINITE_X) {
+          acc = x[i] + z;
+        } else {
 #pragma unroll
-        for (int j = 0; j < D; j++) {  // C @ x, literally (0 * inf = NaN must survive)
-          const float term = ((i == j) ? 1.0f : 0.0f) * x[j];
-          acc = (j == 0) ? term : acc + term;
+          for (int j = 0; j < D; j++) {  // C @ x, literally (0 * inf = NaN must survive)
+            const float term = ((i == j) ? 1.0f : 0.0f) * x[j];
+            acc = (j == 0) ? term : acc + term;
+          }
         }
         if (NOISE != 0) acc = acc + nt[i];
         y[i] = acc;
@@ -291,9 +426,16 @@ struct Env {
     }
     if (ENV == MTGP_ENV_ACROBOT) {
       const float pi = 3.14159274f, two_pi = 6.28318548f;
+      const float w0 = y[0] + pi, w1 = (n_obs > 1) ? y[1] + pi : 0.0f;
+      // warp-uniform choice: every lane's angles within one turn (the usual case) -> two adds each
+      if (__all_sync(__activemask(), fabsf(w0) < two_pi && fabsf(w1) < two_pi)) {
+        y[0] = wrap_in_range(w0);
+        if (n_obs > 1) y[1] = wrap_in_range(w1);
+      } else {
 #pragma unroll
-      for (int i = 0; i < 2; i++)
-        if (i < n_obs) y[i] = mtgp_remainderf_py(y[i] + pi, two_pi) - pi;
+        for (int i = 0; i < 2; i++)
+          if (i < n_obs) y[i] = mtgp_remainderf_py(y[i] + pi, two_pi) - pi;
+      }
     }
   }
 
@@ -336,9 +478,13 @@ struct Env {
   // cond_fn_nan on the env part of the state (the latent part is OR-ed in by the caller)
   __device__ __forceinline__ bool bad_state(const float* y) const {
     bool bad = false;
+    if (ENV == MTGP_ENV_ACROBOT) {
+      // !isfinite(v) | |v| > c  ==  !(|v| <= c): NaN and inf fail the comparison too
+      bad = nonfinite_cmp(y[0]) | nonfinite_cmp(y[1]) | !(fabsf(y[2]) <= 25.1327419f) | !(fabsf(y[3]) <= 56.5486679f);
+    } else {
 #pragma unroll
-    for (int i = 0; i < D; i++) bad |= !mtgp_isfinitef(y[i]);
-    if (ENV == MTGP_ENV_ACROBOT) bad |= (mtgp_absf(y[2]) > 25.1327419f) | (mtgp_absf(y[3]) > 56.5486679f);
+      for (int i = 0; i < D; i++) bad |= nonfinite_cmp(y[i]);
+    }
     return bad;
   }
 

@@ -5,7 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
-#include "mtgp_program.cuh"
+#include "mtgp_threaded.cuh"
 
 // ---- error reporting (thread-local message behind mtgp_last_error) ----------------------------
 void mtgp_set_error(const char* fmt, ...);

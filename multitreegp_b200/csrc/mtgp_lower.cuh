@@ -3,7 +3,7 @@
 // only ever runs it inside k_lower (mtgp_encode.cu).
 #pragma once
 
-#include "mtgp_program.cuh"
+#include "mtgp_threaded.cuh"
 
 #define MTGP_LHD __host__ __device__ __forceinline__
 
@@ -49,7 +49,7 @@ struct SlotAlloc {
 
 
 // Lowers one tree.  op/ra/rb/rc: the tree's level-1 rows; out: its program (>= mtgp_lstride(N)
-// instructions).  Returns n_instr | n_tmp << 16 and the canonical-layout flag through *canonical_out.
+// instructions).  Returns the meta word (MTGP_META_*) and the canonical-layout flag through *canonical_out.
 template <int NMAX>
 MTGP_LHD uint32_t mtgp_lower_tree(const uint8_t* op, const int16_t* ra, const int16_t* rb, const float* rc, int N,
                                   const mtgp_node_table& tab, int tmp_base, uint2* out, bool* canonical_out) {
@@ -210,6 +210,12 @@ MTGP_LHD uint32_t mtgp_lower_tree(const uint8_t* op, const int16_t* ra, const in
   }
   out[n] = mtgp_make_instr(X_END, 0, 0, MTGP_NO_SLOT, 0, 0, 0.0f);
   if (((n + 1) & 1) != 0) out[n + 1] = mtgp_make_instr(X_END, 0, 0, MTGP_NO_SLOT, 0, 0, 0.0f);  // 16-byte granules
-  return (uint32_t)n | ((uint32_t)slots.high << 16);
+  // length of the threaded-code form (header + expanded instructions + END)
+  int n_th = 1;
+  for (int i = 0; i <= n; i++) {
+    mtgp_tinstr tmp[MTGP_TH_MAX_EXPAND];
+    n_th += mtgp_th_expand(out[i], tmp);
+  }
+  return MTGP_META_MAKE(n, n_th, slots.high);
 }
 

@@ -68,8 +68,8 @@ __global__ void __launch_bounds__(kPwWarps * 32, MTGP_PW_MIN_CTAS) k_pointwise(c
       int need = 0, len = 0;
       for (int t = 0; t < P.T; t++) {
         const uint32_t m = P.meta[(size_t)ind * P.T + t];
-        need = max(need, (int)(m >> 16));
-        len = max(len, (int)(m & 0xFFFFu) + 1);
+        need = max(need, (int)MTGP_META_TMP(m));
+        len = max(len, (int)MTGP_META_N(m) + 1);
       }
       const bool fits = (need <= P.cap_tmp) && (len <= P.cap_instr);
       const bool fits_prev = (need <= P.prev_tmp) && (len <= P.prev_instr);
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kPwWarps * 32, MTGP_PW_MIN_CTAS) k_pointwise(c
   for (int gt = wic; gt < G * P.T; gt += kPwWarps) {
     if (!s_need[gt / P.T]) continue;
     const size_t tree = (size_t)s_ind[gt / P.T] * P.T + gt % P.T;
-    const int n = (int)(P.meta[tree] & 0xFFFFu) + 1;
+    const int n = (int)MTGP_META_N(P.meta[tree]) + 1;
     const uint2* src = P.prog + tree * P.lstride;
     uint2* dst = prog_s + (size_t)gt * P.pstride;
     for (int i = lane; i < n; i += 32) dst[i] = __ldg(src + i);

@@ -32,6 +32,14 @@
 #define MTGP_NO_SLOT 0xFFu
 #define MTGP_MAX_SLOTS 254
 
+// meta word of a lowered tree (k_lower): n_instr (compact instructions, X_END excluded) in bits 0-9,
+// n_threaded (threaded-code instructions incl. header and END, mtgp_threaded.cuh) in bits 10-21,
+// n_tmp (temporary value-file slots) in bits 22-31
+#define MTGP_META_N(m) ((uint32_t)(m) & 0x3FFu)
+#define MTGP_META_TH(m) (((uint32_t)(m) >> 10) & 0xFFFu)
+#define MTGP_META_TMP(m) ((uint32_t)(m) >> 22)
+#define MTGP_META_MAKE(n, th, tmp) ((uint32_t)(n) | ((uint32_t)(th) << 10) | ((uint32_t)(tmp) << 22))
+
 // Instruction word .x = opcode (bits 0-3) | x kind (bits 4-5) | y kind (bits 6-7) | store slot << 8
 //                       | x slot << 16 | y slot << 24;   .y = immediate (float bits).
 // The opcode set is closed and small on purpose: dispatch is one short compare chain and the three
@@ -202,84 +210,6 @@ __host__ __device__ MTGP_COMPACT_INLINE Vec<R> mtgp_interpret(const uint2* __res
   return acc;
 }
 
-// ---- pre-decoded ("wide") format for the rollout kernel (R = 1) --------------------------------
-// In the rollout the same program runs thousands of times per trajectory with ONE value per lane,
-// so per-dispatch decode (field extraction, kind tests, compare chains) is the dominant cost.  Each
-// warp therefore expands its compact programs once into 32-byte instructions whose fields are ready
-// to use: byte offsets into the value file and full-width select masks.  The common operators run
-// through ONE branch-free data path:
-//     x = MX ? M[xoff] : acc              y = MY ? M[yoff] : imm
-//     r = fma(x, P, Q)   with  P = MP ? y : c1,   Q = MP ? -0.0 : (y ^ fy)
-//   ADD: c1 = 1, fy = 0         x*1 + y          SUB : c1 = 1, fy = sign   x*1 + (-y)
-//   RSUB: c1 = -1, fy = 0       x*(-1) + y       MUL : MP = ~0             x*y + (-0.0)
-//   LOAD: ADD with y = imm = -0.0                (all exact: one rounding, same bits as the plain op)
-// A result that a later instruction reads from the value file is stored by its producer (W_FAST_ST); the
-// slow operators always store (to a scratch slot when nobody needs the value).
-struct __align__(16) mtgp_wide_instr {
-  uint4 a;  // .x = x byte offset | y byte offset << 16 (slot * 128)
-            // .y = store byte offset | op << 16  (op: W_END, W_FAST, or a slow opcode)
-            // .z = immediate (float bits)      .w = MX: ~0 -> x from memory, 0 -> x = accumulator
-  uint4 b;  // .x = MY: ~0 -> y from memory, 0 -> y = immediate      .y = c1: float bits of +1 / -1
-            // .z = MP: ~0 -> multiply          .w = fy: 0 or 0x80000000
-};
-// W_FAST: fma path, result only needed by the next instruction (no store); W_FAST_ST: fma path + store
-enum mtgp_wop : uint32_t {
-  W_END = 0, W_FAST = 1, W_FAST_ST = 2, W_DIV = 3, W_RDIV = 4, W_MAX = 5, W_MIN = 6, W_SIN = 7, W_COS = 8, W_EXP = 9,
-  W_LOG = 10, W_SQRT = 11, W_TANH = 12, W_NEG = 13, W_ABS = 14, W_SQUARE = 15, W_LOADI = 16
-};
-
-// compact -> wide.  `scratch_slot` receives the results nobody reads.
-__host__ __device__ __forceinline__ mtgp_wide_instr mtgp_expand_instr(uint2 c, uint32_t scratch_slot) {
-  const uint32_t op = c.x & 15u, st = (c.x >> 8) & 0xFFu;
-  uint32_t xk = (c.x >> 4) & 3u, yk = (c.x >> 6) & 3u, xs = (c.x >> 16) & 0xFFu, ys = c.x >> 24;
-  mtgp_wide_instr w;
-  uint32_t wop = W_FAST, imm = c.y, c1 = 0x3F800000u, mp = 0u, fy = 0u;
-  bool swap = false;
-  switch (op) {
-    case X_END: wop = W_END; break;
-    case X_LOAD:
-      if (xk == OK_IMM) wop = W_LOADI;
-      else { yk = OK_IMM; imm = 0x80000000u; }  // x + (-0.0) == x
-      break;
-    case X_ADD: swap = (xk == OK_IMM) || (yk == OK_ACC); break;
-    case X_MUL:
-      swap = (xk == OK_IMM) || (yk == OK_ACC && xk != OK_ACC);
-      mp = 0xFFFFFFFFu;
-      if (xk == OK_ACC && yk == OK_ACC) wop = W_SQUARE;
-      break;
-    case X_SUB:
-      if (xk == OK_IMM || yk == OK_ACC) { swap = true; c1 = 0xBF800000u; }  // y - x
-      else fy = 0x80000000u;
-      break;
-    case X_DIV:
-      wop = W_DIV;
-      if (xk == OK_IMM || yk == OK_ACC) { swap = true; wop = W_RDIV; }
-      break;
-    case X_MAX: wop = W_MAX; swap = (xk == OK_IMM) || (yk == OK_ACC); break;
-    case X_MIN: wop = W_MIN; swap = (xk == OK_IMM) || (yk == OK_ACC); break;
-    default: wop = W_SIN + (op - X_SIN); break;  // unary: SIN COS EXP LOG SQRT TANH NEG ABS
-  }
-  if (swap) {
-    uint32_t t = xk; xk = yk; yk = t;
-    t = xs; xs = ys; ys = t;
-  }
-  if (wop == W_FAST && st != MTGP_NO_SLOT) wop = W_FAST_ST;
-  // after canonicalisation x is the accumulator or memory, y is memory or the immediate
-  w.a.x = ((xk == OK_MEM ? xs : 0u) * 128u) | (((yk == OK_MEM ? ys : 0u) * 128u) << 16);
-  w.a.y = ((st != MTGP_NO_SLOT ? st : scratch_slot) * 128u) | (wop << 16);
-  w.a.z = imm;
-  w.a.w = (xk == OK_MEM) ? 0xFFFFFFFFu : 0u;
-  w.b.x = (yk == OK_MEM) ? 0xFFFFFFFFu : 0u;
-  w.b.y = c1;
-  w.b.z = mp;
-  w.b.w = fy;
-  return w;
-}
-
-__host__ __device__ __forceinline__ uint32_t mtgp_bitsel(uint32_t mask, uint32_t a, uint32_t b) {
-  return (a & mask) | (b & ~mask);  // one LOP3
-}
-
 // Shared-memory accessors on 32-bit shared-space addresses (device) / plain pointers (host build of
 // the unit-test harness).  One IADD + LDS/STS per value-file access, one LDS.128 per half instruction.
 #if defined(__CUDA_ARCH__)
@@ -306,54 +236,3 @@ static inline void mtgp_sts_f32(mtgp_saddr a, float v) { memcpy((void*)a, &v, 4)
 static inline uint4 mtgp_lds_v4(mtgp_saddr a) { uint4 v; memcpy(&v, (const void*)a, 16); return v; }
 #endif
 
-// Everything that is not + - * or a load: kept out of line so that the hot dispatch loop stays a
-// handful of instructions and the compiler cannot fold the fast-path test into a compare tree.
-static __host__ __device__ __noinline__ float mtgp_wide_slow_op(uint32_t wop, float x, float y) {
-  switch (wop) {
-    case W_SIN: return mtgp_sinf(x);
-    case W_COS: return mtgp_cosf(x);
-    case W_DIV: return x / y;
-    case W_RDIV: return y / x;
-    case W_MAX: return mtgp_maximumf(x, y);
-    case W_MIN: return mtgp_minimumf(x, y);
-    case W_EXP: return mtgp_expf(x);
-    case W_LOG: return mtgp_logf(x);
-    case W_SQRT: return mtgp_sqrtf(x);
-    case W_TANH: return mtgp_tanhf(x);
-    case W_NEG: return -x;
-    case W_ABS: return mtgp_absf(x);
-    case W_SQUARE: return x * x;
-    default: return y;  // W_LOADI
-  }
-}
-
-// prog: wide program in shared memory; lane: the lane's base of the value file (value file + lane*4).
-// Warp-uniform control flow throughout.
-#ifndef MTGP_INTERP_INLINE
-#define MTGP_INTERP_INLINE __noinline__
-#endif
-static __host__ __device__ MTGP_INTERP_INLINE float mtgp_interpret_wide(mtgp_saddr prog, mtgp_saddr lane) {
-  float acc = 0.0f;
-  uint4 a = mtgp_lds_v4(prog), b = mtgp_lds_v4(prog + 16);
-  while (a.y >= (W_FAST << 16)) {  // W_END = 0
-    const float xm = mtgp_lds_f32(lane + (a.x & 0xFFFFu));
-    const float ym = mtgp_lds_f32(lane + (a.x >> 16));
-    const mtgp_saddr st = lane + (a.y & 0xFFFFu);
-    const uint32_t ctl = a.y;
-    const uint32_t xb = mtgp_bitsel(a.w, mtgp_f2u(xm), mtgp_f2u(acc));
-    const uint32_t yb = mtgp_bitsel(b.x, mtgp_f2u(ym), a.z);
-    const uint32_t pb = mtgp_bitsel(b.z, yb, b.y);
-    const uint32_t qb = mtgp_bitsel(b.z, 0x80000000u, yb ^ b.w);
-    prog += 32;
-    a = mtgp_lds_v4(prog);
-    b = mtgp_lds_v4(prog + 16);
-    if (ctl < (W_FAST_ST << 16)) {
-      acc = fmaf(mtgp_u2f(xb), mtgp_u2f(pb), mtgp_u2f(qb));
-    } else {
-      if (ctl < ((W_FAST_ST + 1u) << 16)) acc = fmaf(mtgp_u2f(xb), mtgp_u2f(pb), mtgp_u2f(qb));
-      else acc = mtgp_wide_slow_op(ctl >> 16, mtgp_u2f(xb), mtgp_u2f(yb));
-      mtgp_sts_f32(st, acc);
-    }
-  }
-  return acc;
-}

@@ -96,19 +96,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
   constexpr bool FIXED_LATENT = (KIND == MTGP_EVAL_STATIC) || (KIND == MTGP_EVAL_DYNAMIC && SPEC == 2);
   const int n_obs = FULLOBS ? D : P.n_obs;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, wic = (kWarpsPerCta == 1) ? 0 : (int)(threadIdx.x >> 5);
   const int slot0 = blockIdx.x * kWarpsPerCta + wic;
 
-  // shared memory: [mbarriers][per warp: compact programs | tree offsets | wide programs | value file]
-  const size_t per_warp = (size_t)P.prog_words_per_warp * sizeof(uint2) + kMaxTrees * sizeof(int) +
-                          (size_t)P.wide_cap * sizeof(mtgp_wide_instr) + (size_t)P.slots_per_warp * 128;
+  // shared memory: [mbarriers][per warp: compact programs | tree offsets | threaded programs | value file]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  unsigned char* wbase = smem_raw + 16 * kWarpsPerCta + (size_t)wic * per_warp;
-  uint2* prog_s = reinterpret_cast<uint2*>(wbase);
-  int* woff = reinterpret_cast<int*>(wbase + (size_t)P.prog_words_per_warp * sizeof(uint2));
-  mtgp_wide_instr* wide = reinterpret_cast<mtgp_wide_instr*>(woff + kMaxTrees);
-  float* vf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(wide) +
-                                       (size_t)P.wide_cap * sizeof(mtgp_wide_instr));
+  const WarpArea wa =
+      warp_area(P, smem_raw + 16 * kWarpsPerCta + (size_t)wic * warp_area_bytes(P.th_cap, P.slots_per_warp));
   // Persistent warps: every warp draws schedule slots (costliest individual first) from a global counter
   // until the population is exhausted -- no CTA turnover between individuals.
   uint64_t* bar = bars + 2 * wic;
@@ -126,70 +120,57 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
     first_round = false;
     if (slot >= P.P) return;  // whole warp leaves together (no block-wide barrier anywhere)
     const int ind = P.order ? P.order[slot] : slot;
+    if (individual_is_fast(P, ind) != (P.want_fast != 0)) continue;  // the other launch's individual
 
-    // which launch owns this individual: by the temporaries and instructions its programs need
-    {
-      int need = 0, total_instr = 0;
-      for (int t = 0; t < P.T; t++) {
-        const uint32_t m = P.meta[(size_t)ind * P.T + t];
-        need = max(need, (int)(m >> 16));
-        total_instr += (int)(m & 0xFFFFu) + 1;
-      }
-      const bool fast = (need <= P.fast_tmp) && (total_instr <= P.fast_instr);
-      if (fast != (P.want_fast != 0)) continue;
-    }
-
-    // ---- stage this individual's programs: cp.async.bulk -> shared, completion on an mbarrier ----
-    if (lane == 0) {
-      uint32_t total = 0;
-      for (int t = 0; t < P.T; t++) {
-        const uint32_t n = P.meta[(size_t)ind * P.T + t] & 0xFFFFu;
-        total += ((n + 2u) & ~1u) * 8u;
-      }
-      mbar_expect_tx(bar, total);
-      int off = 0;
-      uint32_t soff = 0;  // compact programs are staged back to back (16-byte granules)
-      for (int t = 0; t < P.T; t++) {
-        const uint32_t n = P.meta[(size_t)ind * P.T + t] & 0xFFFFu;
-        bulk_g2s(prog_s + soff, P.prog + ((size_t)ind * P.T + t) * P.lstride, ((n + 2u) & ~1u) * 8u, bar);
-        soff += (n + 2u) & ~1u;
-        woff[t] = off;
-        off += (int)n + 1;
-      }
-    }
-    __syncwarp();
-    float* lb = vf + lane;  // lane base of the value file (R = 1)
+    // ---- stage this individual's programs (cp.async.bulk -> shared, mbarrier) ----
+    warp_stage_programs(P, ind, lane, bar, bar_phase, wa);
+    float* lb = wa.vf + lane;  // lane base of the value file (R = 1)
     const mtgp_saddr lbytes = mtgp_saddr_of(lb);
-    for (int s = 0; s < P.slots_per_warp; s++) lb[s * 32] = 0.0f;
-    mbar_wait(bar, bar_phase);
-    bar_phase ^= 1u;
     bool readout_reads_y = false;
-    // ---- pre-decode: compact (8 B) -> wide (32 B) instructions, once per individual -------------
-    {
-      const uint32_t scratch = (uint32_t)P.slots_per_warp - 1u;
-      uint32_t soff = 0;
-      for (int t = 0; t < P.T; t++) {
-        const int n = (int)(P.meta[(size_t)ind * P.T + t] & 0xFFFFu) + 1;  // including X_END
-        mtgp_wide_instr* dst = wide + woff[t];
-        for (int i = lane; i < n; i += 32) {
-          const uint2 c = prog_s[soff + i];
-          dst[i] = mtgp_expand_instr(c, scratch);
-          if (KIND == MTGP_EVAL_DYNAMIC && t == P.state_size) {  // the readout tree
-            // does the readout read an observation or the control slot?  (conservative: unused operand fields count)
-            const uint32_t xk = (c.x >> 4) & 3u, yk = (c.x >> 6) & 3u, xs = (c.x >> 16) & 0xFFu, ys = c.x >> 24;
-            const bool rx = xk == OK_MEM && ((int)xs < n_obs || (int)xs == P.slot_u);
-            const bool ry = yk == OK_MEM && ((int)ys < n_obs || (int)ys == P.slot_u);
-            readout_reads_y |= (rx || ry) && (c.x & 15u) != X_END;
-          }
-        }
-        soff += ((uint32_t)n + 1u) & ~1u;
+    if (KIND == MTGP_EVAL_DYNAMIC) {
+      // does the readout read an observation or the control slot?  (conservative: unused operand fields count)
+      const uint32_t soff = compact_offset(P, ind, P.state_size);
+      const int n = (int)MTGP_META_N(P.meta[(size_t)ind * P.T + P.state_size]);
+      for (int i = lane; i < n; i += 32) {
+        const uint2 c = wa.prog_s[soff + i];
+        const uint32_t xk = (c.x >> 4) & 3u, yk = (c.x >> 6) & 3u, xs = (c.x >> 16) & 0xFFu, ys = c.x >> 24;
+        const bool rx = xk == OK_MEM && ((int)xs < n_obs || (int)xs == P.slot_u);
+        const bool ry = yk == OK_MEM && ((int)ys < n_obs || (int)ys == P.slot_u);
+        readout_reads_y |= (rx || ry);
       }
     }
-    __syncwarp();
     // The dynamic readout sees zeros for the observations and the control inside the step
     // (dynamic_evaluate.py:113) and the saved observations in the post-pass (:100-101).  With the
     // notebooks' variable lists it reads neither (only the latent state), and the slots need no care.
     const bool readout_sees_y = (KIND == MTGP_EVAL_DYNAMIC) && (__any_sync(0xFFFFFFFFu, readout_reads_y) != 0);
+    // ---- expand to threaded code.  One interpreter call per Euler step runs the whole CHAIN of trees:
+    //   static : [readout]                                          -> u
+    //   dynamic: [readout -> slot_u][state eq j -> slot_out + j]...   (readout first: the state equations read u)
+    //            split in two calls when the readout reads y / u (it must see zeros there, dynamic_evaluate.py:113)
+    //   SR     : [tree j -> slot_out + j]...
+    // plus a stand-alone readout for the save points of the dynamic policy.
+    if (lane == 0) {
+      int off = 0;
+      if (KIND == MTGP_EVAL_STATIC) {
+        wa.woff[0] = wa.woff[1] = wa.woff[2] = 0;
+        off += th_build_chain(P, ind, wa, wa.th, 0, 1, -1);
+      } else if (KIND == MTGP_EVAL_SR) {
+        wa.woff[0] = wa.woff[1] = wa.woff[2] = 0;
+        off += th_build_chain(P, ind, wa, wa.th, 0, P.T, P.slot_out);
+      } else {
+        wa.woff[2] = 0;  // stand-alone readout
+        off += th_build_chain(P, ind, wa, wa.th, P.state_size, 1, -1);
+        if (readout_sees_y) {
+          wa.woff[0] = 0;
+          wa.woff[1] = off;
+          off += th_build_chain(P, ind, wa, wa.th + off, 0, P.state_size, P.slot_out);
+        } else {
+          wa.woff[0] = wa.woff[1] = off;
+          off += th_build_chain(P, ind, wa, wa.th + off, 0, P.state_size, P.slot_out, P.state_size, P.slot_u);
+        }
+      }
+    }
+    __syncwarp();
 
     const float* ts = P.ts;
     const int K = P.K;
@@ -205,13 +186,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
                      a_lat = lbytes + 128u * (uint32_t)slot_lat;
     const float t0 = ts[0], t1 = ts[K - 1];
     const float dts = (K > 1) ? ts[1] - ts[0] : 0.0f;  // ts[1]-ts[0], acrobot.py:82
-    const mtgp_saddr wide_s = mtgp_saddr_of(wide);
-    const mtgp_saddr prog_readout = wide_s + 32u * (uint32_t)woff[(KIND == MTGP_EVAL_DYNAMIC) ? NL : 0];
-    mtgp_saddr prog_lat[2] = {wide_s, wide_s};  // FIXED_SLOTS: the two state-equation programs
-    if (FIXED_SLOTS) {
-      prog_lat[0] = wide_s + 32u * (uint32_t)woff[0];
-      prog_lat[1] = wide_s + 32u * (uint32_t)woff[1];
-    }
+    const mtgp_saddr th_s = mtgp_saddr_of(wa.th);
+    const mtgp_saddr prog_step = th_s + 16u * (uint32_t)wa.woff[0];   // the step's chain (first call)
+    const mtgp_saddr prog_step2 = th_s + 16u * (uint32_t)wa.woff[1];  // dynamic, readout_sees_y: the state equations
+    const mtgp_saddr prog_save = th_s + 16u * (uint32_t)wa.woff[2];   // stand-alone readout (save points)
     float fit_sum = 0.0f;
     unsigned int my_steps = 0;  // Euler steps integrated by this lane (< 2^32: max_steps is capped at 2^22 per solve)
 
@@ -232,6 +210,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
       for (int pass = 0; pass < 2; pass++) {
         // ---------------- one trajectory solve ----------------
         float x[DR], x1[DR];
+        // FIXED_SLOTS: the latent state lives in registers (aS current, aO candidate); slot_lat of the value
+        // file holds what the trees read.  Otherwise it lives in the value file (slot_state / slot_out).
+        float aS[2] = {0.0f, 0.0f}, aO[2] = {0.0f, 0.0f};
         if (KIND != MTGP_EVAL_SR) {
 #pragma unroll
           for (int i = 0; i < D; i++) { x[i] = P.x0[bb * D + i]; x1[i] = x[i]; }
@@ -245,9 +226,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
         if (KIND != MTGP_EVAL_SR) { env.sum = 0.0f; env.sum0 = 0.0f; env.fs = -1; }
         float sr_total = 0.0f;
         bool ev_old_bad;
+        bool x_nonfinite = false;  // some component of the env state x is NaN/inf (C @ x must then be literal)
         {
           bool bad = false;
-          if (KIND != MTGP_EVAL_SR) bad = env.bad_state(x);
+          if (KIND != MTGP_EVAL_SR) {
+            bad = env.bad_state(x);
+#pragma unroll
+            for (int i = 0; i < D; i++) x_nonfinite |= nonfinite_cmp(x[i]);
+          }
           for (int j = 0; j < NL; j++) bad |= !mtgp_isfinitef(lb[(slot_state + j) * 32]);
           ev_old_bad = bad;  // Event: cond_fn at (t0, y0)
         }
@@ -270,8 +256,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
             float u = 0.0f;
             if (KIND != MTGP_EVAL_SR) {
               float y[DR];
-              env.template f_obs<NOISE>(tprev, x, y, n_obs, P.obs_noise, P.partitionable,
-                                        nz_step, nzs);
+              // a dead lane's x is frozen at its last committed (finite) value; only a non-finite x0 takes the literal path
+              if (__any_sync(0xFFFFFFFFu, x_nonfinite))
+                env.template f_obs<NOISE, false>(tprev, x, y, n_obs, P.obs_noise, P.partitionable, nz_step, nzs);
+              else
+                env.template f_obs<NOISE, true>(tprev, x, y, n_obs, P.obs_noise, P.partitionable, nz_step, nzs);
               if (KIND == MTGP_EVAL_STATIC) {
 #pragma unroll
                 for (int i = 0; i < D; i++)
@@ -282,21 +271,38 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
                   if (i < n_obs) lb[i * 32] = 0.0f;
                 lb[slot_u * 32] = 0.0f;
               }
-              u = mtgp_interpret_wide(prog_readout, lbytes);  // feedforward :107 / dynamic readout :113
+              if (KIND == MTGP_EVAL_DYNAMIC && !readout_sees_y) {
+                // the whole chain in one call: the observations are already in place (the readout does not
+                // read them), the readout's ST puts u in its slot before the state equations run
+#pragma unroll
+                for (int i = 0; i < D; i++)
+                  if (i < n_obs) lb[i * 32] = y[i];
+                mtgp_run_threaded(prog_step, lbytes);
+                u = lb[slot_u * 32];
+              } else {
+                u = mtgp_run_threaded(prog_step, lbytes);  // feedforward :107 / dynamic readout :113
+              }
               float dx[DR];
               env.drift(x, u, dx);
 #pragma unroll
               for (int i = 0; i < D; i++) x1[i] = x[i] + dt * dx[i];
-              if (KIND == MTGP_EVAL_DYNAMIC) {
+              if (KIND == MTGP_EVAL_DYNAMIC && readout_sees_y) {
 #pragma unroll
                 for (int i = 0; i < D; i++)
                   if (i < n_obs) lb[i * 32] = y[i];
                 lb[slot_u * 32] = u;
+                mtgp_run_threaded(prog_step2, lbytes);
               }
+            } else {
+              mtgp_run_threaded(prog_step, lbytes);  // SR: the vector field, component j in slot_out + j
             }
-            for (int j = 0; j < NL; j++) {  // latent trees: state equation (:116) / SR vector field
-              const float f = mtgp_interpret_wide(FIXED_SLOTS ? prog_lat[j & 1] : wide_s + 32u * (uint32_t)woff[j], lbytes);
-              mtgp_sts_f32(a_out + 128u * j, mtgp_lds_f32(a_state + 128u * j) + dt * f);
+            // latent Euler update (state equation :116 / SR vector field): f_j is in slot_out + j
+            if (FIXED_SLOTS) {
+#pragma unroll
+              for (int j = 0; j < 2; j++) aO[j] = aS[j] + dt * mtgp_lds_f32(a_out + 128u * j);
+            } else {
+              for (int j = 0; j < NL; j++)
+                mtgp_sts_f32(a_out + 128u * j, mtgp_lds_f32(a_state + 128u * j) + dt * mtgp_lds_f32(a_out + 128u * j));
             }
             new_tprev = tnext < t1 ? tnext : t1;
             new_tnext = tnext + P.dt0;
@@ -315,7 +321,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
             }
             float row = 0.0f;
             for (int j = 0; j < NL; j++) {
-              const float a0 = mtgp_lds_f32(a_state + 128u * j), a1 = mtgp_lds_f32(a_out + 128u * j);
+              const float a0 = FIXED_SLOTS ? aS[j & 1] : mtgp_lds_f32(a_state + 128u * j);
+              const float a1 = FIXED_SLOTS ? aO[j & 1] : mtgp_lds_f32(a_out + 128u * j);
               const float lat = live_save ? a0 + coeff * (a1 - a0) : mtgp_inff();
               if (KIND == MTGP_EVAL_SR) {
                 const float e = lat - P.ys_true[((size_t)bb * K + k) * NL + j];
@@ -330,15 +337,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
               sr_total = sr_total + row;
             } else {
               float ys[DR];
-              env.template f_obs<NOISE>(tk, xs, ys, n_obs, P.obs_noise, P.partitionable,
-                                        nz_base + (size_t)(P.cap_steps + k) * nzs, nzs);
+              env.template f_obs<NOISE, false>(tk, xs, ys, n_obs, P.obs_noise, P.partitionable,
+                                               nz_base + (size_t)(P.cap_steps + k) * nzs, nzs);
               if (KIND == MTGP_EVAL_STATIC || readout_sees_y) {
 #pragma unroll
                 for (int i = 0; i < D; i++)
                   if (i < n_obs) lb[i * 32] = ys[i];
                 if (KIND == MTGP_EVAL_DYNAMIC) lb[slot_u * 32] = 0.0f;  // zeros(control_size) (dynamic_evaluate.py:101)
               }
-              const float uk = mtgp_interpret_wide(prog_readout, lbytes);
+              const float uk = mtgp_run_threaded(prog_save, lbytes);
               const float qk = (ENV == MTGP_ENV_ACROBOT) ? tk / dts : 0.0f;
               if (ENV == MTGP_ENV_ACROBOT && qk > (float)(k + 1)) viol = true;
               env.cost_add(k, qk, xs, uk, fs_known);
@@ -361,22 +368,41 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
             // ---- Event(cond_fn): sign change of cond_fn evaluated at (tnext, y1) ----
             bool bad = false;
             if (KIND != MTGP_EVAL_SR) bad = env.bad_state(x1);
-            for (int j = 0; j < NL; j++) bad |= !mtgp_isfinitef(mtgp_lds_f32(a_out + 128u * j));
+            if (FIXED_SLOTS) {
+              bad |= nonfinite_cmp(aO[0]) | nonfinite_cmp(aO[1]);
+            } else {
+              for (int j = 0; j < NL; j++) bad |= !mtgp_isfinitef(mtgp_lds_f32(a_out + 128u * j));
+            }
             const bool fired = (bad != ev_old_bad);
-            // ---- commit ----
+            // ---- commit ----  (a lane whose event fires never reads its state again -- its remaining save
+            // points are the inf pre-fill -- so it keeps the last finite state and stays on the fast paths)
+            const bool adv = alive && !fired;
             if (alive) {
               ev_old_bad = bad;
               lane_steps++;
-              if (KIND != MTGP_EVAL_SR) {
+            }
+            if (KIND != MTGP_EVAL_SR) {
 #pragma unroll
-                for (int i = 0; i < D; i++) x[i] = x1[i];
+              for (int i = 0; i < D; i++) x[i] = adv ? x1[i] : x[i];
+              if (adv && bad) {  // integrating on in a state that was already bad at t0 (rare)
+                x_nonfinite = false;
+#pragma unroll
+                for (int i = 0; i < D; i++) x_nonfinite |= nonfinite_cmp(x[i]);
               }
             }
-            for (int j = 0; j < NL; j++) {
-              const float cur = mtgp_lds_f32(a_state + 128u * j);
-              const float nv = alive ? mtgp_lds_f32(a_out + 128u * j) : cur;
-              mtgp_sts_f32(a_state + 128u * j, nv);
-              mtgp_sts_f32(a_lat + 128u * j, nv);
+            if (FIXED_SLOTS) {
+#pragma unroll
+              for (int j = 0; j < 2; j++) {
+                aS[j] = adv ? aO[j] : aS[j];
+                mtgp_sts_f32(a_lat + 128u * j, aS[j]);
+              }
+            } else {
+              for (int j = 0; j < NL; j++) {
+                const float cur = mtgp_lds_f32(a_state + 128u * j);
+                const float nv = adv ? mtgp_lds_f32(a_out + 128u * j) : cur;
+                mtgp_sts_f32(a_state + 128u * j, nv);
+                mtgp_sts_f32(a_lat + 128u * j, nv);
+              }
             }
             if (alive && fired) alive = false;
             tprev = new_tprev;
@@ -428,16 +454,13 @@ int sm_count() {
 }
 
 size_t rollout_smem(const RolloutParams& rp) {
-  const size_t per_warp = (size_t)rp.prog_words_per_warp * sizeof(uint2) + kMaxTrees * sizeof(int) +
-                          (size_t)rp.wide_cap * sizeof(mtgp_wide_instr) + (size_t)rp.slots_per_warp * 128;
-  return 16 * kWarpsPerCta + (size_t)kWarpsPerCta * per_warp;
+  return 16 * kWarpsPerCta + (size_t)kWarpsPerCta * warp_area_bytes(rp.th_cap, rp.slots_per_warp);
 }
 
 template <int KIND, int ENV, int NOISE, int SPEC, bool TRAJ_OUT>
-int launch_one(RolloutParams rp, int tmp_base, int n_tmp, int wide_cap, int want_fast, cudaStream_t stream) {
+int launch_one(RolloutParams rp, int tmp_base, int n_tmp, int th_cap, int want_fast, cudaStream_t stream) {
   rp.slots_per_warp = tmp_base + n_tmp + 1;
-  rp.wide_cap = wide_cap;
-  rp.prog_words_per_warp = (wide_cap + rp.T + 1) & ~1;  // sum over trees of (n + 2) & ~1 <= instructions + T
+  rp.th_cap = (th_cap + 1) & ~1;
   rp.want_fast = want_fast;
   const size_t smem = rollout_smem(rp);
   if (smem > 227 * 1024) {
@@ -459,12 +482,10 @@ int launch_one(RolloutParams rp, int tmp_base, int n_tmp, int wide_cap, int want
   return mtgp_check_launch("k_rollout");
 }
 
-// Individuals whose programs need at most kFastTmp temporaries and kFastInstr instructions (every
-// tree of ordinary depth) run with a small shared-memory footprint and high occupancy; the rest
+// Individuals whose programs need at most kFastTmp temporaries and kFastTh threaded instructions
+// (every tree of ordinary depth) run with a small shared-memory footprint and high occupancy; the rest
 // (long combs grown by mutation, very large trees) run in a second launch provisioned with the
-// worst-case bounds.  Each launch skips the other's individuals.
-constexpr int kFastTmp = 8;
-constexpr int kFastInstr = 64;
+// worst-case bounds.  Each launch skips the other's individuals.  (kFastTmp, kFastTh: mtgp_env.cuh)
 
 template <int KIND, int ENV>
 int launch_kind_env(RolloutParams rp, int tmp_base, int bound, void* noise_ws, cudaStream_t stream) {
@@ -483,10 +504,10 @@ int launch_kind_env(RolloutParams rp, int tmp_base, int bound, void* noise_ws, c
       rp.noise = table;
     }
   }
-  const int worst_instr = rp.T * rp.lstride;
-  const bool all_fast = (bound <= kFastTmp) && (worst_instr <= kFastInstr);
+  const int worst_th = mtgp_worst_threaded(rp.T, rp.lstride);
+  const bool all_fast = (bound <= kFastTmp) && (worst_th <= kFastTh);
   rp.fast_tmp = all_fast ? bound : kFastTmp;
-  rp.fast_instr = all_fast ? worst_instr : kFastInstr;
+  rp.fast_th = all_fast ? worst_th : kFastTh;
   int rc;
   constexpr int ENVD = (KIND == MTGP_EVAL_SR) ? 0 : EnvDim<ENV>::D;
   const bool full_obs = (KIND != MTGP_EVAL_SR) && rp.n_obs == ENVD;
@@ -500,9 +521,9 @@ int launch_kind_env(RolloutParams rp, int tmp_base, int bound, void* noise_ws, c
   const bool traj_out = rp.xs_o || rp.ys_o || rp.us_o || rp.act_o || rp.tf_o;
 #define LAUNCH1T(NZ, SPEC, TR)                                                                        \
   {                                                                                                   \
-    rc = launch_one<KIND, ENV, NZ, SPEC, TR>(rp, tmp_base, rp.fast_tmp, rp.fast_instr, 1, stream);    \
+    rc = launch_one<KIND, ENV, NZ, SPEC, TR>(rp, tmp_base, rp.fast_tmp, rp.fast_th, 1, stream);       \
     if (rc == MTGP_OK && !all_fast)                                                                   \
-      rc = launch_one<KIND, ENV, NZ, SPEC, TR>(rp, tmp_base, bound, worst_instr, 0, stream);          \
+      rc = launch_one<KIND, ENV, NZ, SPEC, TR>(rp, tmp_base, bound, worst_th, 0, stream);             \
   }
 #define LAUNCH1(NZ, SPEC) { if (traj_out) LAUNCH1T(NZ, SPEC, true) else LAUNCH1T(NZ, SPEC, false) }
 #define LAUNCH2(NZ)                                                                                   \
@@ -562,7 +583,7 @@ int mtgp_launch_rollout(const mtgp_programs& progs, const int32_t* live, int P, 
   if (P == 0) return MTGP_OK;
   RolloutParams rp{};
   rp.prog = progs.prog; rp.meta = progs.meta; rp.live = live; rp.lstride = progs.lstride;
-  rp.P = P; rp.T = T;
+  rp.P = P; rp.T = T; rp.kind = d.kind;
   if (progs.order) {
     if (int rc = mtgp_launch_cost_order(progs.meta, P, T, progs.order, stream)) return rc;
     rp.order = progs.order;
@@ -599,7 +620,6 @@ int mtgp_launch_rollout(const mtgp_programs& progs, const int32_t* live, int P, 
     mtgp_set_error("internal: slot map mismatch (%d vs %d)", reserved, progs.tmp_base);
     return MTGP_ERR_INVALID_ARGUMENT;
   }
-  rp.prog_words_per_warp = T * progs.lstride;
   const int bound = progs.n_tmp;
   if (d.solver != MTGP_SOLVER_EULER || d.controller != MTGP_CONTROLLER_CONSTANT) {
     // Dopri5 and/or PIDController: the general kernel (same two provisioning classes)
@@ -617,7 +637,7 @@ int mtgp_launch_rollout(const mtgp_programs& progs, const int32_t* live, int P, 
     rp.coeff3 = dc / error_order;
     rp.slot_rk = n_data;
     rp.slots_per_warp = progs.tmp_base + bound + 1;
-    rp.wide_cap = T * progs.lstride;
+    rp.th_cap = mtgp_worst_threaded(T, progs.lstride);
     return mtgp_launch_rollout_rk(rp, d.kind, d.env_id, progs.tmp_base, bound, stream);
   }
 #define DISPATCH(KIND, ENV) return launch_kind_env<KIND, ENV>(rp, progs.tmp_base, bound, noise_ws, stream)

@@ -56,15 +56,8 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const int slot0 = blockIdx.x * kRkWarps + wic;
-  const size_t per_warp = (size_t)P.prog_words_per_warp * sizeof(uint2) + kMaxTrees * sizeof(int) +
-                          (size_t)P.wide_cap * sizeof(mtgp_wide_instr) + (size_t)P.slots_per_warp * 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  unsigned char* wbase = smem_raw + 16 * kRkWarps + (size_t)wic * per_warp;
-  uint2* prog_s = reinterpret_cast<uint2*>(wbase);
-  int* woff = reinterpret_cast<int*>(wbase + (size_t)P.prog_words_per_warp * sizeof(uint2));
-  mtgp_wide_instr* wide = reinterpret_cast<mtgp_wide_instr*>(woff + kMaxTrees);
-  float* vf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(wide) +
-                                       (size_t)P.wide_cap * sizeof(mtgp_wide_instr));
+  const WarpArea wa = warp_area(P, smem_raw + 16 * kRkWarps + (size_t)wic * warp_area_bytes(P.th_cap, P.slots_per_warp));
   // persistent warps, as in k_rollout: the first individual comes with the launch, later ones from the counter
   uint64_t* bar = bars + 2 * wic;
   if (lane == 0) mbar_init(bar, 1);
@@ -81,49 +74,18 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
     first_round = false;
     if (slot >= P.P) return;
     const int ind = P.order ? P.order[slot] : slot;
-
     // which launch owns this individual (as in k_rollout): small programs run with a small footprint
-    {
-      int need = 0, total_instr = 0;
-      for (int t = 0; t < P.T; t++) {
-        const uint32_t m = P.meta[(size_t)ind * P.T + t];
-        need = max(need, (int)(m >> 16));
-        total_instr += (int)(m & 0xFFFFu) + 1;
-      }
-      const bool fast = (need <= P.fast_tmp) && (total_instr <= P.fast_instr);
-      if (fast != (P.want_fast != 0)) continue;
-    }
+    if (individual_is_fast(P, ind) != (P.want_fast != 0)) continue;
 
-    // ---- stage (back to back) + pre-decode the programs (same as K2) ----
-    if (lane == 0) {
-      uint32_t total = 0;
-      for (int t = 0; t < P.T; t++) total += (((P.meta[(size_t)ind * P.T + t] & 0xFFFFu) + 2u) & ~1u) * 8u;
-      mbar_expect_tx(bar, total);
-      int off = 0;
-      uint32_t soff = 0;
-      for (int t = 0; t < P.T; t++) {
-        const uint32_t n = P.meta[(size_t)ind * P.T + t] & 0xFFFFu;
-        bulk_g2s(prog_s + soff, P.prog + ((size_t)ind * P.T + t) * P.lstride, ((n + 2u) & ~1u) * 8u, bar);
-        soff += (n + 2u) & ~1u;
-        woff[t] = off;
-        off += (int)n + 1;
-      }
-    }
-    __syncwarp();
-    float* lb = vf + lane;
+    // ---- stage the programs (same as K2) and expand every tree to its own threaded program (lane t: tree t) ----
+    warp_stage_programs(P, ind, lane, bar, bar_phase, wa);
+    float* lb = wa.vf + lane;
     const mtgp_saddr lbytes = mtgp_saddr_of(lb);
-    for (int s = 0; s < P.slots_per_warp; s++) lb[s * 32] = 0.0f;
-    mbar_wait(bar, bar_phase);
-    bar_phase ^= 1u;
-    {
-      const uint32_t scratch = (uint32_t)P.slots_per_warp - 1u;
-      uint32_t soff = 0;
-      for (int t = 0; t < P.T; t++) {
-        const int n = (int)(P.meta[(size_t)ind * P.T + t] & 0xFFFFu) + 1;
-        mtgp_wide_instr* dst = wide + woff[t];
-        for (int i = lane; i < n; i += 32) dst[i] = mtgp_expand_instr(prog_s[soff + i], scratch);
-        soff += ((uint32_t)n + 1u) & ~1u;
-      }
+    for (int t = lane; t < P.T; t += 32) {
+      int off = 0;
+      for (int q = 0; q < t; q++) off += (int)MTGP_META_TH(P.meta[(size_t)ind * P.T + q]);
+      wa.woff[t] = off;
+      th_build_chain(P, ind, wa, wa.th + off, t, 1, -1);
     }
     __syncwarp();
 
@@ -134,8 +96,8 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
     const float t0 = ts[0], t1 = ts[K - 1];
     const float dts = (K > 1) ? ts[1] - ts[0] : 0.0f;
     const bool dopri = P.solver == MTGP_SOLVER_DOPRI5, pid = P.controller == MTGP_CONTROLLER_PID;
-    const mtgp_saddr wide_s = mtgp_saddr_of(wide);
-    const mtgp_saddr prog_readout = wide_s + 32u * (uint32_t)woff[(KIND == MTGP_EVAL_DYNAMIC) ? NL : 0];
+    const mtgp_saddr th_s = mtgp_saddr_of(wa.th);
+    const mtgp_saddr prog_readout = th_s + 16u * (uint32_t)wa.woff[(KIND == MTGP_EVAL_DYNAMIC) ? NL : 0];
     // solver arrays in the value file: component i of array a is slot slot_rk + a*DT + i
     float* const Y = lb + (size_t)(P.slot_rk + 0 * DT) * 32;
     float* const Y1 = lb + (size_t)(P.slot_rk + 1 * DT) * 32;
@@ -173,7 +135,7 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
               if (i < n_obs) lb[i * 32] = 0.0f;
             lb[P.slot_u * 32] = 0.0f;
           }
-          const float u = mtgp_interpret_wide(prog_readout, lbytes);
+          const float u = mtgp_run_threaded(prog_readout, lbytes);
           env.drift(x, u, dx);
 #pragma unroll
           for (int i = 0; i < D; i++) {
@@ -188,7 +150,7 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
           }
         }
         for (int j = 0; j < NL; j++) {
-          const float f = mtgp_interpret_wide(wide_s + 32u * (uint32_t)woff[j], lbytes);
+          const float f = mtgp_run_threaded(th_s + 16u * (uint32_t)wa.woff[j], lbytes);
           dst[(D + j) * 32] = scale * f;
           if (raw) raw[(D + j) * 32] = f;
         }
@@ -250,7 +212,7 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
             for (int i = 0; i < D; i++)
               if (i < n_obs) lb[i * 32] = ys[i];
             if (KIND == MTGP_EVAL_DYNAMIC) lb[P.slot_u * 32] = 0.0f;
-            const float uk = mtgp_interpret_wide(prog_readout, lbytes);
+            const float uk = mtgp_run_threaded(prog_readout, lbytes);
             const float qk = (ENV == MTGP_ENV_ACROBOT) ? tk / dts : 0.0f;
             if (doit) {
               if (ENV == MTGP_ENV_ACROBOT && qk > (float)(kk + 1)) viol = true;
@@ -438,21 +400,15 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
   }  // persistent loop
 }
 
-// Two provisioning classes as in the fixed-step kernel: individuals whose programs need at most kFastTmp
-// temporaries and kFastInstr instructions run with a small shared-memory footprint (more resident warps), the
-// rest in a second launch provisioned for the worst case.  Each launch skips the other's individuals.
-constexpr int kFastTmp = 8;
-constexpr int kFastInstr = 64;
+// Two provisioning classes as in the fixed-step kernel (kFastTmp, kFastTh: mtgp_env.cuh); each launch skips the
+// other's individuals.
 
 template <int KIND, int ENV>
-int launch_rk_class(RolloutParams rp, int tmp_base, int n_tmp, int wide_cap, int want_fast, cudaStream_t stream) {
+int launch_rk_class(RolloutParams rp, int tmp_base, int n_tmp, int th_cap, int want_fast, cudaStream_t stream) {
   rp.slots_per_warp = tmp_base + n_tmp + 1;
-  rp.wide_cap = wide_cap;
-  rp.prog_words_per_warp = (wide_cap + rp.T + 1) & ~1;  // sum over trees of (n + 2) & ~1 <= instructions + T
+  rp.th_cap = (th_cap + 1) & ~1;
   rp.want_fast = want_fast;
-  const size_t per_warp = (size_t)rp.prog_words_per_warp * sizeof(uint2) + kMaxTrees * sizeof(int) +
-                          (size_t)rp.wide_cap * sizeof(mtgp_wide_instr) + (size_t)rp.slots_per_warp * 128;
-  const size_t smem = 16 * kRkWarps + (size_t)kRkWarps * per_warp;
+  const size_t smem = 16 * kRkWarps + (size_t)kRkWarps * warp_area_bytes(rp.th_cap, rp.slots_per_warp);
   if (smem > 227 * 1024) {
     mtgp_set_error("adaptive rollout needs %zu bytes of shared memory per CTA: over the 227 KB limit", smem);
     return MTGP_ERR_UNSUPPORTED;
@@ -496,12 +452,12 @@ int launch_rk_class(RolloutParams rp, int tmp_base, int n_tmp, int wide_cap, int
 
 template <int KIND, int ENV>
 int launch_rk(RolloutParams rp, int tmp_base, int bound, cudaStream_t stream) {
-  const int worst_instr = rp.T * rp.lstride;
-  const bool all_fast = (bound <= kFastTmp) && (worst_instr <= kFastInstr);
+  const int worst_th = mtgp_worst_threaded(rp.T, rp.lstride);
+  const bool all_fast = (bound <= kFastTmp) && (worst_th <= kFastTh);
   rp.fast_tmp = all_fast ? bound : kFastTmp;
-  rp.fast_instr = all_fast ? worst_instr : kFastInstr;
-  int rc = launch_rk_class<KIND, ENV>(rp, tmp_base, rp.fast_tmp, rp.fast_instr, 1, stream);
-  if (rc == MTGP_OK && !all_fast) rc = launch_rk_class<KIND, ENV>(rp, tmp_base, bound, worst_instr, 0, stream);
+  rp.fast_th = all_fast ? worst_th : kFastTh;
+  int rc = launch_rk_class<KIND, ENV>(rp, tmp_base, rp.fast_tmp, rp.fast_th, 1, stream);
+  if (rc == MTGP_OK && !all_fast) rc = launch_rk_class<KIND, ENV>(rp, tmp_base, bound, worst_th, 0, stream);
   return rc;
 }
 

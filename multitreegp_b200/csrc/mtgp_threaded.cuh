@@ -1,0 +1,280 @@
+// mtgp_threaded.cuh -- the rollout kernels' interpreter: THREADED CODE over 16-byte instructions.
+//
+// In a rollout the same tree program runs thousands of times per trajectory with ONE value per lane,
+// so the cost of an operator node is its dispatch, not its arithmetic.  Round 1's select-mask data
+// path cost ~30 SASS instructions per node (profiles/r01_rollout_c5_by_line.txt).  Here every
+// (operator x operand kinds x store?) combination is its own straight-line HANDLER, and every
+// handler ends with its own indirect branch to the next one (threaded code, no central dispatch
+// loop): ~8 SASS per node --
+//     IADD  ad = lane + B          LDS  t = [ad]          (operand from the warp's value file)
+//     IADD  pc += 16               LDS.128 next = [pc]    (the instruction after the next one)
+//     SHL / LDC / SHF              (jump-table entry of the next handler, c[0x2])
+//     FADD  acc = acc + t          BRX
+// An instruction carries the handler index of its SUCCESSOR (.x), so the jump-table load does not
+// wait for the instruction fetch; the fetch alternates between two register sets (a*, b*), which
+// is why every handler exists twice (position parity) -- no register copies between handlers.
+//
+// The interpreter is one inline-PTX block (CUDA C has no computed goto; `brx.idx` is the PTX
+// form).  Everything that is not + - * load store leaves the block with a status code, is
+// computed by ordinary C code (mtgp_math.h -- the same functions as constant folding and the
+// oracle) and re-enters.  All arithmetic is `.rn` (never contracted, no FTZ): the results are the
+// bits of the reference's float32 operators (genetic_programming.py:24-31, 356-376).
+//
+// Instruction = uint4: .x = 2 * handler(next instruction) + parity(next position)
+//                      .y = A: x operand -- byte offset into the lane's value file (slot * 128) or immediate bits
+//                      .z = B: y operand -- byte offset or immediate bits
+//                      .w = C: store byte offset (…_ST handlers, ST) or slow opcode (SLOW_*)
+// A program is [header][instr 0]...[END]; the header's .x names instruction 0's handler.
+#pragma once
+
+#include "mtgp_program.cuh"
+
+// handler list: X(name, has_store_variant)
+#define MTGP_TH_ARITH(X) \
+  X(ADD_AM) X(ADD_AI) X(ADD_MM) X(ADD_MI) X(ADD_AA) \
+  X(MUL_AM) X(MUL_AI) X(MUL_MM) X(MUL_MI) X(MUL_AA) \
+  X(SUB_AM) X(RSB_AM) X(RSB_AI) X(SUB_MM) X(RSB_MI) \
+  X(LOAD_M) X(LOAD_I)
+#define MTGP_TH_OTHER(X) X(ST) X(LDY_M) X(LDY_I) X(LDY_A) X(SLOW_A) X(SLOW_M) X(SLOW_I) X(END)
+
+enum mtgp_th : uint32_t {
+#define X(n) TH_##n, TH_##n##_ST,
+  MTGP_TH_ARITH(X)
+#undef X
+#define X(n) TH_##n,
+  MTGP_TH_OTHER(X)
+#undef X
+  TH_COUNT
+};
+
+// slow opcodes (status codes of the PTX block; 0 = END)
+enum mtgp_sop : uint32_t {
+  S_END = 0, S_SIN, S_COS, S_EXP, S_LOG, S_SQRT, S_TANH, S_NEG, S_ABS,  // unary: the order of X_SIN .. X_ABS
+  S_DIV, S_MAX, S_MIN, S_ADD, S_SUB, S_MUL
+};
+
+struct __align__(16) mtgp_tinstr {
+  uint32_t next, a, b, c;
+};
+
+// Worst case: a binary slow operator whose result is stored = LDY + SLOW + ST.
+#define MTGP_TH_MAX_EXPAND 3
+
+// compact instruction -> up to 3 threaded instructions; .next holds the instruction's OWN handler
+// until mtgp_th_link() rewrites it.  Returns the count.
+__host__ __device__ __forceinline__ int mtgp_th_expand(uint2 c, mtgp_tinstr* out) {
+  const uint32_t op = c.x & 15u, st = (c.x >> 8) & 0xFFu;
+  const uint32_t xk = (c.x >> 4) & 3u, yk = (c.x >> 6) & 3u, xs = ((c.x >> 16) & 0xFFu) * 128u, ys = (c.x >> 24) * 128u;
+  const uint32_t imm = c.y, nimm = c.y ^ 0x80000000u, sto = st * 128u;
+  const bool has_st = st != MTGP_NO_SLOT;
+  const uint32_t s1 = has_st ? 1u : 0u;
+  auto put = [&](int i, uint32_t h, uint32_t a, uint32_t b, uint32_t cc) {
+    out[i].next = h; out[i].a = a; out[i].b = b; out[i].c = cc;
+  };
+  if (op == X_END) { put(0, TH_END, 0, 0, 0); return 1; }
+  if (op == X_LOAD && xk != OK_ACC) {
+    put(0, (xk == OK_MEM ? TH_LOAD_M : TH_LOAD_I) + s1, xk == OK_MEM ? xs : imm, 0, sto);
+    return 1;
+  }
+  if (op == X_ADD || op == X_MUL) {  // commutative: canonical forms AM AI MM MI AA
+    const uint32_t base = (op == X_ADD) ? TH_ADD_AM : TH_MUL_AM;
+    const uint32_t step = TH_ADD_AI - TH_ADD_AM;
+    int form = -1;
+    uint32_t a = 0, b = 0;
+    if (xk == OK_ACC && yk == OK_ACC) form = 4;
+    else if (xk == OK_ACC && yk == OK_MEM) { form = 0; b = ys; }
+    else if (xk == OK_MEM && yk == OK_ACC) { form = 0; b = xs; }
+    else if (xk == OK_ACC && yk == OK_IMM) { form = 1; b = imm; }
+    else if (xk == OK_IMM && yk == OK_ACC) { form = 1; b = imm; }
+    else if (xk == OK_MEM && yk == OK_MEM) { form = 2; a = xs; b = ys; }
+    else if (xk == OK_MEM && yk == OK_IMM) { form = 3; a = xs; b = imm; }
+    else if (xk == OK_IMM && yk == OK_MEM) { form = 3; a = ys; b = imm; }
+    if (form >= 0) { put(0, base + step * (uint32_t)form + s1, a, b, sto); return 1; }
+  }
+  if (op == X_SUB) {
+    int h = -1;
+    uint32_t a = 0, b = 0;
+    if (xk == OK_ACC && yk == OK_MEM) { h = TH_SUB_AM; b = ys; }
+    else if (xk == OK_ACC && yk == OK_IMM) { h = TH_ADD_AI; b = nimm; }            // x - c == x + (-c)
+    else if (xk == OK_MEM && yk == OK_ACC) { h = TH_RSB_AM; b = xs; }               // M - acc
+    else if (xk == OK_IMM && yk == OK_ACC) { h = TH_RSB_AI; b = imm; }              // c - acc
+    else if (xk == OK_MEM && yk == OK_MEM) { h = TH_SUB_MM; a = xs; b = ys; }
+    else if (xk == OK_MEM && yk == OK_IMM) { h = TH_ADD_MI; a = xs; b = nimm; }
+    else if (xk == OK_IMM && yk == OK_MEM) { h = TH_RSB_MI; a = ys; b = imm; }      // c - M
+    if (h >= 0) { put(0, (uint32_t)h + s1, a, b, sto); return 1; }
+  }
+  // everything else: [LDY] SLOW [ST]
+  uint32_t sop;
+  bool binary = true;
+  switch (op) {
+    case X_ADD: sop = S_ADD; break;
+    case X_SUB: sop = S_SUB; break;
+    case X_MUL: sop = S_MUL; break;
+    case X_DIV: sop = S_DIV; break;
+    case X_MAX: sop = S_MAX; break;
+    case X_MIN: sop = S_MIN; break;
+    case X_LOAD: sop = S_ADD; binary = false; break;  // acc = acc: never emitted by the lowering pass
+    default: sop = S_SIN + (op - X_SIN); binary = false; break;  // SIN COS EXP LOG SQRT TANH NEG ABS
+  }
+  int n = 0;
+  if (op == X_LOAD) { put(n++, TH_LDY_I, 0, 0x80000000u, 0); }  // x + (-0.0) == x
+  else if (binary) put(n++, yk == OK_ACC ? TH_LDY_A : (yk == OK_MEM ? TH_LDY_M : TH_LDY_I), 0, yk == OK_MEM ? ys : imm, 0);
+  put(n++, xk == OK_ACC ? TH_SLOW_A : (xk == OK_MEM ? TH_SLOW_M : TH_SLOW_I), xk == OK_MEM ? xs : imm, 0, sop);
+  if (has_st) put(n++, TH_ST, 0, 0, sto);
+  return n;
+}
+
+// header + n instructions (prog[0] = header, prog[1..n] = instructions with their own handler in .next):
+// rewrite .next to the successor's table index.  Lane-parallel safe when called by one thread.
+__host__ __device__ __forceinline__ void mtgp_th_link(mtgp_tinstr* prog, int n) {
+  prog[0].next = 0; prog[0].a = 0; prog[0].b = 0; prog[0].c = 0;
+  for (int j = 0; j < n; j++) prog[j].next = 2u * prog[j + 1].next + ((uint32_t)j & 1u);  // successor position j (0-based) parity
+  prog[n].next = 0;
+}
+
+// slow operators: ordinary C on the contract's functions
+static __host__ __device__ __forceinline__ float mtgp_th_slow_op(uint32_t sop, float x, float y) {
+  if (sop == S_SIN) return mtgp_sinf(x);
+  if (sop == S_COS) return mtgp_cosf(x);
+  switch (sop) {
+    case S_DIV: return x / y;
+    case S_MAX: return mtgp_maximumf(x, y);
+    case S_MIN: return mtgp_minimumf(x, y);
+    case S_EXP: return mtgp_expf(x);
+    case S_LOG: return mtgp_logf(x);
+    case S_SQRT: return mtgp_sqrtf(x);
+    case S_TANH: return mtgp_tanhf(x);
+    case S_NEG: return -x;
+    case S_ABS: return mtgp_absf(x);
+    case S_ADD: return x + y;
+    case S_SUB: return x - y;
+    default: return x * y;  // S_MUL
+  }
+}
+
+#if defined(__CUDA_ARCH__)
+// ---- the PTX block ---------------------------------------------------------------------------------
+// operands: %0 acc  %1 pc  %2 nh (in: handler of [pc]; out: handler of the instruction after a SLOW)
+//           %3 status  %4 xv  %5 yv  %6 lane
+#define TH_NEXT(N) " add.u32 %1,%1,16;\n ld.shared.v4.u32 {" N "0," N "1," N "2," N "3},[%1];\n"
+#define TH_GO(C) " brx.idx " C "0, TBL;\n"
+#define TH_XM(C) " add.u32 ad,%6," C "1;\n ld.shared.f32 t0,[ad];\n"
+#define TH_YM(C) " add.u32 ae,%6," C "2;\n ld.shared.f32 t1,[ae];\n"
+#define TH_XI(C) " mov.b32 t0," C "1;\n"
+#define TH_YI(C) " mov.b32 t1," C "2;\n"
+#define TH_STORE(C) " add.u32 ad,%6," C "3;\n st.shared.f32 [ad],%0;\n"
+#define TH_NOSTORE(C) ""
+#define TH_OP(PRE, OP, X, Y, C, N, ST) PRE TH_NEXT(N) " " OP " %0," X "," Y ";\n" ST(C) TH_GO(C)
+
+#define TH_B_ADD_AM(C, N, ST) TH_OP(TH_YM(C), "add.rn.f32", "%0", "t1", C, N, ST)
+#define TH_B_ADD_AI(C, N, ST) TH_OP(TH_YI(C), "add.rn.f32", "%0", "t1", C, N, ST)
+#define TH_B_ADD_MM(C, N, ST) TH_OP(TH_XM(C) TH_YM(C), "add.rn.f32", "t0", "t1", C, N, ST)
+#define TH_B_ADD_MI(C, N, ST) TH_OP(TH_XM(C) TH_YI(C), "add.rn.f32", "t0", "t1", C, N, ST)
+#define TH_B_ADD_AA(C, N, ST) TH_OP("", "add.rn.f32", "%0", "%0", C, N, ST)
+#define TH_B_MUL_AM(C, N, ST) TH_OP(TH_YM(C), "mul.rn.f32", "%0", "t1", C, N, ST)
+#define TH_B_MUL_AI(C, N, ST) TH_OP(TH_YI(C), "mul.rn.f32", "%0", "t1", C, N, ST)
+#define TH_B_MUL_MM(C, N, ST) TH_OP(TH_XM(C) TH_YM(C), "mul.rn.f32", "t0", "t1", C, N, ST)
+#define TH_B_MUL_MI(C, N, ST) TH_OP(TH_XM(C) TH_YI(C), "mul.rn.f32", "t0", "t1", C, N, ST)
+#define TH_B_MUL_AA(C, N, ST) TH_OP("", "mul.rn.f32", "%0", "%0", C, N, ST)
+#define TH_B_SUB_AM(C, N, ST) TH_OP(TH_YM(C), "sub.rn.f32", "%0", "t1", C, N, ST)
+#define TH_B_RSB_AM(C, N, ST) TH_OP(TH_YM(C), "sub.rn.f32", "t1", "%0", C, N, ST)
+#define TH_B_RSB_AI(C, N, ST) TH_OP(TH_YI(C), "sub.rn.f32", "t1", "%0", C, N, ST)
+#define TH_B_SUB_MM(C, N, ST) TH_OP(TH_XM(C) TH_YM(C), "sub.rn.f32", "t0", "t1", C, N, ST)
+#define TH_B_RSB_MI(C, N, ST) TH_OP(TH_XM(C) TH_YI(C), "sub.rn.f32", "t1", "t0", C, N, ST)
+#define TH_B_LOAD_M(C, N, ST) TH_XM(C) TH_NEXT(N) " mov.f32 %0,t0;\n" ST(C) TH_GO(C)
+#define TH_B_LOAD_I(C, N, ST) TH_XI(C) TH_NEXT(N) " mov.f32 %0,t0;\n" ST(C) TH_GO(C)
+
+#define TH_B_ST(C, N) TH_NEXT(N) TH_STORE(C) TH_GO(C)
+#define TH_B_LDY_M(C, N) " add.u32 ae,%6," C "2;\n ld.shared.f32 %5,[ae];\n" TH_NEXT(N) TH_GO(C)
+#define TH_B_LDY_I(C, N) " mov.b32 %5," C "2;\n" TH_NEXT(N) TH_GO(C)
+#define TH_B_LDY_A(C, N) " mov.f32 %5,%0;\n" TH_NEXT(N) TH_GO(C)
+#define TH_EXIT(C) " mov.u32 %3," C "3;\n mov.u32 %2," C "0;\n add.u32 %1,%1,16;\n bra DONE;\n"
+#define TH_B_SLOW_A(C, N) " mov.f32 %4,%0;\n" TH_EXIT(C)
+#define TH_B_SLOW_M(C, N) " add.u32 ad,%6," C "1;\n ld.shared.f32 %4,[ad];\n" TH_EXIT(C)
+#define TH_B_SLOW_I(C, N) " mov.b32 %4," C "1;\n" TH_EXIT(C)
+#define TH_B_END(C, N) " mov.u32 %3,0;\n bra DONE;\n"
+
+#define TH_LABELS_ARITH(n) "H_" #n "_a, H_" #n "_b, H_" #n "_ST_a, H_" #n "_ST_b, "
+#define TH_LABELS_OTHER(n) "H_" #n "_a, H_" #n "_b, "
+#define TH_CODE_ARITH(n)                                                                  \
+  "H_" #n "_a:\n" TH_B_##n("a", "b", TH_NOSTORE) "H_" #n "_b:\n" TH_B_##n("b", "a", TH_NOSTORE) \
+  "H_" #n "_ST_a:\n" TH_B_##n("a", "b", TH_STORE) "H_" #n "_ST_b:\n" TH_B_##n("b", "a", TH_STORE)
+#define TH_CODE_OTHER(n) "H_" #n "_a:\n" TH_B_##n("a", "b") "H_" #n "_b:\n" TH_B_##n("b", "a")
+
+// Runs from the instruction at pc (whose handler index is nh) until END (returns 0) or a slow operator
+// (returns its opcode with xv / yv set; pc / nh then name the instruction after it).
+__device__ __forceinline__ uint32_t mtgp_th_block(float& acc, uint32_t& pc, uint32_t& nh, float& xv, float& yv,
+                                                  uint32_t lane) {
+  uint32_t status;
+  asm volatile(
+      "{\n"
+      " .reg .u32 a0,a1,a2,a3,b0,b1,b2,b3,ad,ae;\n"
+      " .reg .f32 t0,t1;\n"
+      " .reg .pred pb;\n"
+      " and.b32 ad,%2,1;\n setp.ne.u32 pb,ad,0;\n"  // the instruction at pc goes to the register set of its position parity
+      " @!pb ld.shared.v4.u32 {a0,a1,a2,a3},[%1];\n"
+      " @pb ld.shared.v4.u32 {b0,b1,b2,b3},[%1];\n"
+      "TBL: .branchtargets " MTGP_TH_ARITH(TH_LABELS_ARITH) MTGP_TH_OTHER(TH_LABELS_OTHER) "DONE;\n"
+      " brx.idx %2, TBL;\n"
+      MTGP_TH_ARITH(TH_CODE_ARITH)
+      MTGP_TH_OTHER(TH_CODE_OTHER)
+      "DONE:\n"
+      "}\n"
+      : "+f"(acc), "+r"(pc), "+r"(nh), "=r"(status), "=f"(xv), "+f"(yv)
+      : "r"(lane)
+      : "memory");
+  return status;
+}
+#endif
+
+// One tree evaluation.  entry: shared address of the program's header; lane: the lane's base of the value file.
+#ifndef MTGP_TH_INLINE
+#define MTGP_TH_INLINE __noinline__
+#endif
+static __host__ __device__ MTGP_TH_INLINE float mtgp_run_threaded(mtgp_saddr entry, mtgp_saddr lane) {
+#if defined(__CUDA_ARCH__)
+  uint32_t nh, pc = entry + 16u;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(nh) : "r"(entry));
+  float acc = 0.0f, xv = 0.0f, yv = 0.0f;
+  for (;;) {
+    const uint32_t sop = mtgp_th_block(acc, pc, nh, xv, yv, lane);
+    if (sop == S_END) return acc;
+    acc = mtgp_th_slow_op(sop, xv, yv);
+  }
+#else
+  // host build (tests/hostlib): the same semantics, one switch per instruction
+  const mtgp_tinstr* prog = reinterpret_cast<const mtgp_tinstr*>(entry);
+  const unsigned char* vb = reinterpret_cast<const unsigned char*>(lane);
+  auto M = [&](uint32_t off) { float v; memcpy(&v, vb + off, 4); return v; };
+  auto I = [](uint32_t bits) { return mtgp_u2f(bits); };
+  float acc = 0.0f, yv = 0.0f;
+  uint32_t h = prog[0].next;
+  for (int j = 1;; j++) {
+    const mtgp_tinstr w = prog[j];
+    if (((uint32_t)(j - 1) & 1u) != (h & 1u)) return mtgp_nanf();  // parity of the link is part of the format
+    const uint32_t hh = h >> 1;
+    h = w.next;
+    bool st = false;
+    switch (hh) {
+#define CASE(n, EXPR) case TH_##n: acc = (EXPR); break; case TH_##n##_ST: acc = (EXPR); st = true; break;
+      CASE(ADD_AM, acc + M(w.b)) CASE(ADD_AI, acc + I(w.b)) CASE(ADD_MM, M(w.a) + M(w.b)) CASE(ADD_MI, M(w.a) + I(w.b))
+      CASE(ADD_AA, acc + acc)
+      CASE(MUL_AM, acc * M(w.b)) CASE(MUL_AI, acc * I(w.b)) CASE(MUL_MM, M(w.a) * M(w.b)) CASE(MUL_MI, M(w.a) * I(w.b))
+      CASE(MUL_AA, acc * acc)
+      CASE(SUB_AM, acc - M(w.b)) CASE(RSB_AM, M(w.b) - acc) CASE(RSB_AI, I(w.b) - acc) CASE(SUB_MM, M(w.a) - M(w.b))
+      CASE(RSB_MI, I(w.b) - M(w.a))
+      CASE(LOAD_M, M(w.a)) CASE(LOAD_I, I(w.a))
+#undef CASE
+      case TH_ST: st = true; break;
+      case TH_LDY_M: yv = M(w.b); break;
+      case TH_LDY_I: yv = I(w.b); break;
+      case TH_LDY_A: yv = acc; break;
+      case TH_SLOW_A: acc = mtgp_th_slow_op(w.c, acc, yv); break;
+      case TH_SLOW_M: acc = mtgp_th_slow_op(w.c, M(w.a), yv); break;
+      case TH_SLOW_I: acc = mtgp_th_slow_op(w.c, I(w.a), yv); break;
+      default: return acc;  // TH_END
+    }
+    if (st) memcpy(const_cast<unsigned char*>(vb) + w.c, &acc, 4);
+  }
+#endif
+}

@@ -44,17 +44,21 @@ int hostlib_eval_tree(const float* tree, int N, const mtgp_node_table* tab, cons
   uint32_t meta = mtgp_lower_tree<MTGP_MAX_NODES>(op.data(), a.data(), b.data(), c.data(), N, *tab, tmp_base,
                                                   prog.data(), &canonical);
   *flags_out = (canonical ? 1 : 0) | (lossy ? 2 : 0);
-  const int n_tmp = (int)(meta >> 16);
+  const int n_tmp = (int)MTGP_META_TMP(meta);
   std::vector<float> vf((size_t)(tmp_base + n_tmp + 2) * 32, 0.0f);
-  // the rollout kernel's pre-decoded form of the same program
-  const int n_instr = (int)(meta & 0xFFFFu) + 1;
-  std::vector<mtgp_wide_instr> wide(n_instr + 1);
-  for (int i = 0; i < n_instr; i++) wide[i] = mtgp_expand_instr(prog[i], (uint32_t)(tmp_base + n_tmp));
+  // the rollout kernels' threaded-code form of the same program (mtgp_threaded.cuh): expansion and linking are
+  // the product's code; the host build interprets it with the C restatement of the PTX handlers
+  const int n_instr = (int)MTGP_META_N(meta) + 1;
+  std::vector<mtgp_tinstr> th(1 + MTGP_TH_MAX_EXPAND * n_instr);
+  int m = 1;
+  for (int i = 0; i < n_instr; i++) m += mtgp_th_expand(prog[i], th.data() + m);
+  mtgp_th_link(th.data(), m - 1);
+  if (m != (int)MTGP_META_TH(meta)) return -1;
   for (int p = 0; p < n_pts; p++) {
     for (int j = 0; j < n_data; j++) vf[j * 32] = data[(size_t)p * n_data + j];
     out[p] = mtgp_interpret<1>(prog.data(), vf.data()).v[0];
     if (out_wide)
-      out_wide[p] = mtgp_interpret_wide(mtgp_saddr_of(wide.data()), mtgp_saddr_of(vf.data()));
+      out_wide[p] = mtgp_run_threaded(mtgp_saddr_of(th.data()), mtgp_saddr_of(vf.data()));
   }
   if (prog_out)
     for (int i = 0; i < lstride && i < prog_cap; i++) memcpy(&prog_out[i], &prog[i], 8);

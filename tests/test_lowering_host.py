@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def hostlib():
     d = os.path.join(HERE, "hostlib")
     so, src = os.path.join(d, "libmtgp_hosttest.so"), os.path.join(d, "host_harness.cu")
-    deps = [src] + [os.path.join(HERE, "..", "multitreegp_b200", "csrc", f) for f in ("mtgp_lower.cuh", "mtgp_program.cuh")]
+    deps = [src] + [os.path.join(HERE, "..", "multitreegp_b200", "csrc", f) for f in ("mtgp_lower.cuh", "mtgp_program.cuh", "mtgp_threaded.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(p) > os.path.getmtime(so) for p in deps):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler",
                                "-ffp-contract=off", "-Xcompiler", "-w", "-shared", "-o", so, src])
@@ -42,7 +42,7 @@ def host_eval(L, tree, tab, data):
                                C.c_void_p(out_wide.ctypes.data))
     # the compact interpreter (pointwise kernel) and the pre-decoded one (rollout kernel) must agree bit for bit
     assert util.same_or_both_nan(out, out_wide).all(), (out, out_wide)
-    return out, meta & 0xFFFF, meta >> 16, fl.value, prog
+    return out, meta & 0x3FF, (meta >> 22) & 0x3FF, fl.value, prog
 
 
 DATA = np.float32([[0.3, -1.2, 2.5], [1.5, 0.25, -0.75], [0, 0, 0], [-2.0, 3.0, 1e-3], [np.inf, 1, -1],
