@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MTGP_ABI_VERSION 2
+#define MTGP_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define MTGP_API __attribute__((visibility("default")))
@@ -153,14 +153,23 @@ typedef struct mtgp_rollout_desc {
   float pid_factormin;   /* 0 -> 0.2 */
   float pid_factormax;   /* 0 -> 10.0 */
   float pcoeff, icoeff, dcoeff; /* all 0 -> diffrax defaults (0, 1, 0): an I-controller */
-  int32_t reserved_;
+  uint32_t flags;        /* MTGP_DESC_* */
   const float* x0;        /* [B, D] */
   const float* ts;        /* [K]    */
   const float* targets;   /* [B, n_targets] or NULL */
   const uint32_t* obs_keys; /* [B, 2] threefry keys (NULL allowed when obs_noise == 0) */
   const float* params;    /* [B, n_params] or NULL */
   const float* ys_true;   /* SR only: [B, K, D] recorded trajectories */
+  /* [host] optional copy of `params` (same layout), or NULL.  The reference's own parameter samplers return
+   * the same values for every trajectory (acrobot.py:24-27: ones); when the library can see that on the
+   * host it runs kernels that take the environment constants from the constant bank instead of registers.
+   * Results are bit-identical either way. */
+  const float* params_host;
 } mtgp_rollout_desc;
+
+/* mtgp_rollout_desc.flags */
+#define MTGP_DESC_NOISE_INLINE 1u /* generate the observation noise inside the rollout kernel instead of reading
+                                     the per-evaluation table (same bits; exercised by the tests) */
 
 /* Optional per-trajectory outputs of evaluate_candidate (feedforward_evaluate.py:53-62 returns
  * xs, ys, us, fitness; dynamic_evaluate.py:54-63 adds activities; SR_evaluator.py:47-55 returns

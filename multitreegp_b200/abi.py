@@ -10,7 +10,7 @@ import ctypes as C
 
 import numpy as np
 
-MTGP_ABI_VERSION = 2
+MTGP_ABI_VERSION = 3
 MTGP_MAX_NODE_IDS = 64
 MTGP_MAX_NODES = 512
 
@@ -86,14 +86,17 @@ class RolloutDesc(C.Structure):
         ("pcoeff", C.c_float),
         ("icoeff", C.c_float),
         ("dcoeff", C.c_float),
-        ("reserved_", C.c_int32),
+        ("flags", C.c_uint32),
         ("x0", C.c_void_p),
         ("ts", C.c_void_p),
         ("targets", C.c_void_p),
         ("obs_keys", C.c_void_p),
         ("params", C.c_void_p),
         ("ys_true", C.c_void_p),
+        ("params_host", C.c_void_p),
     ]
+
+DESC_NOISE_INLINE = 1
 
 
 class TrajectoryOut(C.Structure):

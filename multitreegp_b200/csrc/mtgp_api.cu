@@ -439,6 +439,7 @@ int mtgp_population_fitness_host(const float* population_host, int P, int T, int
   if ((rc = scratch_for_device(total, &base_v))) return rc;
   unsigned char* base = static_cast<unsigned char*>(base_v);
   mtgp_rollout_desc dd = *dh;
+  dd.params_host = dh->params;  // the host copy is at hand: trajectory-uniform parameters are detected
 #define H2D(field, off, bytes)                                                                          \
   if (dh->field && (bytes) > 0) {                                                                       \
     MTGP_CUDA_TRY(cudaMemcpyAsync(base + off, dh->field, (bytes), cudaMemcpyHostToDevice, s));          \

@@ -43,6 +43,7 @@ struct RolloutParams {
   int slot_state;      // n_latent slots: master copy of the latent state
   int slots_per_warp;      // data + latent copies + temporaries + 1 scratch slot
   int th_cap;              // threaded-code instructions provisioned per warp (also bounds the compact staging area)
+  float envc[12];          // UPAR kernels: the environment's derived constants (acrobot_derive), same for every trajectory
   // general Runge-Kutta path (mtgp_rollout_rk.cu): Dopri5 and/or PIDController
   int solver, controller;
   float rtol, atol, dtmin, safety, factormin, factormax, coeff1, coeff2, coeff3;
@@ -143,26 +144,28 @@ __device__ __forceinline__ void warp_stage_programs(const RolloutParams& P, int 
   bar_phase ^= 1u;
 }
 
-// Offset of tree t's compact program in the staging area.
-__device__ __forceinline__ uint32_t compact_offset(const RolloutParams& P, int ind, int t) {
+// Offset of tree t's compact program in the staging area.  meta_ind = P.meta + ind * T.
+__device__ __forceinline__ uint32_t compact_offset(const uint32_t* meta_ind, int t) {
   uint32_t soff = 0;
-  for (int q = 0; q < t; q++) soff += (MTGP_META_N(P.meta[(size_t)ind * P.T + q]) + 2u) & ~1u;
+  for (int q = 0; q < t; q++) soff += (MTGP_META_N(meta_ind[q]) + 2u) & ~1u;
   return soff;
 }
 
-#define MTGP_NO_STORE 0xFFFFFFFFu
-// One threaded program = a CHAIN of trees run by a single interpreter call: tree `first + i` (i < count) is
-// expanded in turn; its value is stored to value-file slot `store_slot0 + i` (when store_slot0 >= 0) by giving
-// its last instruction the ..._ST form (or an ST instruction).  The value of the last tree is also the call's
-// result.  Writes [header]...[END] at dst, returns the instruction count.  Called by ONE lane.
-__device__ __forceinline__ int th_build_chain(const RolloutParams& P, int ind, const WarpArea& w, mtgp_tinstr* dst,
-                                              int first, int count, int store_slot0, int readout_tree = -1,
-                                              int readout_store = -1) {
+// One threaded program = a CHAIN of trees run by a single interpreter call: [readout_tree,] first, first + 1, ...
+// are expanded in turn; a tree's value is stored to its value-file slot (readout_store / store_slot0 + i, when
+// >= 0) by giving its last instruction the ..._ST form (or an ST instruction).  The value of the last tree is
+// also the call's result.  Writes [header]...[END] at dst, returns the instruction count.  Called by ONE lane;
+// out of line: it runs once per individual and is expanded at several sites.
+static __device__ __noinline__ int th_build_chain(const uint32_t* meta_ind, const uint2* prog_s, mtgp_tinstr* dst,
+                                                  int first, int count, int store_slot0, int readout_tree,
+                                                  int readout_store) {
   int m = 1;
-  auto append = [&](int t, int store_slot) {
-    const uint32_t soff = compact_offset(P, ind, t);
-    const int n = (int)MTGP_META_N(P.meta[(size_t)ind * P.T + t]);  // without X_END
-    for (int i = 0; i < n; i++) m += mtgp_th_expand(w.prog_s[soff + i], dst + m);
+  for (int i = (readout_tree >= 0 ? -1 : 0); i < count; i++) {
+    const int t = (i < 0) ? readout_tree : first + i;
+    const int store_slot = (i < 0) ? readout_store : (store_slot0 >= 0 ? store_slot0 + i : -1);
+    const uint32_t soff = compact_offset(meta_ind, t);
+    const int n = (int)MTGP_META_N(meta_ind[t]);  // without X_END
+    for (int q = 0; q < n; q++) m += mtgp_th_expand(prog_s[soff + q], dst + m);
     if (n == 0) {  // (the lowering pass always emits at least a load)
       dst[m].next = TH_LOAD_I; dst[m].a = 0; dst[m].b = 0; dst[m].c = 0;
       m++;
@@ -177,9 +180,7 @@ __device__ __forceinline__ int th_build_chain(const RolloutParams& P, int ind, c
         m++;
       }
     }
-  };
-  if (readout_tree >= 0) append(readout_tree, readout_store);
-  for (int i = 0; i < count; i++) append(first + i, store_slot0 >= 0 ? store_slot0 + i : -1);
+  }
   dst[m].next = TH_END; dst[m].a = 0; dst[m].b = 0; dst[m].c = 0;
   m++;
   mtgp_th_link(dst, m - 1);
@@ -311,6 +312,51 @@ __device__ __forceinline__ void sincos_contract(float x, float& s, float& c) {
   c = ((q + 1) & 2) ? -cv : cv;
 }
 
+// Branch-free sin / cos for arguments the caller has range-checked (|x| < 1e5, warp-uniformly): the contract's
+// Cody-Waite reduction, BOTH kernels, quadrant by select, sign by xor -- the same operations on the same values
+// as mtgp_sinf / mtgp_cosf, hence the same bits, without per-call range branches and quadrant branches.
+__device__ __forceinline__ float trig_pick(float sk, float ck, int n) {  // sin(r + n pi/2) from the two kernels
+  const float v = (n & 1) ? ck : sk;
+  return __uint_as_float(__float_as_uint(v) ^ (((uint32_t)n & 2u) << 30));
+}
+__device__ __forceinline__ float sin_checked(float x) {
+  int q;
+  const float r = mtgp_trig_reduce_cw(x, &q);
+  return trig_pick(mtgp_sin_kernel(r), mtgp_cos_kernel(r), q);
+}
+__device__ __forceinline__ float cos_checked(float x) {
+  int q;
+  const float r = mtgp_trig_reduce_cw(x, &q);
+  return trig_pick(mtgp_sin_kernel(r), mtgp_cos_kernel(r), q + 1);
+}
+__device__ __forceinline__ void sincos_checked(float x, float& s, float& c) {
+  int q;
+  const float r = mtgp_trig_reduce_cw(x, &q);
+  const float sk = mtgp_sin_kernel(r), ck = mtgp_cos_kernel(r);
+  s = trig_pick(sk, ck, q);
+  c = trig_pick(sk, ck, q + 1);
+}
+
+// Loop-invariant sub-expressions of Acrobot.drift (acrobot.py:51-72), in the source's own grouping, so that
+// the drift is the same sequence of float32 operations whether they are computed per lane on the device or
+// once on the host (IEEE mul/add: same bits) for the trajectory-uniform-parameter kernels.
+enum { AK_M2 = 0, AK_D1A, AK_D1B, AK_D1C, AK_D2A, AK_D2B, AK_PHI2, AK_P1A, AK_P1B, AK_P1C, AK_T2A, AK_DEN, AK_COUNT };
+__host__ __device__ inline void acrobot_derive(float l1, float l2, float m1, float m2, float* k) {
+  const float lc1 = 0.5f * l1, lc2 = 0.5f * l2, g = 9.81f, moi2 = 1.0f;
+  k[AK_M2] = m2;
+  k[AK_D1A] = m1 * (lc1 * lc1);
+  k[AK_D1B] = (l1 * l1) + (lc2 * lc2);
+  k[AK_D1C] = (2.0f * l1) * lc2;
+  k[AK_D2A] = lc2 * lc2;
+  k[AK_D2B] = l1 * lc2;
+  k[AK_PHI2] = (m2 * lc2) * g;
+  k[AK_P1A] = ((-m2) * l1) * lc2;
+  k[AK_P1B] = ((2.0f * m2) * l1) * lc2;
+  k[AK_P1C] = ((m1 * lc1) + (m2 * l1)) * g;
+  k[AK_T2A] = (m2 * l1) * lc2;
+  k[AK_DEN] = (m2 * (lc2 * lc2)) + moi2;
+}
+
 // ---- environments --------------------------------------------------------------------------------
 template <int ENV>
 struct EnvDim { static constexpr int D = 1, NT = 0; };  // D state components, NT targets (acrobot.py:11, harmonic_oscillator.py:12, reactor.py:11)
@@ -321,7 +367,7 @@ template <> struct EnvDim<MTGP_ENV_REACTOR> { static constexpr int D = 3, NT = 1
 template <int ENV>
 struct Env {
   static constexpr int D = EnvDim<ENV>::D;
-  float p[8];
+  float p[ENV == MTGP_ENV_ACROBOT ? AK_COUNT : 8];  // Acrobot: the derived constants (acrobot_derive)
   float target;
   uint32_t key0, key1;
   // cost accumulators
@@ -330,11 +376,8 @@ struct Env {
 
   __device__ __forceinline__ void init(const RolloutParams& P, int b) {
     if (ENV == MTGP_ENV_ACROBOT) {
-      const float l1 = P.params[b * P.n_params + 0], l2 = P.params[b * P.n_params + 1];
-      const float m1 = P.params[b * P.n_params + 2], m2 = P.params[b * P.n_params + 3];
-      p[0] = l1; p[1] = l2; p[2] = m1; p[3] = m2;
-      p[4] = 0.5f * l1;  // lc1
-      p[5] = 0.5f * l2;  // lc2
+      acrobot_derive(P.params[b * P.n_params + 0], P.params[b * P.n_params + 1], P.params[b * P.n_params + 2],
+                     P.params[b * P.n_params + 3], p);
     } else {
 #pragma unroll
       for (int i = 0; i < 8; i++) p[i] = (i < P.n_params) ? P.params[b * P.n_params + i] : 0.0f;
@@ -388,23 +431,21 @@ struct Env {
     return r;
   }
 
-  // NOISE: 0 none, 1 = noise term read from the precomputed table row `nz` (element stride `nzs`),
+  // NOISE: 0 none, 1 = noise term given in nz[0..3] (the caller read it from the precomputed table),
   //        2 = generated inline.  All three give the same bits.
   // FINITE_X: the caller guarantees (warp-uniformly) that every component of x is finite
   template <int NOISE, bool FINITE_X = false>
   __device__ __forceinline__ void f_obs(float t, const float* x, float* y, int n_obs, float obs_noise,
-                                        int partitionable, const float* nz, int nzs) const {
+                                        int partitionable, const float* nz) const {
     float nt[D];
     if (NOISE == 2) {
       const Noise4 r = noise_term_ool(t, n_obs, obs_noise, partitionable);
 #pragma unroll
       for (int i = 0; i < D; i++) nt[i] = r.v[i < 4 ? i : 3];
     }
-    if (NOISE == 1) {  // table row: [b][4] floats, one 16-byte load per lane
-      const float4 v = __ldg(reinterpret_cast<const float4*>(nz));
-      const float t4[4] = {v.x, v.y, v.z, v.w};
+    if (NOISE == 1) {
 #pragma unroll
-      for (int i = 0; i < D; i++) nt[i] = t4[i < 4 ? i : 3];
+      for (int i = 0; i < D; i++) nt[i] = nz[i < 4 ? i : 3];
     }
     const float z = FINITE_X ? obs_zero_term<D>(x) : 0.0f;
 #pragma unroll
@@ -439,23 +480,39 @@ struct Env {
     }
   }
 
-  __device__ __forceinline__ void drift(const float* s, float u_in, float* ds) const {
+  // UPAR: every trajectory has the same parameters and the derived constants come from the kernel
+  // parameters (constant bank operands, no registers) instead of this lane's p[].
+  template <bool UPAR = false>
+  __device__ __forceinline__ void drift(const float* s, float u_in, float* ds, const RolloutParams& P) const {
     if (ENV == MTGP_ENV_ACROBOT) {  // acrobot.py:51-72
       const float control = clip_jnp(u_in, -1.0f, 1.0f);
       const float theta1 = s[0], theta2 = s[1], theta1_dot = s[2], theta2_dot = s[3];
-      const float l1 = p[0], m1 = p[2], m2 = p[3], lc1 = p[4], lc2 = p[5];
-      const float g = 9.81f, moi1 = 1.0f, moi2 = 1.0f, half_pi = 1.57079637f;
-      float s2, c2;
-      sincos_contract(theta2, s2, c2);
-      const float d1 = m1 * (lc1 * lc1) + m2 * (((l1 * l1) + (lc2 * lc2)) + ((2.0f * l1) * lc2) * c2) + moi1 + moi2;
-      const float d2 = m2 * ((lc2 * lc2) + (l1 * lc2) * c2) + moi2;
-      const float phi2 = ((m2 * lc2) * g) * mtgp_cosf((theta1 + theta2) - half_pi);
-      const float phi1 = ((((-m2) * l1) * lc2) * (theta2_dot * theta2_dot)) * s2 -
-                         (((((2.0f * m2) * l1) * lc2) * theta1_dot) * theta2_dot) * mtgp_sinf(theta1) +
-                         (((m1 * lc1) + (m2 * l1)) * g) * mtgp_cosf(theta1 - half_pi) + phi2;
+#define AK(i) (UPAR ? P.envc[i] : p[i])
+      const float m2 = AK(AK_M2);
+      const float moi1 = 1.0f, moi2 = 1.0f, half_pi = 1.57079637f;
+      // the five trigonometric values: when every lane's angles are small enough that all four arguments are
+      // inside the contract's fast range (|theta| < 4e4 => |theta1 + theta2 - pi/2| < 1e5), without range branches
+      float s2, c2, c12, s1, c1h;
+      if (__all_sync(__activemask(), fabsf(theta1) < 40000.0f && fabsf(theta2) < 40000.0f)) {
+        sincos_checked(theta2, s2, c2);
+        c12 = cos_checked((theta1 + theta2) - half_pi);
+        s1 = sin_checked(theta1);
+        c1h = cos_checked(theta1 - half_pi);
+      } else {
+        sincos_contract(theta2, s2, c2);
+        c12 = mtgp_cosf((theta1 + theta2) - half_pi);
+        s1 = mtgp_sinf(theta1);
+        c1h = mtgp_cosf(theta1 - half_pi);
+      }
+      const float d1 = AK(AK_D1A) + m2 * (AK(AK_D1B) + AK(AK_D1C) * c2) + moi1 + moi2;
+      const float d2 = m2 * (AK(AK_D2A) + AK(AK_D2B) * c2) + moi2;
+      const float phi2 = AK(AK_PHI2) * c12;
+      const float phi1 = (AK(AK_P1A) * (theta2_dot * theta2_dot)) * s2 -
+                         ((AK(AK_P1B) * theta1_dot) * theta2_dot) * s1 + AK(AK_P1C) * c1h + phi2;
       const float theta2_acc =
-          (((control + (d2 / d1) * phi1) - (((m2 * l1) * lc2) * (theta1_dot * theta1_dot)) * s2) - phi2) /
-          (((m2 * (lc2 * lc2)) + moi2) - (d2 * d2) / d1);
+          (((control + (d2 / d1) * phi1) - (AK(AK_T2A) * (theta1_dot * theta1_dot)) * s2) - phi2) /
+          (AK(AK_DEN) - (d2 * d2) / d1);
+#undef AK
       const float theta1_acc = (-((d2 * theta2_acc) + phi1)) / d1;
       ds[0] = theta1_dot; ds[1] = theta2_dot; ds[2] = theta1_acc; ds[3] = theta2_acc;
     } else if (ENV == MTGP_ENV_HARMONIC) {  // harmonic_oscillator.py:61-63,70-71

@@ -22,8 +22,6 @@
 #ifndef MTGP_INTERP_INLINE
 #define MTGP_INTERP_INLINE __forceinline__
 #endif
-#include <stdlib.h>
-
 #include "mtgp_env.cuh"
 
 using namespace mtgp_dev;
@@ -88,7 +86,9 @@ __global__ void __launch_bounds__(256) k_noise_table(const RolloutParams P, cons
 //   states (DynamicPolicy.ipynb: state_size = 2).  The per-component predicates and the latent loops vanish.
 // TRAJ_OUT: the evaluate_candidate outputs (xs, ys, us, activities, per-trajectory fitness) are requested.
 // Population evaluation never asks for them, and without their code the hot loop is 120 instructions shorter.
-template <int KIND, int ENV, int NOISE, int SPEC, bool TRAJ_OUT>
+// UPAR: the environment parameters are the same for every trajectory (the reference's samplers: acrobot.py:24-27)
+// and their derived constants are kernel parameters (constant bank) instead of per-lane registers.
+template <int KIND, int ENV, int NOISE, int SPEC, bool TRAJ_OUT, bool UPAR>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_rollout(const RolloutParams P) {
   constexpr int D = (KIND == MTGP_EVAL_SR) ? 0 : EnvDim<ENV>::D;
   constexpr int DR = D > 0 ? D : 1;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
     bool readout_reads_y = false;
     if (KIND == MTGP_EVAL_DYNAMIC) {
       // does the readout read an observation or the control slot?  (conservative: unused operand fields count)
-      const uint32_t soff = compact_offset(P, ind, P.state_size);
+      const uint32_t soff = compact_offset(P.meta + (size_t)ind * P.T, P.state_size);
       const int n = (int)MTGP_META_N(P.meta[(size_t)ind * P.T + P.state_size]);
       for (int i = lane; i < n; i += 32) {
         const uint2 c = wa.prog_s[soff + i];
@@ -150,24 +150,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
     //   SR     : [tree j -> slot_out + j]...
     // plus a stand-alone readout for the save points of the dynamic policy.
     if (lane == 0) {
+      const uint32_t* mi = P.meta + (size_t)ind * P.T;
       int off = 0;
       if (KIND == MTGP_EVAL_STATIC) {
         wa.woff[0] = wa.woff[1] = wa.woff[2] = 0;
-        off += th_build_chain(P, ind, wa, wa.th, 0, 1, -1);
+        off += th_build_chain(mi, wa.prog_s, wa.th, 0, 1, -1, -1, -1);
       } else if (KIND == MTGP_EVAL_SR) {
         wa.woff[0] = wa.woff[1] = wa.woff[2] = 0;
-        off += th_build_chain(P, ind, wa, wa.th, 0, P.T, P.slot_out);
+        off += th_build_chain(mi, wa.prog_s, wa.th, 0, P.T, P.slot_out, -1, -1);
       } else {
         wa.woff[2] = 0;  // stand-alone readout
-        off += th_build_chain(P, ind, wa, wa.th, P.state_size, 1, -1);
-        if (readout_sees_y) {
-          wa.woff[0] = 0;
-          wa.woff[1] = off;
-          off += th_build_chain(P, ind, wa, wa.th + off, 0, P.state_size, P.slot_out);
-        } else {
-          wa.woff[0] = wa.woff[1] = off;
-          off += th_build_chain(P, ind, wa, wa.th + off, 0, P.state_size, P.slot_out, P.state_size, P.slot_u);
-        }
+        off += th_build_chain(mi, wa.prog_s, wa.th, P.state_size, 1, -1, -1, -1);
+        wa.woff[0] = readout_sees_y ? 0 : off;
+        wa.woff[1] = off;
+        // the state equations, preceded by the readout (-> slot_u) unless it has to see zeros
+        off += th_build_chain(mi, wa.prog_s, wa.th + off, 0, P.state_size, P.slot_out,
+                              readout_sees_y ? -1 : P.state_size, P.slot_u);
       }
     }
     __syncwarp();
@@ -241,26 +239,29 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
         float tprev = t0, tnext = t0 + P.dt0;
         tnext = tnext < t1 ? tnext : t1;
         int steps = 0, k = 0;
-        const float* nz_step = nz_base;  // noise-table row of the current step
         unsigned int lane_steps = 0;  // steps this lane integrated before its event fired
         float ts_k = ts[0];  // ts[k], reloaded only when k advances
+        // NOISE == 1: the table row of the coming step, fetched one step ahead (an L2 hit is ~250 cycles)
+        float4 nz_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (NOISE == 1) nz_next = __ldg(reinterpret_cast<const float4*>(nz_base));
         // One iteration = one Euler step while any lane is still integrating, then the save points that
         // step covers.  Once the solve is over (t1 reached, max_steps, or every lane's event fired) the
         // remaining save points are emitted from the inf pre-fill of SaveAt -- by the same code.
         while (k < K) {
           const bool stepping = (tprev < t1) && (steps < P.max_steps) &&
                                 (__ballot_sync(0xFFFFFFFFu, alive && lane_valid) != 0u);
-          float save_until = mtgp_inff(), new_tprev = tprev, new_tnext = tnext;
+          float save_until = mtgp_inff();
           if (stepping) {
             const float dt = tnext - tprev;
             float u = 0.0f;
             if (KIND != MTGP_EVAL_SR) {
               float y[DR];
               // a dead lane's x is frozen at its last committed (finite) value; only a non-finite x0 takes the literal path
+              const float nzv[4] = {nz_next.x, nz_next.y, nz_next.z, nz_next.w};
               if (__any_sync(0xFFFFFFFFu, x_nonfinite))
-                env.template f_obs<NOISE, false>(tprev, x, y, n_obs, P.obs_noise, P.partitionable, nz_step, nzs);
+                env.template f_obs<NOISE, false>(tprev, x, y, n_obs, P.obs_noise, P.partitionable, nzv);
               else
-                env.template f_obs<NOISE, true>(tprev, x, y, n_obs, P.obs_noise, P.partitionable, nz_step, nzs);
+                env.template f_obs<NOISE, true>(tprev, x, y, n_obs, P.obs_noise, P.partitionable, nzv);
               if (KIND == MTGP_EVAL_STATIC) {
 #pragma unroll
                 for (int i = 0; i < D; i++)
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
                 u = mtgp_run_threaded(prog_step, lbytes);  // feedforward :107 / dynamic readout :113
               }
               float dx[DR];
-              env.drift(x, u, dx);
+              env.template drift<UPAR>(x, u, dx, P);
 #pragma unroll
               for (int i = 0; i < D; i++) x1[i] = x[i] + dt * dx[i];
               if (KIND == MTGP_EVAL_DYNAMIC && readout_sees_y) {
@@ -304,9 +305,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
               for (int j = 0; j < NL; j++)
                 mtgp_sts_f32(a_out + 128u * j, mtgp_lds_f32(a_state + 128u * j) + dt * mtgp_lds_f32(a_out + 128u * j));
             }
-            new_tprev = tnext < t1 ? tnext : t1;
-            new_tnext = tnext + P.dt0;
-            new_tnext = (new_tnext > t1 - 1e-6f) ? t1 : new_tnext;  // _clip_to_end
             save_until = tnext;
           }
           const bool live_save = stepping && alive;
@@ -337,8 +335,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
               sr_total = sr_total + row;
             } else {
               float ys[DR];
-              env.template f_obs<NOISE, false>(tk, xs, ys, n_obs, P.obs_noise, P.partitionable,
-                                               nz_base + (size_t)(P.cap_steps + k) * nzs, nzs);
+              float nzk[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+              if (NOISE == 1) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(nz_base + (size_t)(P.cap_steps + k) * nzs));
+                nzk[0] = v.x; nzk[1] = v.y; nzk[2] = v.z; nzk[3] = v.w;
+              }
+              env.template f_obs<NOISE, false>(tk, xs, ys, n_obs, P.obs_noise, P.partitionable, nzk);
               if (KIND == MTGP_EVAL_STATIC || readout_sees_y) {
 #pragma unroll
                 for (int i = 0; i < D; i++)
@@ -405,10 +407,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
               }
             }
             if (alive && fired) alive = false;
-            tprev = new_tprev;
-            tnext = new_tnext;
+            {  // ConstantStepSize: accumulated tnext + dt0, clipped to t1 (_clip_to_end)
+              const float new_tprev = tnext < t1 ? tnext : t1;
+              float new_tnext = tnext + P.dt0;
+              new_tnext = (new_tnext > t1 - 1e-6f) ? t1 : new_tnext;
+              tprev = new_tprev;
+              tnext = new_tnext;
+            }
             steps++;
-            if (NOISE == 1) nz_step += nzs;
+            if (NOISE == 1 && steps < P.cap_steps) nz_next = __ldg(reinterpret_cast<const float4*>(nz_base + (size_t)steps * nzs));
           }
         }
         if (pass == 0 && lane_valid) my_steps += lane_steps;
@@ -457,7 +464,7 @@ size_t rollout_smem(const RolloutParams& rp) {
   return 16 * kWarpsPerCta + (size_t)kWarpsPerCta * warp_area_bytes(rp.th_cap, rp.slots_per_warp);
 }
 
-template <int KIND, int ENV, int NOISE, int SPEC, bool TRAJ_OUT>
+template <int KIND, int ENV, int NOISE, int SPEC, bool TRAJ_OUT, bool UPAR>
 int launch_one(RolloutParams rp, int tmp_base, int n_tmp, int th_cap, int want_fast, cudaStream_t stream) {
   rp.slots_per_warp = tmp_base + n_tmp + 1;
   rp.th_cap = (th_cap + 1) & ~1;
@@ -467,7 +474,7 @@ int launch_one(RolloutParams rp, int tmp_base, int n_tmp, int th_cap, int want_f
     mtgp_set_error("rollout needs %zu bytes of shared memory per CTA: over the 227 KB limit", smem);
     return MTGP_ERR_UNSUPPORTED;
   }
-  auto kern = k_rollout<KIND, ENV, NOISE, SPEC, TRAJ_OUT>;
+  auto kern = k_rollout<KIND, ENV, NOISE, SPEC, TRAJ_OUT, UPAR>;
   MTGP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   unsigned blocks = (unsigned)((rp.P + kWarpsPerCta - 1) / kWarpsPerCta);
   rp.next_slot = nullptr;
@@ -488,7 +495,7 @@ int launch_one(RolloutParams rp, int tmp_base, int n_tmp, int th_cap, int want_f
 // worst-case bounds.  Each launch skips the other's individuals.  (kFastTmp, kFastTh: mtgp_env.cuh)
 
 template <int KIND, int ENV>
-int launch_kind_env(RolloutParams rp, int tmp_base, int bound, void* noise_ws, cudaStream_t stream) {
+int launch_kind_env(RolloutParams rp, int tmp_base, int bound, void* noise_ws, bool upar, cudaStream_t stream) {
   int noise = 0;
   if (rp.obs_noise != 0.0f && KIND != MTGP_EVAL_SR) {
     noise = noise_ws ? 1 : 2;
@@ -519,11 +526,17 @@ int launch_kind_env(RolloutParams rp, int tmp_base, int bound, void* noise_ws, c
       spec = 1;
   }
   const bool traj_out = rp.xs_o || rp.ys_o || rp.us_o || rp.act_o || rp.tf_o;
+#define LAUNCH1U(NZ, SPEC, TR, UP)                                                                    \
+  {                                                                                                   \
+    rc = launch_one<KIND, ENV, NZ, SPEC, TR, UP>(rp, tmp_base, rp.fast_tmp, rp.fast_th, 1, stream);   \
+    if (rc == MTGP_OK && !all_fast)                                                                   \
+      rc = launch_one<KIND, ENV, NZ, SPEC, TR, UP>(rp, tmp_base, bound, worst_th, 0, stream);         \
+  }
+  // the uniform-parameter instantiation exists for the Acrobot (the environment whose drift constants matter)
 #define LAUNCH1T(NZ, SPEC, TR)                                                                        \
   {                                                                                                   \
-    rc = launch_one<KIND, ENV, NZ, SPEC, TR>(rp, tmp_base, rp.fast_tmp, rp.fast_th, 1, stream);       \
-    if (rc == MTGP_OK && !all_fast)                                                                   \
-      rc = launch_one<KIND, ENV, NZ, SPEC, TR>(rp, tmp_base, bound, worst_th, 0, stream);             \
+    if constexpr (ENV == MTGP_ENV_ACROBOT) { if (upar) LAUNCH1U(NZ, SPEC, TR, true) else LAUNCH1U(NZ, SPEC, TR, false) } \
+    else LAUNCH1U(NZ, SPEC, TR, false)                                                                \
   }
 #define LAUNCH1(NZ, SPEC) { if (traj_out) LAUNCH1T(NZ, SPEC, true) else LAUNCH1T(NZ, SPEC, false) }
 #define LAUNCH2(NZ)                                                                                   \
@@ -534,6 +547,7 @@ int launch_kind_env(RolloutParams rp, int tmp_base, int bound, void* noise_ws, c
 #undef LAUNCH2
 #undef LAUNCH1
 #undef LAUNCH1T
+#undef LAUNCH1U
   return rc;
 }
 
@@ -569,8 +583,8 @@ int mtgp_noise_cap_steps(const mtgp_rollout_desc& d) { return d.max_steps < (1 <
 size_t mtgp_noise_workspace_bytes(const mtgp_rollout_desc& d) {
   if (d.kind == MTGP_EVAL_SR || d.obs_noise == 0.0f) return 0;
   if (d.solver != MTGP_SOLVER_EULER || d.controller != MTGP_CONTROLLER_CONSTANT) return 0;  // per-lane times
-  const char* force_inline = getenv("MTGP_NOISE_INLINE");  // test hook: exercise the in-kernel generator
-  if (force_inline && force_inline[0] == '1') return 0;
+  if (d.flags & MTGP_DESC_NOISE_INLINE) return 0;
+  if (d.max_steps > mtgp_noise_cap_steps(d)) return 0;  // the table could not hold every step row
   const size_t cap = (size_t)mtgp_noise_cap_steps(d);
   const size_t bytes = ((cap + 64 + 3) & ~(size_t)3) * sizeof(float) + (cap + d.K) * (size_t)4 * d.B * sizeof(float);
   return bytes <= kNoiseTableMaxBytes ? bytes : 0;
@@ -640,7 +654,15 @@ int mtgp_launch_rollout(const mtgp_programs& progs, const int32_t* live, int P, 
     rp.th_cap = mtgp_worst_threaded(T, progs.lstride);
     return mtgp_launch_rollout_rk(rp, d.kind, d.env_id, progs.tmp_base, bound, stream);
   }
-#define DISPATCH(KIND, ENV) return launch_kind_env<KIND, ENV>(rp, progs.tmp_base, bound, noise_ws, stream)
+  // trajectory-uniform environment parameters, visible on the host: derived constants into the kernel parameters
+  bool upar = false;
+  if (d.env_id == MTGP_ENV_ACROBOT && d.kind != MTGP_EVAL_SR && d.params_host && d.n_params == 4) {
+    upar = true;
+    for (int b = 1; b < d.B && upar; b++)
+      for (int i = 0; i < 4; i++) upar &= (mtgp_f2u(d.params_host[b * 4 + i]) == mtgp_f2u(d.params_host[i]));
+    if (upar) acrobot_derive(d.params_host[0], d.params_host[1], d.params_host[2], d.params_host[3], rp.envc);
+  }
+#define DISPATCH(KIND, ENV) return launch_kind_env<KIND, ENV>(rp, progs.tmp_base, bound, noise_ws, upar, stream)
   if (d.kind == MTGP_EVAL_SR) DISPATCH(MTGP_EVAL_SR, MTGP_ENV_NONE);
   if (d.kind == MTGP_EVAL_STATIC) {
     if (d.env_id == MTGP_ENV_ACROBOT) DISPATCH(MTGP_EVAL_STATIC, MTGP_ENV_ACROBOT);

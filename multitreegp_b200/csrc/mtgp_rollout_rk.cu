@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
       int off = 0;
       for (int q = 0; q < t; q++) off += (int)MTGP_META_TH(P.meta[(size_t)ind * P.T + q]);
       wa.woff[t] = off;
-      th_build_chain(P, ind, wa, wa.th + off, t, 1, -1);
+      th_build_chain(P.meta + (size_t)ind * P.T, wa.prog_s, wa.th + off, t, 1, -1, -1, -1);
     }
     __syncwarp();
 
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
         if (KIND != MTGP_EVAL_SR) {
 #pragma unroll
           for (int i = 0; i < D; i++) x[i] = src[i * 32];
-          env.template f_obs<NOISE ? 2 : 0>(t, x, y, n_obs, P.obs_noise, P.partitionable, nullptr, 0);
+          env.template f_obs<NOISE ? 2 : 0>(t, x, y, n_obs, P.obs_noise, P.partitionable, nullptr);
           if (KIND == MTGP_EVAL_STATIC) {
 #pragma unroll
             for (int i = 0; i < D; i++)
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
             lb[P.slot_u * 32] = 0.0f;
           }
           const float u = mtgp_run_threaded(prog_readout, lbytes);
-          env.drift(x, u, dx);
+          env.template drift<false>(x, u, dx, P);
 #pragma unroll
           for (int i = 0; i < D; i++) {
             dst[i * 32] = scale * dx[i];
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
               lb[(P.slot_lat + j) * 32] = lat;
               if (doit && P.act_o && lane_valid && pass == 0) P.act_o[(((size_t)ind * P.B + b) * K + kk) * NL + j] = lat;
             }
-            env.template f_obs<NOISE ? 2 : 0>(tk, xs, ys, n_obs, P.obs_noise, P.partitionable, nullptr, 0);
+            env.template f_obs<NOISE ? 2 : 0>(tk, xs, ys, n_obs, P.obs_noise, P.partitionable, nullptr);
 #pragma unroll
             for (int i = 0; i < D; i++)
               if (i < n_obs) lb[i * 32] = ys[i];

@@ -29,16 +29,20 @@
 
 #include "mtgp_program.cuh"
 
-// handler list: X(name, has_store_variant)
+// handler lists.  Arithmetic / load forms exist with and without a fused store: X(name, dispatch of the plain
+// form, dispatch of the ..._ST form) -- the dispatch macros (TH_GO*) are defined with the PTX block below.
 #define MTGP_TH_ARITH(X) \
-  X(ADD_AM) X(ADD_AI) X(ADD_MM) X(ADD_MI) X(ADD_AA) \
-  X(MUL_AM) X(MUL_AI) X(MUL_MM) X(MUL_MI) X(MUL_AA) \
-  X(SUB_AM) X(RSB_AM) X(RSB_AI) X(SUB_MM) X(RSB_MI) \
-  X(LOAD_M) X(LOAD_I)
-#define MTGP_TH_OTHER(X) X(ST) X(LDY_M) X(LDY_I) X(LDY_A) X(SLOW_A) X(SLOW_M) X(SLOW_I) X(END)
+  X(ADD_AM, TH_GO_L1A, TH_GO_L1A) X(ADD_AI, TH_GO_L1A, TH_GO_L2A) X(ADD_MM, TH_GO_L2C, TH_GOC) \
+  X(ADD_MI, TH_GO_L1C, TH_GOC) X(ADD_AA, TH_GOC, TH_GOC) \
+  X(MUL_AM, TH_GO_L1A, TH_GO_L1A) X(MUL_AI, TH_GO_L1A, TH_GO_L2A) X(MUL_MM, TH_GO_L2C, TH_GOC) \
+  X(MUL_MI, TH_GO_L1C, TH_GOC) X(MUL_AA, TH_GOC, TH_GOC) \
+  X(SUB_AM, TH_GOC, TH_GOC) X(RSB_AM, TH_GOC, TH_GOC) X(RSB_AI, TH_GOC, TH_GOC) X(SUB_MM, TH_GOC, TH_GOC) \
+  X(RSB_MI, TH_GOC, TH_GOC) X(LOAD_M, TH_GOC, TH_GOC) X(LOAD_I, TH_GOC, TH_GOC)
+#define MTGP_TH_OTHER(X) \
+  X(ST) X(LDY_M) X(LDY_I) X(LDY_A) X(SLOW_A) X(SLOW_M) X(SLOW_I) X(SIN_A) X(SIN_M) X(COS_A) X(COS_M) X(END)
 
 enum mtgp_th : uint32_t {
-#define X(n) TH_##n, TH_##n##_ST,
+#define X(n, g0, g1) TH_##n, TH_##n##_ST,
   MTGP_TH_ARITH(X)
 #undef X
 #define X(n) TH_##n,
@@ -117,6 +121,12 @@ __host__ __device__ __forceinline__ int mtgp_th_expand(uint2 c, mtgp_tinstr* out
     default: sop = S_SIN + (op - X_SIN); binary = false; break;  // SIN COS EXP LOG SQRT TANH NEG ABS
   }
   int n = 0;
+  if ((op == X_SIN || op == X_COS) && xk != OK_IMM) {  // in-block handlers (fast path inside the PTX block)
+    const uint32_t h = (op == X_SIN) ? (xk == OK_ACC ? TH_SIN_A : TH_SIN_M) : (xk == OK_ACC ? TH_COS_A : TH_COS_M);
+    put(n++, h, xk == OK_MEM ? xs : 0u, 0, 0);
+    if (has_st) put(n++, TH_ST, 0, 0, sto);
+    return n;
+  }
   if (op == X_LOAD) { put(n++, TH_LDY_I, 0, 0x80000000u, 0); }  // x + (-0.0) == x
   else if (binary) put(n++, yk == OK_ACC ? TH_LDY_A : (yk == OK_MEM ? TH_LDY_M : TH_LDY_I), 0, yk == OK_MEM ? ys : imm, 0);
   put(n++, xk == OK_ACC ? TH_SLOW_A : (xk == OK_MEM ? TH_SLOW_M : TH_SLOW_I), xk == OK_MEM ? xs : imm, 0, sop);
@@ -124,12 +134,57 @@ __host__ __device__ __forceinline__ int mtgp_th_expand(uint2 c, mtgp_tinstr* out
   return n;
 }
 
-// header + n instructions (prog[0] = header, prog[1..n] = instructions with their own handler in .next):
-// rewrite .next to the successor's table index.  Lane-parallel safe when called by one thread.
+// Two-level dispatch.  ptxas gives every brx.idx its own jump table in the constant bank; with one table per
+// handler (fully threaded code) the tables (85 x 85 entries) thrash the indexed-constant cache and every
+// dispatch waits for a miss (measured: 25 % issue utilisation).  So: the HOT handlers -- the + and * forms that
+// make up most of a program -- end with their own brx.idx over a SHORT table (hot targets + one "cold" entry),
+// indexed by the hot index of the successor, which the instruction carries in the operand word its form does
+// not use; everything else goes through one shared brx.idx per register set over the full table.
+#ifndef MTGP_TH_HOT_LEVEL
+#define MTGP_TH_HOT_LEVEL 2
+#endif
+#if MTGP_TH_HOT_LEVEL >= 2
+#define MTGP_TH_NHOT 12
+#elif MTGP_TH_HOT_LEVEL == 1
+#define MTGP_TH_NHOT 8
+#else
+#define MTGP_TH_NHOT 0
+#endif
+// hot index of a handler (MTGP_TH_NHOT = cold); the order is the order of the HOT label lists below
+__host__ __device__ __forceinline__ uint32_t mtgp_th_hot_index(uint32_t h) {
+#if MTGP_TH_HOT_LEVEL >= 1
+  switch (h) {
+    case TH_ADD_AM: return 0; case TH_ADD_AM_ST: return 1; case TH_ADD_AI: return 2; case TH_ADD_MI: return 3;
+    case TH_MUL_AM: return 4; case TH_MUL_AM_ST: return 5; case TH_MUL_AI: return 6; case TH_MUL_MI: return 7;
+#if MTGP_TH_HOT_LEVEL >= 2
+    case TH_ADD_AI_ST: return 8; case TH_ADD_MM: return 9; case TH_MUL_AI_ST: return 10; case TH_MUL_MM: return 11;
+#endif
+    default: break;
+  }
+#endif
+  return MTGP_TH_NHOT;
+}
+// which operand word of a hot handler's instruction carries the successor's hot index: 1 = .a (forms whose x
+// is the accumulator), 3 = .c (forms without a store), 0 = the handler is not hot
+__host__ __device__ __forceinline__ int mtgp_th_hot_word(uint32_t h) {
+  if (mtgp_th_hot_index(h) == MTGP_TH_NHOT) return 0;
+  return (h == TH_ADD_MI || h == TH_MUL_MI || h == TH_ADD_MM || h == TH_MUL_MM) ? 3 : 1;
+}
+
+// header + n instructions (prog[0] = header, prog[1..n] = instructions with their OWN handler in .next):
+// rewrite .next to the successor's handler, and give hot instructions their successor's hot index.
 __host__ __device__ __forceinline__ void mtgp_th_link(mtgp_tinstr* prog, int n) {
-  prog[0].next = 0; prog[0].a = 0; prog[0].b = 0; prog[0].c = 0;
-  for (int j = 0; j < n; j++) prog[j].next = 2u * prog[j + 1].next + ((uint32_t)j & 1u);  // successor position j (0-based) parity
-  prog[n].next = 0;
+  prog[0].next = TH_COUNT; prog[0].a = 0; prog[0].b = 0; prog[0].c = 0;
+  uint32_t own = TH_COUNT;  // the header is not an instruction
+  for (int j = 0; j < n; j++) {
+    const uint32_t nxt = prog[j + 1].next;
+    const int hw = (own < TH_COUNT) ? mtgp_th_hot_word(own) : 0;
+    prog[j].next = nxt;
+    if (hw == 1) prog[j].a = mtgp_th_hot_index(nxt);
+    if (hw == 3) prog[j].c = mtgp_th_hot_index(nxt);
+    own = nxt;
+  }
+  prog[n].next = TH_END;
 }
 
 // slow operators: ordinary C on the contract's functions
@@ -154,74 +209,149 @@ static __host__ __device__ __forceinline__ float mtgp_th_slow_op(uint32_t sop, f
 
 #if defined(__CUDA_ARCH__)
 // ---- the PTX block ---------------------------------------------------------------------------------
-// operands: %0 acc  %1 pc  %2 nh (in: handler of [pc]; out: handler of the instruction after a SLOW)
-//           %3 status  %4 xv  %5 yv  %6 lane
-#define TH_NEXT(N) " add.u32 %1,%1,16;\n ld.shared.v4.u32 {" N "0," N "1," N "2," N "3},[%1];\n"
-#define TH_GO(C) " brx.idx " C "0, TBL;\n"
-#define TH_XM(C) " add.u32 ad,%6," C "1;\n ld.shared.f32 t0,[ad];\n"
-#define TH_YM(C) " add.u32 ae,%6," C "2;\n ld.shared.f32 t1,[ae];\n"
-#define TH_XI(C) " mov.b32 t0," C "1;\n"
-#define TH_YI(C) " mov.b32 t1," C "2;\n"
-#define TH_STORE(C) " add.u32 ad,%6," C "3;\n st.shared.f32 [ad],%0;\n"
+// operands: %0 acc  %1 pc  %2 nh (in: handler of [pc]; out: handler of the instruction after a slow exit)
+//           %3 status  %4 xv  %5 yv  %6 lane  %7 parity (register set the instruction at pc belongs to: 0 = a, 1 = b)
+// Macro parameters C / N: the register set of the current / next instruction (tokens a, b).
+#define TH_PARNUM_a "0"
+#define TH_PARNUM_b "1"
+#define TH_NEXT(N) " add.u32 %1,%1,16;\n ld.shared.v4.u32 {" #N "0," #N "1," #N "2," #N "3},[%1];\n"
+#define TH_GOC(C, N) " bra DISP_" #C ";\n"                       // shared dispatch of this register set
+#define TH_GOH1(C, N) " brx.idx " #C "1, HOT" #N ";\n"           // own dispatch, hot index in word .a
+#define TH_GOH3(C, N) " brx.idx " #C "3, HOT" #N ";\n"           // own dispatch, hot index in word .c
+#if MTGP_TH_HOT_LEVEL >= 1
+#define TH_GO_L1A TH_GOH1
+#define TH_GO_L1C TH_GOH3
+#else
+#define TH_GO_L1A TH_GOC
+#define TH_GO_L1C TH_GOC
+#endif
+#if MTGP_TH_HOT_LEVEL >= 2
+#define TH_GO_L2A TH_GOH1
+#define TH_GO_L2C TH_GOH3
+#else
+#define TH_GO_L2A TH_GOC
+#define TH_GO_L2C TH_GOC
+#endif
+#define TH_XM(C) " add.u32 ad,%6," #C "1;\n ld.shared.f32 t0,[ad];\n"
+#define TH_YM(C) " add.u32 ae,%6," #C "2;\n ld.shared.f32 t1,[ae];\n"
+#define TH_XI(C) " mov.b32 t0," #C "1;\n"
+#define TH_YI(C) " mov.b32 t1," #C "2;\n"
+#define TH_NONE(C) ""
+#define TH_XMYM(C) TH_XM(C) TH_YM(C)
+#define TH_XMYI(C) TH_XM(C) TH_YI(C)
+#define TH_STORE(C) " add.u32 ad,%6," #C "3;\n st.shared.f32 [ad],%0;\n"
 #define TH_NOSTORE(C) ""
-#define TH_OP(PRE, OP, X, Y, C, N, ST) PRE TH_NEXT(N) " " OP " %0," X "," Y ";\n" ST(C) TH_GO(C)
+#define TH_OP(PRE, OP, X, Y, C, N, ST, GO) PRE(C) TH_NEXT(N) " " OP " %0," X "," Y ";\n" ST(C) GO(C, N)
 
-#define TH_B_ADD_AM(C, N, ST) TH_OP(TH_YM(C), "add.rn.f32", "%0", "t1", C, N, ST)
-#define TH_B_ADD_AI(C, N, ST) TH_OP(TH_YI(C), "add.rn.f32", "%0", "t1", C, N, ST)
-#define TH_B_ADD_MM(C, N, ST) TH_OP(TH_XM(C) TH_YM(C), "add.rn.f32", "t0", "t1", C, N, ST)
-#define TH_B_ADD_MI(C, N, ST) TH_OP(TH_XM(C) TH_YI(C), "add.rn.f32", "t0", "t1", C, N, ST)
-#define TH_B_ADD_AA(C, N, ST) TH_OP("", "add.rn.f32", "%0", "%0", C, N, ST)
-#define TH_B_MUL_AM(C, N, ST) TH_OP(TH_YM(C), "mul.rn.f32", "%0", "t1", C, N, ST)
-#define TH_B_MUL_AI(C, N, ST) TH_OP(TH_YI(C), "mul.rn.f32", "%0", "t1", C, N, ST)
-#define TH_B_MUL_MM(C, N, ST) TH_OP(TH_XM(C) TH_YM(C), "mul.rn.f32", "t0", "t1", C, N, ST)
-#define TH_B_MUL_MI(C, N, ST) TH_OP(TH_XM(C) TH_YI(C), "mul.rn.f32", "t0", "t1", C, N, ST)
-#define TH_B_MUL_AA(C, N, ST) TH_OP("", "mul.rn.f32", "%0", "%0", C, N, ST)
-#define TH_B_SUB_AM(C, N, ST) TH_OP(TH_YM(C), "sub.rn.f32", "%0", "t1", C, N, ST)
-#define TH_B_RSB_AM(C, N, ST) TH_OP(TH_YM(C), "sub.rn.f32", "t1", "%0", C, N, ST)
-#define TH_B_RSB_AI(C, N, ST) TH_OP(TH_YI(C), "sub.rn.f32", "t1", "%0", C, N, ST)
-#define TH_B_SUB_MM(C, N, ST) TH_OP(TH_XM(C) TH_YM(C), "sub.rn.f32", "t0", "t1", C, N, ST)
-#define TH_B_RSB_MI(C, N, ST) TH_OP(TH_XM(C) TH_YI(C), "sub.rn.f32", "t1", "t0", C, N, ST)
-#define TH_B_LOAD_M(C, N, ST) TH_XM(C) TH_NEXT(N) " mov.f32 %0,t0;\n" ST(C) TH_GO(C)
-#define TH_B_LOAD_I(C, N, ST) TH_XI(C) TH_NEXT(N) " mov.f32 %0,t0;\n" ST(C) TH_GO(C)
+#define TH_B_ADD_AM(C, N, ST, GO) TH_OP(TH_YM, "add.rn.f32", "%0", "t1", C, N, ST, GO)
+#define TH_B_ADD_AI(C, N, ST, GO) TH_OP(TH_YI, "add.rn.f32", "%0", "t1", C, N, ST, GO)
+#define TH_B_ADD_MM(C, N, ST, GO) TH_OP(TH_XMYM, "add.rn.f32", "t0", "t1", C, N, ST, GO)
+#define TH_B_ADD_MI(C, N, ST, GO) TH_OP(TH_XMYI, "add.rn.f32", "t0", "t1", C, N, ST, GO)
+#define TH_B_ADD_AA(C, N, ST, GO) TH_OP(TH_NONE, "add.rn.f32", "%0", "%0", C, N, ST, GO)
+#define TH_B_MUL_AM(C, N, ST, GO) TH_OP(TH_YM, "mul.rn.f32", "%0", "t1", C, N, ST, GO)
+#define TH_B_MUL_AI(C, N, ST, GO) TH_OP(TH_YI, "mul.rn.f32", "%0", "t1", C, N, ST, GO)
+#define TH_B_MUL_MM(C, N, ST, GO) TH_OP(TH_XMYM, "mul.rn.f32", "t0", "t1", C, N, ST, GO)
+#define TH_B_MUL_MI(C, N, ST, GO) TH_OP(TH_XMYI, "mul.rn.f32", "t0", "t1", C, N, ST, GO)
+#define TH_B_MUL_AA(C, N, ST, GO) TH_OP(TH_NONE, "mul.rn.f32", "%0", "%0", C, N, ST, GO)
+#define TH_B_SUB_AM(C, N, ST, GO) TH_OP(TH_YM, "sub.rn.f32", "%0", "t1", C, N, ST, GO)
+#define TH_B_RSB_AM(C, N, ST, GO) TH_OP(TH_YM, "sub.rn.f32", "t1", "%0", C, N, ST, GO)
+#define TH_B_RSB_AI(C, N, ST, GO) TH_OP(TH_YI, "sub.rn.f32", "t1", "%0", C, N, ST, GO)
+#define TH_B_SUB_MM(C, N, ST, GO) TH_OP(TH_XMYM, "sub.rn.f32", "t0", "t1", C, N, ST, GO)
+#define TH_B_RSB_MI(C, N, ST, GO) TH_OP(TH_XMYI, "sub.rn.f32", "t1", "t0", C, N, ST, GO)
+#define TH_B_LOAD_M(C, N, ST, GO) TH_XM(C) TH_NEXT(N) " mov.f32 %0,t0;\n" ST(C) GO(C, N)
+#define TH_B_LOAD_I(C, N, ST, GO) TH_XI(C) TH_NEXT(N) " mov.f32 %0,t0;\n" ST(C) GO(C, N)
 
-#define TH_B_ST(C, N) TH_NEXT(N) TH_STORE(C) TH_GO(C)
-#define TH_B_LDY_M(C, N) " add.u32 ae,%6," C "2;\n ld.shared.f32 %5,[ae];\n" TH_NEXT(N) TH_GO(C)
-#define TH_B_LDY_I(C, N) " mov.b32 %5," C "2;\n" TH_NEXT(N) TH_GO(C)
-#define TH_B_LDY_A(C, N) " mov.f32 %5,%0;\n" TH_NEXT(N) TH_GO(C)
-#define TH_EXIT(C) " mov.u32 %3," C "3;\n mov.u32 %2," C "0;\n add.u32 %1,%1,16;\n bra DONE;\n"
-#define TH_B_SLOW_A(C, N) " mov.f32 %4,%0;\n" TH_EXIT(C)
-#define TH_B_SLOW_M(C, N) " add.u32 ad,%6," C "1;\n ld.shared.f32 %4,[ad];\n" TH_EXIT(C)
-#define TH_B_SLOW_I(C, N) " mov.b32 %4," C "1;\n" TH_EXIT(C)
+#define TH_B_ST(C, N) TH_NEXT(N) TH_STORE(C) TH_GOC(C, N)
+#define TH_B_LDY_M(C, N) " add.u32 ae,%6," #C "2;\n ld.shared.f32 %5,[ae];\n" TH_NEXT(N) TH_GOC(C, N)
+#define TH_B_LDY_I(C, N) " mov.b32 %5," #C "2;\n" TH_NEXT(N) TH_GOC(C, N)
+#define TH_B_LDY_A(C, N) " mov.f32 %5,%0;\n" TH_NEXT(N) TH_GOC(C, N)
+// leaving the block before the next instruction is fetched: pc / nh / parity name it
+#define TH_LEAVE(C, N) " mov.u32 %2," #C "0;\n add.u32 %1,%1,16;\n mov.u32 %7," TH_PARNUM_##N ";\n bra DONE;\n"
+#define TH_B_SLOW_A(C, N) " mov.f32 %4,%0;\n mov.u32 %3," #C "3;\n" TH_LEAVE(C, N)
+#define TH_B_SLOW_M(C, N) " add.u32 ad,%6," #C "1;\n ld.shared.f32 %4,[ad];\n mov.u32 %3," #C "3;\n" TH_LEAVE(C, N)
+#define TH_B_SLOW_I(C, N) " mov.b32 %4," #C "1;\n mov.u32 %3," #C "3;\n" TH_LEAVE(C, N)
 #define TH_B_END(C, N) " mov.u32 %3,0;\n bra DONE;\n"
+// sin / cos: the operand goes to t0, cf = 0 (sin) / 1 (cos: sin(x + pi/2), one quadrant on), then the common body
+#define TH_B_SIN_A(C, N) " mov.f32 t0,%0;\n mov.u32 cf,0;\n bra TRIG_" #C ";\n"
+#define TH_B_SIN_M(C, N) TH_XM(C) " mov.u32 cf,0;\n bra TRIG_" #C ";\n"
+#define TH_B_COS_A(C, N) " mov.f32 t0,%0;\n mov.u32 cf,1;\n bra TRIG_" #C ";\n"
+#define TH_B_COS_M(C, N) TH_XM(C) " mov.u32 cf,1;\n bra TRIG_" #C ";\n"
+// mtgp_sinf / mtgp_cosf (include/mtgp_math.h) for |x| < 1e5, operation for operation: Cody-Waite reduction
+// (mul, add magic, sub, three fma), both kernels, quadrant select, sign.  Any lane outside the fast range
+// (or NaN) sends the whole warp to the C code (Payne-Hanek) with status S_SIN / S_COS.
+#define TH_TRIG_BODY(C, N)                                                                   \
+  "TRIG_" #C ":\n"                                                                           \
+  " abs.f32 t2,t0;\n setp.geu.f32 pq,t2,0f47C35000;\n vote.sync.any.pred pq,pq,0xffffffff;\n" \
+  " @pq bra TRIGSLOW_" #C ";\n"                                                              \
+  TH_NEXT(N)                                                                                 \
+  " mul.rn.f32 t2,t0,0f3F22F983;\n add.rn.f32 t2,t2,0f4B400000;\n sub.rn.f32 t3,t2,0f4B400000;\n" \
+  " neg.f32 t3,t3;\n fma.rn.f32 t4,t3,0f3FC90FDB,t0;\n fma.rn.f32 t4,t3,0fB33BBD2E,t4;\n"    \
+  " fma.rn.f32 t4,t3,0fA6F72CED,t4;\n"                                                       \
+  " mov.b32 qi,t2;\n add.u32 qi,qi,cf;\n"                                                    \
+  " mul.rn.f32 t5,t4,t4;\n"                                                                  \
+  " fma.rn.f32 t6,t5,0f3636C3EF,0fB950097E;\n fma.rn.f32 t6,t6,t5,0f3C088887;\n"             \
+  " fma.rn.f32 t6,t6,t5,0fBE2AAAAB;\n mul.rn.f32 t3,t4,t5;\n fma.rn.f32 t6,t3,t6,t4;\n"      \
+  " fma.rn.f32 t7,t5,0fB4928012,0f37D00AA9;\n fma.rn.f32 t7,t7,t5,0fBAB60B5F;\n"             \
+  " fma.rn.f32 t7,t7,t5,0f3D2AAAAB;\n mul.rn.f32 t3,t5,t5;\n fma.rn.f32 t2,t5,0fBF000000,0f3F800000;\n" \
+  " fma.rn.f32 t7,t3,t7,t2;\n"                                                               \
+  " and.b32 ad,qi,1;\n setp.ne.u32 pq,ad,0;\n selp.f32 t6,t7,t6,pq;\n"                       \
+  " shl.b32 ad,qi,30;\n and.b32 ad,ad,0x80000000;\n mov.b32 ae,t6;\n xor.b32 ae,ae,ad;\n mov.b32 %0,ae;\n" \
+  TH_GOC(C, N)                                                                               \
+  "TRIGSLOW_" #C ":\n"                                                                       \
+  " mov.f32 %4,t0;\n add.u32 %3,cf,1;\n" TH_LEAVE(C, N)
 
-#define TH_LABELS_ARITH(n) "H_" #n "_a, H_" #n "_b, H_" #n "_ST_a, H_" #n "_ST_b, "
-#define TH_LABELS_OTHER(n) "H_" #n "_a, H_" #n "_b, "
-#define TH_CODE_ARITH(n)                                                                  \
-  "H_" #n "_a:\n" TH_B_##n("a", "b", TH_NOSTORE) "H_" #n "_b:\n" TH_B_##n("b", "a", TH_NOSTORE) \
-  "H_" #n "_ST_a:\n" TH_B_##n("a", "b", TH_STORE) "H_" #n "_ST_b:\n" TH_B_##n("b", "a", TH_STORE)
-#define TH_CODE_OTHER(n) "H_" #n "_a:\n" TH_B_##n("a", "b") "H_" #n "_b:\n" TH_B_##n("b", "a")
+// label lists: the full table of one register set, and the hot tables (order = mtgp_th_hot_index)
+#define TH_LABELS_ARITH_a(n, g0, g1) "H_" #n "_a, H_" #n "_ST_a, "
+#define TH_LABELS_ARITH_b(n, g0, g1) "H_" #n "_b, H_" #n "_ST_b, "
+#define TH_LABELS_OTHER_a(n) "H_" #n "_a, "
+#define TH_LABELS_OTHER_b(n) "H_" #n "_b, "
+#if MTGP_TH_HOT_LEVEL >= 2
+#define TH_HOT_LABELS(p)                                                                                       \
+  "H_ADD_AM_" #p ", H_ADD_AM_ST_" #p ", H_ADD_AI_" #p ", H_ADD_MI_" #p ", H_MUL_AM_" #p ", H_MUL_AM_ST_" #p    \
+  ", H_MUL_AI_" #p ", H_MUL_MI_" #p ", H_ADD_AI_ST_" #p ", H_ADD_MM_" #p ", H_MUL_AI_ST_" #p ", H_MUL_MM_" #p ", "
+#else
+#define TH_HOT_LABELS(p)                                                                                       \
+  "H_ADD_AM_" #p ", H_ADD_AM_ST_" #p ", H_ADD_AI_" #p ", H_ADD_MI_" #p ", H_MUL_AM_" #p ", H_MUL_AM_ST_" #p    \
+  ", H_MUL_AI_" #p ", H_MUL_MI_" #p ", "
+#endif
+#define TH_CODE_ARITH(n, g0, g1)                                                                           \
+  "H_" #n "_a:\n" TH_B_##n(a, b, TH_NOSTORE, g0) "H_" #n "_b:\n" TH_B_##n(b, a, TH_NOSTORE, g0)            \
+  "H_" #n "_ST_a:\n" TH_B_##n(a, b, TH_STORE, g1) "H_" #n "_ST_b:\n" TH_B_##n(b, a, TH_STORE, g1)
+#define TH_CODE_OTHER(n) "H_" #n "_a:\n" TH_B_##n(a, b) "H_" #n "_b:\n" TH_B_##n(b, a)
 
-// Runs from the instruction at pc (whose handler index is nh) until END (returns 0) or a slow operator
-// (returns its opcode with xv / yv set; pc / nh then name the instruction after it).
-__device__ __forceinline__ uint32_t mtgp_th_block(float& acc, uint32_t& pc, uint32_t& nh, float& xv, float& yv,
-                                                  uint32_t lane) {
+// Runs from the instruction at pc (handler nh, register set `parity`) until END (returns 0) or a slow
+// operator (returns its opcode with xv / yv set; pc / nh / parity then name the instruction after it).
+__device__ __forceinline__ uint32_t mtgp_th_block(float& acc, uint32_t& pc, uint32_t& nh, uint32_t& parity, float& xv,
+                                                  float& yv, uint32_t lane) {
   uint32_t status;
   asm volatile(
       "{\n"
       " .reg .u32 a0,a1,a2,a3,b0,b1,b2,b3,ad,ae;\n"
-      " .reg .f32 t0,t1;\n"
-      " .reg .pred pb;\n"
-      " and.b32 ad,%2,1;\n setp.ne.u32 pb,ad,0;\n"  // the instruction at pc goes to the register set of its position parity
-      " @!pb ld.shared.v4.u32 {a0,a1,a2,a3},[%1];\n"
-      " @pb ld.shared.v4.u32 {b0,b1,b2,b3},[%1];\n"
-      "TBL: .branchtargets " MTGP_TH_ARITH(TH_LABELS_ARITH) MTGP_TH_OTHER(TH_LABELS_OTHER) "DONE;\n"
-      " brx.idx %2, TBL;\n"
+      " .reg .f32 t0,t1,t2,t3,t4,t5,t6,t7;\n"
+      " .reg .u32 qi,cf;\n"
+      " .reg .pred pq;\n"
+      "TBLa: .branchtargets " MTGP_TH_ARITH(TH_LABELS_ARITH_a) MTGP_TH_OTHER(TH_LABELS_OTHER_a) "DONE;\n"
+      "TBLb: .branchtargets " MTGP_TH_ARITH(TH_LABELS_ARITH_b) MTGP_TH_OTHER(TH_LABELS_OTHER_b) "DONE;\n"
+#if MTGP_TH_HOT_LEVEL >= 1
+      "HOTa: .branchtargets " TH_HOT_LABELS(a) "DISP_b;\n"  // reached from set-b handlers; their cold exit is DISP_b
+      "HOTb: .branchtargets " TH_HOT_LABELS(b) "DISP_a;\n"
+#endif
+      " setp.ne.u32 pq,%7,0;\n"
+      " @pq bra ENTRY_b;\n"
+      " ld.shared.v4.u32 {a0,a1,a2,a3},[%1];\n"
+      " brx.idx %2, TBLa;\n"
+      "ENTRY_b:\n"
+      " ld.shared.v4.u32 {b0,b1,b2,b3},[%1];\n"
+      " brx.idx %2, TBLb;\n"
+      "DISP_a:\n brx.idx a0, TBLb;\n"
+      "DISP_b:\n brx.idx b0, TBLa;\n"
       MTGP_TH_ARITH(TH_CODE_ARITH)
       MTGP_TH_OTHER(TH_CODE_OTHER)
+      TH_TRIG_BODY(a, b) TH_TRIG_BODY(b, a)
       "DONE:\n"
       "}\n"
-      : "+f"(acc), "+r"(pc), "+r"(nh), "=r"(status), "=f"(xv), "+f"(yv)
-      : "r"(lane)
+      : "+f"(acc), "+r"(pc), "+r"(nh), "=r"(status), "=f"(xv), "+f"(yv), "+r"(lane), "+r"(parity)
+      :
       : "memory");
   return status;
 }
@@ -233,12 +363,13 @@ __device__ __forceinline__ uint32_t mtgp_th_block(float& acc, uint32_t& pc, uint
 #endif
 static __host__ __device__ MTGP_TH_INLINE float mtgp_run_threaded(mtgp_saddr entry, mtgp_saddr lane) {
 #if defined(__CUDA_ARCH__)
-  uint32_t nh, pc = entry + 16u;
+  uint32_t nh, pc = entry + 16u, parity = 0u;  // instruction 0 goes to register set a
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(nh) : "r"(entry));
   float acc = 0.0f, xv = 0.0f, yv = 0.0f;
   for (;;) {
-    const uint32_t sop = mtgp_th_block(acc, pc, nh, xv, yv, lane);
+    uint32_t sop = mtgp_th_block(acc, pc, nh, parity, xv, yv, lane);
     if (sop == S_END) return acc;
+    asm volatile("" : "+r"(sop));  // (keeps the END test first: otherwise it is folded into the operator switch)
     acc = mtgp_th_slow_op(sop, xv, yv);
   }
 #else
@@ -251,9 +382,12 @@ static __host__ __device__ MTGP_TH_INLINE float mtgp_run_threaded(mtgp_saddr ent
   uint32_t h = prog[0].next;
   for (int j = 1;; j++) {
     const mtgp_tinstr w = prog[j];
-    if (((uint32_t)(j - 1) & 1u) != (h & 1u)) return mtgp_nanf();  // parity of the link is part of the format
-    const uint32_t hh = h >> 1;
+    const uint32_t hh = h;
     h = w.next;
+    {  // the hot index a hot instruction carries must name its successor
+      const int hw = mtgp_th_hot_word(hh);
+      if ((hw == 1 && w.a != mtgp_th_hot_index(h)) || (hw == 3 && w.c != mtgp_th_hot_index(h))) return mtgp_nanf();
+    }
     bool st = false;
     switch (hh) {
 #define CASE(n, EXPR) case TH_##n: acc = (EXPR); break; case TH_##n##_ST: acc = (EXPR); st = true; break;
@@ -269,6 +403,10 @@ static __host__ __device__ MTGP_TH_INLINE float mtgp_run_threaded(mtgp_saddr ent
       case TH_LDY_M: yv = M(w.b); break;
       case TH_LDY_I: yv = I(w.b); break;
       case TH_LDY_A: yv = acc; break;
+      case TH_SIN_A: acc = mtgp_sinf(acc); break;
+      case TH_SIN_M: acc = mtgp_sinf(M(w.a)); break;
+      case TH_COS_A: acc = mtgp_cosf(acc); break;
+      case TH_COS_M: acc = mtgp_cosf(M(w.a)); break;
       case TH_SLOW_A: acc = mtgp_th_slow_op(w.c, acc, yv); break;
       case TH_SLOW_M: acc = mtgp_th_slow_op(w.c, M(w.a), yv); break;
       case TH_SLOW_I: acc = mtgp_th_slow_op(w.c, I(w.a), yv); break;

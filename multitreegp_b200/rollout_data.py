@@ -27,6 +27,7 @@ class RolloutData:
     targets: np.ndarray | None = None   # [B, n_targets]
     obs_keys: np.ndarray | None = None  # [B, 2] uint32
     params: np.ndarray | None = None    # [B, n_params]
+    noise_inline: bool = False          # generate the observation noise in-kernel (same bits as the table; tests)
     ys_true: np.ndarray | None = None   # [B, K, D] (SR)
     n_obs: int = 0
     state_size: int = 0
@@ -95,6 +96,8 @@ class RolloutData:
         d.targets = ptr(self.targets if self.targets.size else None)
         d.obs_keys = ptr(self.obs_keys)
         d.params = ptr(self.params)
+        d.params_host = abi.np_ptr(self.params)  # lets the library see trajectory-uniform parameters
+        d.flags = abi.DESC_NOISE_INLINE if self.noise_inline else 0
         d.ys_true = ptr(self.ys_true)
         return d
 

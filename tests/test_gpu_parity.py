@@ -170,15 +170,15 @@ def test_populations_larger_than_the_resident_warps(engine, oracle):
     assert int(gpu["steps"][0]) == ref["steps"]
 
 
-def test_inline_noise_generator_matches_the_table(engine, oracle, monkeypatch):
+def test_inline_noise_generator_matches_the_table(engine, oracle):
     """The rollout kernel normally reads the observation noise from a table computed once per
     evaluation; when the table would be too large it generates the noise in-kernel.  Same bits."""
     rng = np.random.default_rng(4)
     lib, pop, data = util.control_case("acrobot", abi.EVAL_DYNAMIC, rng, P=64, B=16, T_end=6.0, obs_noise=0.1)
     ref = oracle.rollout_population(pop, lib.table(), data)
     a = _gpu_rollout(engine, lib, pop, data, trajectories=True)
-    monkeypatch.setenv("MTGP_NOISE_INLINE", "1")
-    b = _gpu_rollout(engine, lib, pop, data, trajectories=True)
+    import dataclasses
+    b = _gpu_rollout(engine, lib, pop, dataclasses.replace(data, noise_inline=True), trajectories=True)  # MTGP_DESC_NOISE_INLINE
     for g in (a, b):
         assert util.same_or_both_nan(g["traj_fitness"], ref["traj_fitness"]).all()
         assert util.same_or_both_nan(g["ys"], a["ys"]).all()

@@ -49,3 +49,12 @@ ts = sum(smp_line.values())
 print("top lines:")
 for loc, c in by_line.most_common(45):
     print(f"  {loc[0]:<22}:{loc[1]:<5} {c / unit:7.1f}/step {100 * c / tot:5.1f}%  samples {100 * smp_line[loc] / max(ts, 1):5.1f}%")
+if len(sys.argv) > 5 and sys.argv[5] == "all":  # every line with >= 0.3 instructions per step, in source order
+    print("all lines:")
+    for loc in sorted(by_line):
+        if by_line[loc] / unit >= 0.3:
+            print(f"  {loc[0]:<22}:{loc[1]:<5} {by_line[loc] / unit:7.1f}/step  samples {100 * smp_line[loc] / max(ts, 1):5.1f}%")
+if len(sys.argv) > 5 and sys.argv[5] == "sass":  # the executed SASS in address order with per-step counts
+    for (off, loc, text), (s, c, k) in zip(lines[:n], ins[:n]):
+        if c / unit >= 0.05:
+            print(f"{off:6x} {c / unit:6.2f} {100 * k / max(ts, 1):5.2f}%  {loc[0]}:{loc[1]:<4} {text}")
