@@ -25,6 +25,12 @@ NVCC_FLAGS = [
 ]
 
 
+# The rollout kernels' device code stays uncompressed in the fat binary: sass_patch.py (jump-table merge of the
+# threaded-code interpreter) patches the embedded cubin in place.
+PER_SOURCE_FLAGS = {"mtgp_rollout.cu": ["--no-compress"], "mtgp_rollout_rk.cu": ["--no-compress"]}
+PATCHED_CUBINS = ("mtgp_rollout",)
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
         if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
@@ -48,7 +54,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(_HERE, "build", src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + PER_SOURCE_FLAGS.get(src, []) + ["-c", s, "-o", o]
             jobs.append(cmd)
 
     def run(cmd):
@@ -67,6 +73,10 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
+        from .sass_patch import patch_library
+        st = patch_library(LIB, PATCHED_CUBINS, verbose=verbose)
+        if not st.get("patched"):
+            raise RuntimeError("sass_patch: no jump table was merged -- the interpreter's dispatch sites were not found")
     build_ffi_shim(verbose)
     return LIB
 

@@ -469,7 +469,7 @@ struct Env {
       const float pi = 3.14159274f, two_pi = 6.28318548f;
       const float w0 = y[0] + pi, w1 = (n_obs > 1) ? y[1] + pi : 0.0f;
       // warp-uniform choice: every lane's angles within one turn (the usual case) -> two adds each
-      if (__all_sync(__activemask(), fabsf(w0) < two_pi && fabsf(w1) < two_pi)) {
+      if (__all_sync(0xFFFFFFFFu, fabsf(w0) < two_pi && fabsf(w1) < two_pi)) {  // (every caller is warp-convergent)
         y[0] = wrap_in_range(w0);
         if (n_obs > 1) y[1] = wrap_in_range(w1);
       } else {
@@ -493,7 +493,7 @@ struct Env {
       // the five trigonometric values: when every lane's angles are small enough that all four arguments are
       // inside the contract's fast range (|theta| < 4e4 => |theta1 + theta2 - pi/2| < 1e5), without range branches
       float s2, c2, c12, s1, c1h;
-      if (__all_sync(__activemask(), fabsf(theta1) < 40000.0f && fabsf(theta2) < 40000.0f)) {
+      if (__all_sync(0xFFFFFFFFu, fabsf(theta1) < 40000.0f && fabsf(theta2) < 40000.0f)) {
         sincos_checked(theta2, s2, c2);
         c12 = cos_checked((theta1 + theta2) - half_pi);
         s1 = sin_checked(theta1);

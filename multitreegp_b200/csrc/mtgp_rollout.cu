@@ -125,7 +125,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
     // ---- stage this individual's programs (cp.async.bulk -> shared, mbarrier) ----
     warp_stage_programs(P, ind, lane, bar, bar_phase, wa);
     float* lb = wa.vf + lane;  // lane base of the value file (R = 1)
-    const mtgp_saddr lbytes = mtgp_saddr_of(lb);
+    mtgp_saddr lbytes = mtgp_saddr_of(lb);
+    // opaque to the compiler: it would otherwise re-derive this address (special registers, four uniform
+    // operations) at every use in the step loop instead of keeping it in a register
+    asm volatile("mov.u32 %0, %0;" : "+r"(lbytes));
     bool readout_reads_y = false;
     if (KIND == MTGP_EVAL_DYNAMIC) {
       // does the readout read an observation or the control slot?  (conservative: unused operand fields count)
@@ -262,24 +265,27 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
                 env.template f_obs<NOISE, false>(tprev, x, y, n_obs, P.obs_noise, P.partitionable, nzv);
               else
                 env.template f_obs<NOISE, true>(tprev, x, y, n_obs, P.obs_noise, P.partitionable, nzv);
+              // the next step's row, a whole step ahead of its use
+              if (NOISE == 1 && steps + 1 < P.cap_steps)
+                nz_next = __ldg(reinterpret_cast<const float4*>(nz_base + (size_t)(steps + 1) * nzs));
               if (KIND == MTGP_EVAL_STATIC) {
 #pragma unroll
                 for (int i = 0; i < D; i++)
-                  if (i < n_obs) lb[i * 32] = y[i];
+                  if (i < n_obs) mtgp_sts_f32(lbytes + 128u * (uint32_t)(i), y[i]);
               } else if (readout_sees_y) {
 #pragma unroll
                 for (int i = 0; i < D; i++)
-                  if (i < n_obs) lb[i * 32] = 0.0f;
-                lb[slot_u * 32] = 0.0f;
+                  if (i < n_obs) mtgp_sts_f32(lbytes + 128u * (uint32_t)(i), 0.0f);
+                mtgp_sts_f32(lbytes + 128u * (uint32_t)(slot_u), 0.0f);
               }
               if (KIND == MTGP_EVAL_DYNAMIC && !readout_sees_y) {
                 // the whole chain in one call: the observations are already in place (the readout does not
                 // read them), the readout's ST puts u in its slot before the state equations run
 #pragma unroll
                 for (int i = 0; i < D; i++)
-                  if (i < n_obs) lb[i * 32] = y[i];
+                  if (i < n_obs) mtgp_sts_f32(lbytes + 128u * (uint32_t)(i), y[i]);
                 mtgp_run_threaded(prog_step, lbytes);
-                u = lb[slot_u * 32];
+                u = mtgp_lds_f32(lbytes + 128u * (uint32_t)(slot_u));
               } else {
                 u = mtgp_run_threaded(prog_step, lbytes);  // feedforward :107 / dynamic readout :113
               }
@@ -290,8 +296,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
               if (KIND == MTGP_EVAL_DYNAMIC && readout_sees_y) {
 #pragma unroll
                 for (int i = 0; i < D; i++)
-                  if (i < n_obs) lb[i * 32] = y[i];
-                lb[slot_u * 32] = u;
+                  if (i < n_obs) mtgp_sts_f32(lbytes + 128u * (uint32_t)(i), y[i]);
+                mtgp_sts_f32(lbytes + 128u * (uint32_t)(slot_u), u);
                 mtgp_run_threaded(prog_step2, lbytes);
               }
             } else {
@@ -344,8 +350,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
               if (KIND == MTGP_EVAL_STATIC || readout_sees_y) {
 #pragma unroll
                 for (int i = 0; i < D; i++)
-                  if (i < n_obs) lb[i * 32] = ys[i];
-                if (KIND == MTGP_EVAL_DYNAMIC) lb[slot_u * 32] = 0.0f;  // zeros(control_size) (dynamic_evaluate.py:101)
+                  if (i < n_obs) mtgp_sts_f32(lbytes + 128u * (uint32_t)(i), ys[i]);
+                if (KIND == MTGP_EVAL_DYNAMIC) mtgp_sts_f32(lbytes + 128u * (uint32_t)(slot_u), 0.0f);  // zeros(control_size) (dynamic_evaluate.py:101)
               }
               const float uk = mtgp_run_threaded(prog_save, lbytes);
               const float qk = (ENV == MTGP_ENV_ACROBOT) ? tk / dts : 0.0f;
@@ -415,7 +421,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
               tnext = new_tnext;
             }
             steps++;
-            if (NOISE == 1 && steps < P.cap_steps) nz_next = __ldg(reinterpret_cast<const float4*>(nz_base + (size_t)steps * nzs));
           }
         }
         if (pass == 0 && lane_valid) my_steps += lane_steps;

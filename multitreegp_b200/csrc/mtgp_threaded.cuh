@@ -12,7 +12,8 @@
 //     FADD  acc = acc + t          BRX
 // An instruction carries the handler index of its SUCCESSOR (.x), so the jump-table load does not
 // wait for the instruction fetch; the fetch alternates between two register sets (a*, b*), which
-// is why every handler exists twice (position parity) -- no register copies between handlers.
+// is why every handler exists twice -- no register copies between handlers: a handler of set a
+// loads the next instruction into set b and jumps to a handler of set b.
 //
 // The interpreter is one inline-PTX block (CUDA C has no computed goto; `brx.idx` is the PTX
 // form).  Everything that is not + - * load store leaves the block with a status code, is
@@ -20,7 +21,7 @@
 // oracle) and re-enters.  All arithmetic is `.rn` (never contracted, no FTZ): the results are the
 // bits of the reference's float32 operators (genetic_programming.py:24-31, 356-376).
 //
-// Instruction = uint4: .x = 2 * handler(next instruction) + parity(next position)
+// Instruction = uint4: .x = handler of the NEXT instruction (mtgp_th)
 //                      .y = A: x operand -- byte offset into the lane's value file (slot * 128) or immediate bits
 //                      .z = B: y operand -- byte offset or immediate bits
 //                      .w = C: store byte offset (…_ST handlers, ST) or slow opcode (SLOW_*)
@@ -29,20 +30,17 @@
 
 #include "mtgp_program.cuh"
 
-// handler lists.  Arithmetic / load forms exist with and without a fused store: X(name, dispatch of the plain
-// form, dispatch of the ..._ST form) -- the dispatch macros (TH_GO*) are defined with the PTX block below.
+// handler lists: arithmetic / load forms exist with and without a fused store (..._ST)
 #define MTGP_TH_ARITH(X) \
-  X(ADD_AM, TH_GO_L1A, TH_GO_L1A) X(ADD_AI, TH_GO_L1A, TH_GO_L2A) X(ADD_MM, TH_GO_L2C, TH_GOC) \
-  X(ADD_MI, TH_GO_L1C, TH_GOC) X(ADD_AA, TH_GOC, TH_GOC) \
-  X(MUL_AM, TH_GO_L1A, TH_GO_L1A) X(MUL_AI, TH_GO_L1A, TH_GO_L2A) X(MUL_MM, TH_GO_L2C, TH_GOC) \
-  X(MUL_MI, TH_GO_L1C, TH_GOC) X(MUL_AA, TH_GOC, TH_GOC) \
-  X(SUB_AM, TH_GOC, TH_GOC) X(RSB_AM, TH_GOC, TH_GOC) X(RSB_AI, TH_GOC, TH_GOC) X(SUB_MM, TH_GOC, TH_GOC) \
-  X(RSB_MI, TH_GOC, TH_GOC) X(LOAD_M, TH_GOC, TH_GOC) X(LOAD_I, TH_GOC, TH_GOC)
+  X(ADD_AM) X(ADD_AI) X(ADD_MM) X(ADD_MI) X(ADD_AA) \
+  X(MUL_AM) X(MUL_AI) X(MUL_MM) X(MUL_MI) X(MUL_AA) \
+  X(SUB_AM) X(RSB_AM) X(RSB_AI) X(SUB_MM) X(RSB_MI) \
+  X(LOAD_M) X(LOAD_I)
 #define MTGP_TH_OTHER(X) \
   X(ST) X(LDY_M) X(LDY_I) X(LDY_A) X(SLOW_A) X(SLOW_M) X(SLOW_I) X(SIN_A) X(SIN_M) X(COS_A) X(COS_M) X(END)
 
 enum mtgp_th : uint32_t {
-#define X(n, g0, g1) TH_##n, TH_##n##_ST,
+#define X(n) TH_##n, TH_##n##_ST,
   MTGP_TH_ARITH(X)
 #undef X
 #define X(n) TH_##n,
@@ -134,56 +132,22 @@ __host__ __device__ __forceinline__ int mtgp_th_expand(uint2 c, mtgp_tinstr* out
   return n;
 }
 
-// Two-level dispatch.  ptxas gives every brx.idx its own jump table in the constant bank; with one table per
-// handler (fully threaded code) the tables (85 x 85 entries) thrash the indexed-constant cache and every
-// dispatch waits for a miss (measured: 25 % issue utilisation).  So: the HOT handlers -- the + and * forms that
-// make up most of a program -- end with their own brx.idx over a SHORT table (hot targets + one "cold" entry),
-// indexed by the hot index of the successor, which the instruction carries in the operand word its form does
-// not use; everything else goes through one shared brx.idx per register set over the full table.
-#ifndef MTGP_TH_HOT_LEVEL
-#define MTGP_TH_HOT_LEVEL 2
-#endif
-#if MTGP_TH_HOT_LEVEL >= 2
-#define MTGP_TH_NHOT 12
-#elif MTGP_TH_HOT_LEVEL == 1
-#define MTGP_TH_NHOT 8
-#else
-#define MTGP_TH_NHOT 0
-#endif
-// hot index of a handler (MTGP_TH_NHOT = cold); the order is the order of the HOT label lists below
-__host__ __device__ __forceinline__ uint32_t mtgp_th_hot_index(uint32_t h) {
-#if MTGP_TH_HOT_LEVEL >= 1
-  switch (h) {
-    case TH_ADD_AM: return 0; case TH_ADD_AM_ST: return 1; case TH_ADD_AI: return 2; case TH_ADD_MI: return 3;
-    case TH_MUL_AM: return 4; case TH_MUL_AM_ST: return 5; case TH_MUL_AI: return 6; case TH_MUL_MI: return 7;
-#if MTGP_TH_HOT_LEVEL >= 2
-    case TH_ADD_AI_ST: return 8; case TH_ADD_MM: return 9; case TH_MUL_AI_ST: return 10; case TH_MUL_MM: return 11;
-#endif
-    default: break;
-  }
-#endif
-  return MTGP_TH_NHOT;
-}
-// which operand word of a hot handler's instruction carries the successor's hot index: 1 = .a (forms whose x
-// is the accumulator), 3 = .c (forms without a store), 0 = the handler is not hot
-__host__ __device__ __forceinline__ int mtgp_th_hot_word(uint32_t h) {
-  if (mtgp_th_hot_index(h) == MTGP_TH_NHOT) return 0;
-  return (h == TH_ADD_MI || h == TH_MUL_MI || h == TH_ADD_MM || h == TH_MUL_MM) ? 3 : 1;
-}
+// Dispatch.  Every handler ends with its own `brx.idx <successor's handler>` (threaded code: one taken branch
+// per node, the jump-table load issued at the top of the handler, overlapping the operand load).  ptxas gives
+// every brx.idx its OWN copy of the jump table in constant bank 2 -- 92 copies of 2 x 47 entries = 17 KB, which
+// thrash the indexed-constant cache so badly that every dispatch waits for a miss (measured: issue utilisation
+// 25 %, 287 ms on the C5 workload).  The copies are byte-identical (the table holds function-relative
+// offsets), so the build redirects every jump-table LDC to the first copy of its table
+// (multitreegp_b200/sass_patch.py, verified by re-disassembly): two 188-byte tables stay resident.
+// MTGP_TH_CENTRAL selects the fallback that needs no patch: one shared brx.idx per register set, reached
+// by a `bra` from every handler (two taken branches per node, table load after the operand wait).
+// (Also measured, slower than both: own short tables for the 8 / 12 most frequent handlers.)
 
 // header + n instructions (prog[0] = header, prog[1..n] = instructions with their OWN handler in .next):
-// rewrite .next to the successor's handler, and give hot instructions their successor's hot index.
+// rewrite .next to the successor's handler.
 __host__ __device__ __forceinline__ void mtgp_th_link(mtgp_tinstr* prog, int n) {
-  prog[0].next = TH_COUNT; prog[0].a = 0; prog[0].b = 0; prog[0].c = 0;
-  uint32_t own = TH_COUNT;  // the header is not an instruction
-  for (int j = 0; j < n; j++) {
-    const uint32_t nxt = prog[j + 1].next;
-    const int hw = (own < TH_COUNT) ? mtgp_th_hot_word(own) : 0;
-    prog[j].next = nxt;
-    if (hw == 1) prog[j].a = mtgp_th_hot_index(nxt);
-    if (hw == 3) prog[j].c = mtgp_th_hot_index(nxt);
-    own = nxt;
-  }
+  prog[0].a = 0; prog[0].b = 0; prog[0].c = 0;
+  for (int j = 0; j < n; j++) prog[j].next = prog[j + 1].next;
   prog[n].next = TH_END;
 }
 
@@ -215,22 +179,10 @@ static __host__ __device__ __forceinline__ float mtgp_th_slow_op(uint32_t sop, f
 #define TH_PARNUM_a "0"
 #define TH_PARNUM_b "1"
 #define TH_NEXT(N) " add.u32 %1,%1,16;\n ld.shared.v4.u32 {" #N "0," #N "1," #N "2," #N "3},[%1];\n"
-#define TH_GOC(C, N) " bra DISP_" #C ";\n"                       // shared dispatch of this register set
-#define TH_GOH1(C, N) " brx.idx " #C "1, HOT" #N ";\n"           // own dispatch, hot index in word .a
-#define TH_GOH3(C, N) " brx.idx " #C "3, HOT" #N ";\n"           // own dispatch, hot index in word .c
-#if MTGP_TH_HOT_LEVEL >= 1
-#define TH_GO_L1A TH_GOH1
-#define TH_GO_L1C TH_GOH3
+#ifdef MTGP_TH_CENTRAL
+#define TH_GO(C, N) " bra DISP_" #C ";\n"               // shared dispatch of this register set
 #else
-#define TH_GO_L1A TH_GOC
-#define TH_GO_L1C TH_GOC
-#endif
-#if MTGP_TH_HOT_LEVEL >= 2
-#define TH_GO_L2A TH_GOH1
-#define TH_GO_L2C TH_GOH3
-#else
-#define TH_GO_L2A TH_GOC
-#define TH_GO_L2C TH_GOC
+#define TH_GO(C, N) " brx.idx " #C "0, TBL" #N ";\n"    // own dispatch (its jump-table copy is merged by sass_patch.py)
 #endif
 #define TH_XM(C) " add.u32 ad,%6," #C "1;\n ld.shared.f32 t0,[ad];\n"
 #define TH_YM(C) " add.u32 ae,%6," #C "2;\n ld.shared.f32 t1,[ae];\n"
@@ -241,30 +193,30 @@ static __host__ __device__ __forceinline__ float mtgp_th_slow_op(uint32_t sop, f
 #define TH_XMYI(C) TH_XM(C) TH_YI(C)
 #define TH_STORE(C) " add.u32 ad,%6," #C "3;\n st.shared.f32 [ad],%0;\n"
 #define TH_NOSTORE(C) ""
-#define TH_OP(PRE, OP, X, Y, C, N, ST, GO) PRE(C) TH_NEXT(N) " " OP " %0," X "," Y ";\n" ST(C) GO(C, N)
+#define TH_OP(PRE, OP, X, Y, C, N, ST) PRE(C) TH_NEXT(N) " " OP " %0," X "," Y ";\n" ST(C) TH_GO(C, N)
 
-#define TH_B_ADD_AM(C, N, ST, GO) TH_OP(TH_YM, "add.rn.f32", "%0", "t1", C, N, ST, GO)
-#define TH_B_ADD_AI(C, N, ST, GO) TH_OP(TH_YI, "add.rn.f32", "%0", "t1", C, N, ST, GO)
-#define TH_B_ADD_MM(C, N, ST, GO) TH_OP(TH_XMYM, "add.rn.f32", "t0", "t1", C, N, ST, GO)
-#define TH_B_ADD_MI(C, N, ST, GO) TH_OP(TH_XMYI, "add.rn.f32", "t0", "t1", C, N, ST, GO)
-#define TH_B_ADD_AA(C, N, ST, GO) TH_OP(TH_NONE, "add.rn.f32", "%0", "%0", C, N, ST, GO)
-#define TH_B_MUL_AM(C, N, ST, GO) TH_OP(TH_YM, "mul.rn.f32", "%0", "t1", C, N, ST, GO)
-#define TH_B_MUL_AI(C, N, ST, GO) TH_OP(TH_YI, "mul.rn.f32", "%0", "t1", C, N, ST, GO)
-#define TH_B_MUL_MM(C, N, ST, GO) TH_OP(TH_XMYM, "mul.rn.f32", "t0", "t1", C, N, ST, GO)
-#define TH_B_MUL_MI(C, N, ST, GO) TH_OP(TH_XMYI, "mul.rn.f32", "t0", "t1", C, N, ST, GO)
-#define TH_B_MUL_AA(C, N, ST, GO) TH_OP(TH_NONE, "mul.rn.f32", "%0", "%0", C, N, ST, GO)
-#define TH_B_SUB_AM(C, N, ST, GO) TH_OP(TH_YM, "sub.rn.f32", "%0", "t1", C, N, ST, GO)
-#define TH_B_RSB_AM(C, N, ST, GO) TH_OP(TH_YM, "sub.rn.f32", "t1", "%0", C, N, ST, GO)
-#define TH_B_RSB_AI(C, N, ST, GO) TH_OP(TH_YI, "sub.rn.f32", "t1", "%0", C, N, ST, GO)
-#define TH_B_SUB_MM(C, N, ST, GO) TH_OP(TH_XMYM, "sub.rn.f32", "t0", "t1", C, N, ST, GO)
-#define TH_B_RSB_MI(C, N, ST, GO) TH_OP(TH_XMYI, "sub.rn.f32", "t1", "t0", C, N, ST, GO)
-#define TH_B_LOAD_M(C, N, ST, GO) TH_XM(C) TH_NEXT(N) " mov.f32 %0,t0;\n" ST(C) GO(C, N)
-#define TH_B_LOAD_I(C, N, ST, GO) TH_XI(C) TH_NEXT(N) " mov.f32 %0,t0;\n" ST(C) GO(C, N)
+#define TH_B_ADD_AM(C, N, ST) TH_OP(TH_YM, "add.rn.f32", "%0", "t1", C, N, ST)
+#define TH_B_ADD_AI(C, N, ST) TH_OP(TH_YI, "add.rn.f32", "%0", "t1", C, N, ST)
+#define TH_B_ADD_MM(C, N, ST) TH_OP(TH_XMYM, "add.rn.f32", "t0", "t1", C, N, ST)
+#define TH_B_ADD_MI(C, N, ST) TH_OP(TH_XMYI, "add.rn.f32", "t0", "t1", C, N, ST)
+#define TH_B_ADD_AA(C, N, ST) TH_OP(TH_NONE, "add.rn.f32", "%0", "%0", C, N, ST)
+#define TH_B_MUL_AM(C, N, ST) TH_OP(TH_YM, "mul.rn.f32", "%0", "t1", C, N, ST)
+#define TH_B_MUL_AI(C, N, ST) TH_OP(TH_YI, "mul.rn.f32", "%0", "t1", C, N, ST)
+#define TH_B_MUL_MM(C, N, ST) TH_OP(TH_XMYM, "mul.rn.f32", "t0", "t1", C, N, ST)
+#define TH_B_MUL_MI(C, N, ST) TH_OP(TH_XMYI, "mul.rn.f32", "t0", "t1", C, N, ST)
+#define TH_B_MUL_AA(C, N, ST) TH_OP(TH_NONE, "mul.rn.f32", "%0", "%0", C, N, ST)
+#define TH_B_SUB_AM(C, N, ST) TH_OP(TH_YM, "sub.rn.f32", "%0", "t1", C, N, ST)
+#define TH_B_RSB_AM(C, N, ST) TH_OP(TH_YM, "sub.rn.f32", "t1", "%0", C, N, ST)
+#define TH_B_RSB_AI(C, N, ST) TH_OP(TH_YI, "sub.rn.f32", "t1", "%0", C, N, ST)
+#define TH_B_SUB_MM(C, N, ST) TH_OP(TH_XMYM, "sub.rn.f32", "t0", "t1", C, N, ST)
+#define TH_B_RSB_MI(C, N, ST) TH_OP(TH_XMYI, "sub.rn.f32", "t1", "t0", C, N, ST)
+#define TH_B_LOAD_M(C, N, ST) TH_XM(C) TH_NEXT(N) " mov.f32 %0,t0;\n" ST(C) TH_GO(C, N)
+#define TH_B_LOAD_I(C, N, ST) TH_XI(C) TH_NEXT(N) " mov.f32 %0,t0;\n" ST(C) TH_GO(C, N)
 
-#define TH_B_ST(C, N) TH_NEXT(N) TH_STORE(C) TH_GOC(C, N)
-#define TH_B_LDY_M(C, N) " add.u32 ae,%6," #C "2;\n ld.shared.f32 %5,[ae];\n" TH_NEXT(N) TH_GOC(C, N)
-#define TH_B_LDY_I(C, N) " mov.b32 %5," #C "2;\n" TH_NEXT(N) TH_GOC(C, N)
-#define TH_B_LDY_A(C, N) " mov.f32 %5,%0;\n" TH_NEXT(N) TH_GOC(C, N)
+#define TH_B_ST(C, N) TH_NEXT(N) TH_STORE(C) TH_GO(C, N)
+#define TH_B_LDY_M(C, N) " add.u32 ae,%6," #C "2;\n ld.shared.f32 %5,[ae];\n" TH_NEXT(N) TH_GO(C, N)
+#define TH_B_LDY_I(C, N) " mov.b32 %5," #C "2;\n" TH_NEXT(N) TH_GO(C, N)
+#define TH_B_LDY_A(C, N) " mov.f32 %5,%0;\n" TH_NEXT(N) TH_GO(C, N)
 // leaving the block before the next instruction is fetched: pc / nh / parity name it
 #define TH_LEAVE(C, N) " mov.u32 %2," #C "0;\n add.u32 %1,%1,16;\n mov.u32 %7," TH_PARNUM_##N ";\n bra DONE;\n"
 #define TH_B_SLOW_A(C, N) " mov.f32 %4,%0;\n mov.u32 %3," #C "3;\n" TH_LEAVE(C, N)
@@ -296,27 +248,18 @@ static __host__ __device__ __forceinline__ float mtgp_th_slow_op(uint32_t sop, f
   " fma.rn.f32 t7,t3,t7,t2;\n"                                                               \
   " and.b32 ad,qi,1;\n setp.ne.u32 pq,ad,0;\n selp.f32 t6,t7,t6,pq;\n"                       \
   " shl.b32 ad,qi,30;\n and.b32 ad,ad,0x80000000;\n mov.b32 ae,t6;\n xor.b32 ae,ae,ad;\n mov.b32 %0,ae;\n" \
-  TH_GOC(C, N)                                                                               \
+  TH_GO(C, N)                                                                               \
   "TRIGSLOW_" #C ":\n"                                                                       \
   " mov.f32 %4,t0;\n add.u32 %3,cf,1;\n" TH_LEAVE(C, N)
 
-// label lists: the full table of one register set, and the hot tables (order = mtgp_th_hot_index)
-#define TH_LABELS_ARITH_a(n, g0, g1) "H_" #n "_a, H_" #n "_ST_a, "
-#define TH_LABELS_ARITH_b(n, g0, g1) "H_" #n "_b, H_" #n "_ST_b, "
+// label lists: the full table of one register set
+#define TH_LABELS_ARITH_a(n) "H_" #n "_a, H_" #n "_ST_a, "
+#define TH_LABELS_ARITH_b(n) "H_" #n "_b, H_" #n "_ST_b, "
 #define TH_LABELS_OTHER_a(n) "H_" #n "_a, "
 #define TH_LABELS_OTHER_b(n) "H_" #n "_b, "
-#if MTGP_TH_HOT_LEVEL >= 2
-#define TH_HOT_LABELS(p)                                                                                       \
-  "H_ADD_AM_" #p ", H_ADD_AM_ST_" #p ", H_ADD_AI_" #p ", H_ADD_MI_" #p ", H_MUL_AM_" #p ", H_MUL_AM_ST_" #p    \
-  ", H_MUL_AI_" #p ", H_MUL_MI_" #p ", H_ADD_AI_ST_" #p ", H_ADD_MM_" #p ", H_MUL_AI_ST_" #p ", H_MUL_MM_" #p ", "
-#else
-#define TH_HOT_LABELS(p)                                                                                       \
-  "H_ADD_AM_" #p ", H_ADD_AM_ST_" #p ", H_ADD_AI_" #p ", H_ADD_MI_" #p ", H_MUL_AM_" #p ", H_MUL_AM_ST_" #p    \
-  ", H_MUL_AI_" #p ", H_MUL_MI_" #p ", "
-#endif
-#define TH_CODE_ARITH(n, g0, g1)                                                                           \
-  "H_" #n "_a:\n" TH_B_##n(a, b, TH_NOSTORE, g0) "H_" #n "_b:\n" TH_B_##n(b, a, TH_NOSTORE, g0)            \
-  "H_" #n "_ST_a:\n" TH_B_##n(a, b, TH_STORE, g1) "H_" #n "_ST_b:\n" TH_B_##n(b, a, TH_STORE, g1)
+#define TH_CODE_ARITH(n)                                                                       \
+  "H_" #n "_a:\n" TH_B_##n(a, b, TH_NOSTORE) "H_" #n "_b:\n" TH_B_##n(b, a, TH_NOSTORE)        \
+  "H_" #n "_ST_a:\n" TH_B_##n(a, b, TH_STORE) "H_" #n "_ST_b:\n" TH_B_##n(b, a, TH_STORE)
 #define TH_CODE_OTHER(n) "H_" #n "_a:\n" TH_B_##n(a, b) "H_" #n "_b:\n" TH_B_##n(b, a)
 
 // Runs from the instruction at pc (handler nh, register set `parity`) until END (returns 0) or a slow
@@ -332,10 +275,6 @@ __device__ __forceinline__ uint32_t mtgp_th_block(float& acc, uint32_t& pc, uint
       " .reg .pred pq;\n"
       "TBLa: .branchtargets " MTGP_TH_ARITH(TH_LABELS_ARITH_a) MTGP_TH_OTHER(TH_LABELS_OTHER_a) "DONE;\n"
       "TBLb: .branchtargets " MTGP_TH_ARITH(TH_LABELS_ARITH_b) MTGP_TH_OTHER(TH_LABELS_OTHER_b) "DONE;\n"
-#if MTGP_TH_HOT_LEVEL >= 1
-      "HOTa: .branchtargets " TH_HOT_LABELS(a) "DISP_b;\n"  // reached from set-b handlers; their cold exit is DISP_b
-      "HOTb: .branchtargets " TH_HOT_LABELS(b) "DISP_a;\n"
-#endif
       " setp.ne.u32 pq,%7,0;\n"
       " @pq bra ENTRY_b;\n"
       " ld.shared.v4.u32 {a0,a1,a2,a3},[%1];\n"
@@ -343,8 +282,10 @@ __device__ __forceinline__ uint32_t mtgp_th_block(float& acc, uint32_t& pc, uint
       "ENTRY_b:\n"
       " ld.shared.v4.u32 {b0,b1,b2,b3},[%1];\n"
       " brx.idx %2, TBLb;\n"
+#ifdef MTGP_TH_CENTRAL
       "DISP_a:\n brx.idx a0, TBLb;\n"
       "DISP_b:\n brx.idx b0, TBLa;\n"
+#endif
       MTGP_TH_ARITH(TH_CODE_ARITH)
       MTGP_TH_OTHER(TH_CODE_OTHER)
       TH_TRIG_BODY(a, b) TH_TRIG_BODY(b, a)
@@ -384,10 +325,6 @@ static __host__ __device__ MTGP_TH_INLINE float mtgp_run_threaded(mtgp_saddr ent
     const mtgp_tinstr w = prog[j];
     const uint32_t hh = h;
     h = w.next;
-    {  // the hot index a hot instruction carries must name its successor
-      const int hw = mtgp_th_hot_word(hh);
-      if ((hw == 1 && w.a != mtgp_th_hot_index(h)) || (hw == 3 && w.c != mtgp_th_hot_index(h))) return mtgp_nanf();
-    }
     bool st = false;
     switch (hh) {
 #define CASE(n, EXPR) case TH_##n: acc = (EXPR); break; case TH_##n##_ST: acc = (EXPR); st = true; break;
