@@ -265,9 +265,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
                 env.template f_obs<NOISE, false>(tprev, x, y, n_obs, P.obs_noise, P.partitionable, nzv);
               else
                 env.template f_obs<NOISE, true>(tprev, x, y, n_obs, P.obs_noise, P.partitionable, nzv);
-              // the next step's row, a whole step ahead of its use
-              if (NOISE == 1 && steps + 1 < P.cap_steps)
-                nz_next = __ldg(reinterpret_cast<const float4*>(nz_base + (size_t)(steps + 1) * nzs));
               if (KIND == MTGP_EVAL_STATIC) {
 #pragma unroll
                 for (int i = 0; i < D; i++)
@@ -289,6 +286,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
               } else {
                 u = mtgp_run_threaded(prog_step, lbytes);  // feedforward :107 / dynamic readout :113
               }
+              // the next step's noise row, most of a step ahead of its use (after the interpreter call: a call
+              // waits for every outstanding load)
+              if (NOISE == 1 && steps + 1 < P.cap_steps)
+                nz_next = __ldg(reinterpret_cast<const float4*>(nz_base + (size_t)(steps + 1) * nzs));
               float dx[DR];
               env.template drift<UPAR>(x, u, dx, P);
 #pragma unroll

@@ -18,14 +18,19 @@ OPS_ALL = OPS_SR + [("sin", 1, 0.1), ("cos", 1, 0.1), ("exp", 1, 0.05), ("log", 
 ENVS = {"acrobot": Acrobot, "harmonic": HarmonicOscillator, "reactor": StirredTankReactor}
 
 
-def control_library(env, kind: int, state_size: int = 2, ops=OPS_CONTROL) -> NodeLibrary:
+def control_library_args(env, kind: int, state_size: int = 2, ops=OPS_CONTROL):
+    """(operator_list, variable_list, layer_sizes) as the reference's GeneticProgramming constructor takes them."""
     obs = [f"y{i + 1}" for i in range(env.n_obs)]
     tar = [f"tar{i + 1}" for i in range(env.n_targets)]
     if kind == abi.EVAL_STATIC:
-        return NodeLibrary(ops, [obs + tar], [env.n_control])
+        return ops, [obs + tar], [env.n_control]
     lat = [f"a{i + 1}" for i in range(state_size)]
     # DynamicPolicy.ipynb:100-102: state trees see [y, a, u(, target)], the readout sees [a(, target)]
-    return NodeLibrary(ops, [obs + lat + ["u"] + tar, lat + tar], [state_size, env.n_control])
+    return ops, [obs + lat + ["u"] + tar, lat + tar], [state_size, env.n_control]
+
+
+def control_library(env, kind: int, state_size: int = 2, ops=OPS_CONTROL) -> NodeLibrary:
+    return NodeLibrary(*control_library_args(env, kind, state_size, ops))
 
 
 def control_data(env, kind: int, rng, B: int, T_end: float, dt_save: float, dt0: float, state_size: int = 0,

@@ -5,10 +5,11 @@ cd /root/repo/multitreegp_b200/csrc
 name=$1; tu=$2; shift; shift
 mkdir -p /root/repo/variants
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -prec-div=true -prec-sqrt=true -ftz=false \
-  -Xcompiler -fPIC -Xcompiler -fvisibility=hidden "$@" -Xptxas -v -c mtgp_$tu.cu -o /tmp/var_$name.o 2>&1 | grep -A2 -E "k_rolloutILi2ELi1ELi1ELi2ELb0|k_rollout_rkILi2ELi1ELb1ELi2|k_pointwiseILi8" | grep -E "Used|spill" | tr '\n' ' '
+  -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --no-compress "$@" -Xptxas -v -c mtgp_$tu.cu -o /tmp/var_$name.o 2>&1 | grep -A2 -E "k_rolloutILi2ELi1ELi1ELi2ELb0|k_rollout_rkILi2ELi1ELb1ELi2|k_pointwiseILi8" | grep -E "Used|spill" | tr '\n' ' '
 echo " <- $name"
 objs=""
 for o in api encode rollout rollout_rk pointwise select; do
   if [ "$o" == "$tu" ]; then objs="$objs /tmp/var_$name.o"; else objs="$objs ../build/mtgp_$o.o"; fi
 done
 nvcc -shared -o /root/repo/variants/libmtgp_$name.so $objs -gencode arch=compute_100a,code=sm_100a -lcudart
+cd /root/repo && python -m multitreegp_b200.sass_patch variants/libmtgp_$name.so 2>&1 | tail -1

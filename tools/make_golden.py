@@ -37,25 +37,39 @@ def save_case(name, lib, pop, data, out):
         steps=out["steps"])
 
 
-def main():
-    os.makedirs(OUT, exist_ok=True)
-    po.build()
-    po.set_math(po.MATH_CONTRACT)
+def golden_cases():
+    """The case list, in a fixed order on one RNG stream: (name, lib, pop, data, env_name, library_args).
+    tools/record_reference_golden.py replays the same list through the real reference."""
     rng = np.random.default_rng(20261018)
     lib, pop, data = util.sr_case(rng, P=48, B=6, T_end=3.0, dt0=0.01)
-    save_case("sr_vdp", lib, pop, data, po.rollout_population(pop, lib.table(), data))
+    yield "sr_vdp", lib, pop, data, None, (util.OPS_SR, [["x0", "x1"]], [2])
     for env, grid in (("harmonic", dict(T_end=5.0, dt_save=0.2, dt0=0.05)),
                       ("acrobot", dict(T_end=5.0, dt_save=0.2, dt0=0.05)),
                       ("reactor", dict(T_end=1.0, dt_save=0.04, dt0=0.002))):
         for kind, kname in ((abi.EVAL_STATIC, "static"), (abi.EVAL_DYNAMIC, "dynamic")):
             lib, pop, data = util.control_case(env, kind, rng, P=48, B=6, obs_noise=0.1,
                                                param_mode="Constant" if env == "acrobot" else "Different", **grid)
-            save_case(f"{kname}_{env}", lib, pop, data, po.rollout_population(pop, lib.table(), data))
+            yield f"{kname}_{env}", lib, pop, data, env, util.control_library_args(util.ENVS[env](0.05, 0.1), kind, 2)
     # the notebooks' solver settings: Dopri5 + PIDController(1e-4, 1e-4, dtmin=0.001), max_steps 1000
     lib, pop, data = util.control_case("acrobot", abi.EVAL_DYNAMIC, rng, P=32, B=6, T_end=6.0, dt_save=0.2, dt0=0.05,
                                        obs_noise=0.1, max_steps=1000)
     util.with_solver(data, **util.DOPRI_PID)
-    save_case("dynamic_acrobot_dopri5_pid", lib, pop, data, po.rollout_population(pop, lib.table(), data))
+    yield ("dynamic_acrobot_dopri5_pid", lib, pop, data, "acrobot",
+           util.control_library_args(util.ENVS["acrobot"](0.05, 0.1), abi.EVAL_DYNAMIC, 2))
+    # the rng continues into the jax.random vectors of main()
+    yield "_rng", rng, None, None, None, None
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    po.build()
+    po.set_math(po.MATH_CONTRACT)
+    rng = None
+    for name, lib, pop, data, _env, _args in golden_cases():
+        if name == "_rng":
+            rng = lib
+            continue
+        save_case(name, lib, pop, data, po.rollout_population(pop, lib.table(), data))
     # jax.random vectors (threefry known answers are asserted literally in the tests)
     keys = util.random_keys(rng, 16)
     ts = np.float32(rng.uniform(0, 50, 16))
