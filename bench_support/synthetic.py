@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .node_library import NodeLibrary
+from multitreegp_b200.node_library import NodeLibrary
 
 
 def create_map_b_to_d(depth: int) -> np.ndarray:
@@ -34,10 +34,12 @@ def create_map_b_to_d(depth: int) -> np.ndarray:
 
 def sample_population(rng: np.random.Generator, population_size: int, library: NodeLibrary,
                       max_init_depth: int = 4, max_nodes: int = 30, coefficient_sd: float = 1.0,
-                      full: bool = False) -> np.ndarray:
+                      full: bool = False, op_growth: float = 0.7) -> np.ndarray:
     """Returns f32[population_size, num_trees, max_nodes, 4] in the reference's array format.
 
-    ``full=True`` makes every internal position an operator (worst-case 2^depth-1 live rows).
+    ``full=True`` makes every internal position an operator (worst-case 2^depth-1 live rows);
+    ``op_growth`` is the base of the reference's operator probability ``0.7 ** depth``
+    (initialization.py:35) -- larger values give the bloated trees of an evolved population.
     """
     T = library.num_trees
     M = population_size * T
@@ -52,6 +54,9 @@ def sample_population(rng: np.random.Generator, population_size: int, library: N
     open_slots = np.ones(M, dtype=np.int64)
 
     op_p = library.operator_probabilities / library.operator_probabilities.sum()
+    if full:  # only binary operators: every one of the 2^depth-1 scaffold rows is live
+        op_p = np.where(slots[library.operator_indices] == 2, op_p, 0.0)
+        op_p = op_p / op_p.sum()
     op_cdf = np.cumsum(op_p)
     var_p = library.variable_array / library.variable_array.sum(axis=1, keepdims=True)
     var_cdf = np.tile(np.cumsum(var_p, axis=1), (population_size, 1))  # [M, n_data]
@@ -67,7 +72,7 @@ def sample_population(rng: np.random.Generator, population_size: int, library: N
         op_choice = library.operator_indices[np.minimum(np.searchsorted(op_cdf, rng.random(M)),
                                                         len(op_cdf) - 1)]
         grow = (open_slots < max_nodes - i - 1) & (depth + 1 < max_init_depth)
-        p_op = 1.0 if full else 0.7 ** depth
+        p_op = 1.0 if full else op_growth ** depth
         index = np.where(grow, np.where(rng.random(M) < p_op, op_choice, leaf), leaf)
         index = np.where(open_slots == 0, 0, index)
         if i > 0:

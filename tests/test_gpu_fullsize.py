@@ -60,7 +60,7 @@ def test_c4_full_size_properties(engine, oracle):
     """Pointwise scale-up: 100 000 individuals x 100 000 points (max_nodes 255)."""
     import bench
     from multitreegp_b200.node_library import NodeLibrary
-    from multitreegp_b200.synthetic import pointwise_data, sample_population
+    from bench_support.synthetic import pointwise_data, sample_population
     rng = np.random.default_rng(7)
     c = bench.C4
     lib = NodeLibrary(bench.OPS_SR, [[f"x{i}" for i in range(c["n_vars"])]], [1])
@@ -85,7 +85,7 @@ def test_c4_full_size_properties(engine, oracle):
 def test_empty_and_maximum_sizes(engine, oracle):
     from multitreegp_b200.engine import DeviceData
     from multitreegp_b200.environments.control_environments import HarmonicOscillator
-    from multitreegp_b200.synthetic import sample_population
+    from bench_support.synthetic import sample_population
     from tests import util
     import torch
     rng = np.random.default_rng(5)

@@ -254,7 +254,7 @@ def test_configuration_corners(engine, oracle):
     """Shapes away from the notebooks' defaults: partial observability, more latent trees, big trees that
     fall into the worst-case-provisioned launch, max_nodes 255, B > 32 with observation noise."""
     from multitreegp_b200.environments.control_environments import Acrobot, HarmonicOscillator
-    from multitreegp_b200.synthetic import sample_population
+    from bench_support.synthetic import sample_population
     rng = np.random.default_rng(13)
     cases = []
     # n_obs < n_var (C = eye(4)[:2]), state_size 4 -> T = 5, B = 40 (two passes) with noise
@@ -340,7 +340,7 @@ def test_parsimony_and_host_api(engine, oracle):
 
 def test_pointwise_parity(engine, oracle):
     from multitreegp_b200.node_library import NodeLibrary
-    from multitreegp_b200.synthetic import pointwise_data, sample_population
+    from bench_support.synthetic import pointwise_data, sample_population
     rng = np.random.default_rng(10)
     for n_vars, T, depth, N, n_points in ((2, 1, 8, 255, 1000), (3, 2, 4, 30, 257), (8, 1, 6, 63, 4096)):
         lib = NodeLibrary(util.OPS_ALL, [[f"x{i}" for i in range(n_vars)]] * 1, [T])
@@ -505,7 +505,7 @@ def test_sr_and_static_evaluator_classes(engine, oracle):
     host (numpy) populations: __call__, evaluate_population (host C-ABI entry), evaluate_candidate."""
     from multitreegp_b200.evaluators import SR_evaluator, feedforward_evaluate, pointwise_evaluate
     from multitreegp_b200.environments.control_environments import StirredTankReactor
-    from multitreegp_b200.synthetic import van_der_pol_data, pointwise_data
+    from bench_support.synthetic import van_der_pol_data, pointwise_data
     rng = np.random.default_rng(51)
     # --- symbolic regression on Van der Pol trajectories (SymbolicRegression.ipynb) ---
     ev = SR_evaluator.Evaluator(dt0=0.01).bind(util.OPS_SR, [["x0", "x1"]], [2])

@@ -58,7 +58,7 @@ def test_solver_arguments_as_in_the_notebooks():
 
 
 def test_sr_data_tuple_and_unbound_evaluator():
-    from multitreegp_b200.synthetic import van_der_pol_data
+    from bench_support.synthetic import van_der_pol_data
     rng = np.random.default_rng(3)
     x0, ts, ys, keys = van_der_pol_data(rng, 5, 2.0, 0.2)
     ev = SR_evaluator.Evaluator()

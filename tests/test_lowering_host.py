@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from multitreegp_b200.node_library import NodeLibrary
-from multitreegp_b200.synthetic import sample_population
+from bench_support.synthetic import sample_population
 from tests import util
 
 HERE = os.path.dirname(os.path.abspath(__file__))

@@ -7,7 +7,7 @@ from multitreegp_b200 import abi
 from multitreegp_b200.environments.control_environments import Acrobot, HarmonicOscillator
 from multitreegp_b200.node_library import NodeLibrary
 from multitreegp_b200.rollout_data import RolloutData
-from multitreegp_b200.synthetic import sample_population
+from bench_support.synthetic import sample_population
 from tests import np_reference, util
 
 F32 = np.float32

@@ -7,7 +7,7 @@ from multitreegp_b200 import abi
 from multitreegp_b200.environments.control_environments import Acrobot, HarmonicOscillator, StirredTankReactor
 from multitreegp_b200.node_library import NodeLibrary
 from multitreegp_b200.rollout_data import RolloutData
-from multitreegp_b200.synthetic import random_keys, sample_population, van_der_pol_data
+from bench_support.synthetic import random_keys, sample_population, van_der_pol_data
 
 OPS_CONTROL = [("+", 2, 0.5), ("-", 2, 0.1), ("*", 2, 0.5), ("sin", 1, 0.1), ("cos", 1, 0.1)]  # StaticPolicy.ipynb:91-95
 OPS_SR = [("+", 2, 0.5), ("-", 2, 0.1), ("*", 2, 0.5), ("/", 2, 0.1)]                          # SymbolicRegression.ipynb:138-141

@@ -1,4 +1,4 @@
-"""Writes profiles/r01_traffic.json (the ncu-derived fields bench.py quotes in its roofline block) from
+"""Writes profiles/r02_traffic.json (the ncu-derived fields bench.py quotes in its roofline block) from
 the two --set full captures made by tools/gpu_final.sh:
 
     python tools/ncu_traffic.py gpurun_out/prof_rollout_full.ncu-rep gpurun_out/prof_pointwise_full.ncu-rep
@@ -58,6 +58,12 @@ if __name__ == "__main__":
         line = json.load(fh)
     warp_steps = line["config"]["executed_rollout_steps_per_step"] / 32.0
     out = {"k_rollout": block(roll, 65536, warp_steps), "k_pointwise": block(pw, 100000)}
-    with open(os.path.join(ROOT, "profiles", "r01_traffic.json"), "w") as fh:
+    commit = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    dirty = subprocess.run(["git", "-C", ROOT, "status", "--porcelain", "--", "multitreegp_b200"], capture_output=True,
+                           text=True).stdout.strip()
+    for b in out.values():
+        b["commit"] = commit + ("+uncommitted" if dirty else "")
+        b["dram_bytes_per_launch"] = b["dram_bytes_read"] + b["dram_bytes_write"]
+    with open(os.path.join(ROOT, "profiles", "r02_traffic.json"), "w") as fh:
         json.dump(out, fh, indent=1)
     print(json.dumps(out, indent=1))
