@@ -69,6 +69,11 @@ class EvaluatorBase:
             self._engine = FitnessEngine()
         return self._engine
 
+    def solver_settings(self) -> dict:
+        """RolloutData fields of the evaluator's solver / step-size controller (solver, controller, rtol, atol,
+        dtmin, pid, pid_limits): what the FFI binding forwards as attributes."""
+        return dict(getattr(self, "_solver_settings", {}) or {})
+
     # -- to be provided by subclasses ------------------------------------------------------------
     def rollout_data(self, data) -> RolloutData:
         raise NotImplementedError
