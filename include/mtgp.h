@@ -275,6 +275,11 @@ MTGP_API int mtgp_population_fitness_pointwise_host(const float* population_host
                                            float max_fitness, float size_parsimony,
                                            float* fitness_host, void* stream);
 
+/* Frees the device scratch buffers the *_host entry points keep per device (they are grow-only and reused
+ * from call to call).  The *_host entry points are serialised per device by the library; the pointer-based
+ * entry points above own no state and are re-entrant. */
+MTGP_API int mtgp_release_scratch(void);
+
 /* What the strategy does with the gathered fitness vector, without a host round trip:
  *   best_index = argmin(fitness) over the flattened population, best_fitness = fitness[best_index],
  *   best_solution = population[best_index]                   (genetic_programming.py:426-431)

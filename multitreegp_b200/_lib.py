@@ -81,5 +81,5 @@ EXPORTED_SYMBOLS = [
     "mtgp_bytecode_bytes", "mtgp_program_stride", "mtgp_encode", "mtgp_decode", "mtgp_lower",
     "mtgp_eval_pointwise", "mtgp_rollout", "mtgp_population_fitness", "mtgp_population_fitness_ex",
     "mtgp_population_fitness_host", "mtgp_population_fitness_pointwise", "mtgp_population_fitness_pointwise_host",
-    "mtgp_select",
+    "mtgp_select", "mtgp_release_scratch",
 ]

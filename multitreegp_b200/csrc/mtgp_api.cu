@@ -6,6 +6,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <map>
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -386,20 +388,31 @@ int mtgp_population_fitness_pointwise(const float* nodes, int nodes_stride, cons
 
 // ---- host-buffer entry points: H2D copies + evaluation + D2H, one call ---------------------------
 namespace {
+// Scratch of the *_host entry points: one grow-only buffer per device, owned for the WHOLE call by the caller
+// that holds the device's mutex -- two host threads evaluating on the same device are serialised (the calls
+// synchronise their stream before returning, so the buffer is idle whenever the mutex is free and may be
+// replaced by a larger one).  mtgp_release_scratch() frees the buffers.
 struct DeviceScratch {
+  std::mutex mu;
   void* ptr = nullptr;
   size_t bytes = 0;
 };
-std::mutex g_scratch_mu;
-DeviceScratch g_scratch[64];
+std::mutex g_scratch_table_mu;
+std::map<int, std::unique_ptr<DeviceScratch>> g_scratch;
 
-int scratch_for_device(size_t bytes, void** out) {
+DeviceScratch* scratch_of_current_device() {
   int dev = 0;
-  MTGP_CUDA_TRY(cudaGetDevice(&dev));
-  std::lock_guard<std::mutex> lk(g_scratch_mu);
-  DeviceScratch& s = g_scratch[dev & 63];
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lk(g_scratch_table_mu);
+  auto& slot = g_scratch[dev];
+  if (!slot) slot.reset(new DeviceScratch());
+  return slot.get();
+}
+
+// call with s.mu held
+int scratch_reserve(DeviceScratch& s, size_t bytes, void** out) {
   if (s.bytes < bytes) {
-    if (s.ptr) MTGP_CUDA_TRY(cudaFree(s.ptr));
+    if (s.ptr) MTGP_CUDA_TRY(cudaFree(s.ptr));  // idle: every host call synchronises before it releases the mutex
     s.ptr = nullptr;
     s.bytes = 0;
     MTGP_CUDA_TRY(cudaMalloc(&s.ptr, bytes));
@@ -408,7 +421,30 @@ int scratch_for_device(size_t bytes, void** out) {
   *out = s.ptr;
   return MTGP_OK;
 }
+
+// ts must be finite and non-decreasing (diffrax requires it of SaveAt(ts)); host copy at hand in the *_host path
+int validate_ts_host(const float* ts, int K) {
+  if (K < 1 || !ts) { mtgp_set_error("ts: need at least one save point"); return MTGP_ERR_INVALID_ARGUMENT; }
+  for (int k = 0; k < K; k++) {
+    if (!(ts[k] - ts[k] == 0.0f) || (k > 0 && ts[k] < ts[k - 1])) {
+      mtgp_set_error("ts[%d] = %g: save times must be finite and non-decreasing", k, (double)ts[k]);
+      return MTGP_ERR_INVALID_ARGUMENT;
+    }
+  }
+  return MTGP_OK;
+}
 }  // namespace
+
+int mtgp_release_scratch(void) {
+  std::lock_guard<std::mutex> lk(g_scratch_table_mu);
+  for (auto& kv : g_scratch) {
+    std::lock_guard<std::mutex> lk2(kv.second->mu);
+    if (kv.second->ptr) cudaFree(kv.second->ptr);
+    kv.second->ptr = nullptr;
+    kv.second->bytes = 0;
+  }
+  return MTGP_OK;
+}
 
 int mtgp_population_fitness_host(const float* population_host, int P, int T, int N, const mtgp_node_table* table,
                                  const mtgp_rollout_desc* dh, float size_parsimony, float* fitness_host,
@@ -421,7 +457,10 @@ int mtgp_population_fitness_host(const float* population_host, int P, int T, int
   const size_t pop_bytes = (size_t)P * T * N * 4 * sizeof(float);
   const size_t ws_bytes = mtgp_workspace_bytes(P, T, N, dh);
   const size_t B = dh->B, K = dh->K, D = dh->D;
-  Carver c(nullptr);
+  if ((rc = validate_ts_host(dh->ts, dh->K))) return rc;
+  DeviceScratch* sc = scratch_of_current_device();
+  if (!sc) { mtgp_set_error("cudaGetDevice failed"); return MTGP_ERR_CUDA; }
+  std::lock_guard<std::mutex> scratch_lock(sc->mu);  // the scratch is this call's until it has synchronised
   // layout of the scratch: population | fitness | data arrays | workspace
   size_t off_pop = 0, off_fit, off_x0, off_ts, off_tg, off_keys, off_par, off_ys, off_ws, total;
   {
@@ -436,7 +475,7 @@ int mtgp_population_fitness_host(const float* population_host, int P, int T, int
     off_ws = o; total = o + ws_bytes;
   }
   void* base_v = nullptr;
-  if ((rc = scratch_for_device(total, &base_v))) return rc;
+  if ((rc = scratch_reserve(*sc, total, &base_v))) return rc;
   unsigned char* base = static_cast<unsigned char*>(base_v);
   mtgp_rollout_desc dd = *dh;
   dd.params_host = dh->params;  // the host copy is at hand: trajectory-uniform parameters are detected
@@ -484,8 +523,11 @@ int mtgp_population_fitness_pointwise_host(const float* population_host, int P, 
   const size_t off_x = o; o = align_up(o + (size_t)n_points * n_vars * 4, 256);
   const size_t off_y = o; o = align_up(o + (size_t)n_points * T * 4, 256);
   const size_t off_ws = o;
+  DeviceScratch* sc = scratch_of_current_device();
+  if (!sc) { mtgp_set_error("cudaGetDevice failed"); return MTGP_ERR_CUDA; }
+  std::lock_guard<std::mutex> scratch_lock(sc->mu);
   void* base_v = nullptr;
-  if ((rc = scratch_for_device(o + ws_bytes, &base_v))) return rc;
+  if ((rc = scratch_reserve(*sc, o + ws_bytes, &base_v))) return rc;
   unsigned char* base = static_cast<unsigned char*>(base_v);
   MTGP_CUDA_TRY(cudaMemcpyAsync(base, population_host, pop_bytes, cudaMemcpyHostToDevice, s));
   MTGP_CUDA_TRY(cudaMemcpyAsync(base + off_x, X_host, (size_t)n_points * n_vars * 4, cudaMemcpyHostToDevice, s));

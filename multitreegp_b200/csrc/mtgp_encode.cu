@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(128) k_lower(mtgp_bytecode bc, long long n_tre
   if (tree >= n_trees) return;
   bool canonical;
   meta[tree] = mtgp_lower_tree<NMAX>(bc.op + tree * N, bc.a + tree * N, bc.b + tree * N, bc.coef + tree * N, N, tab,
-                                     tmp_base, prog + tree * lstride, &canonical);
+                                     tmp_base, prog + tree * lstride, &canonical, mtgp_tmp_bound(N));
   bc.flags[tree] = (uint8_t)((bc.flags[tree] & MTGP_BC_LOSSY) | (canonical ? MTGP_BC_CANONICAL : 0));
 }
 

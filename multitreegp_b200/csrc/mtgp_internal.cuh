@@ -52,5 +52,5 @@ int mtgp_launch_transpose_points(const float* X, const float* Y, int n_points, i
                                  int n_vars, int T, float* Xt, float* Yt, cudaStream_t stream);
 
 // slot bookkeeping shared by the host code
-static inline int mtgp_tmp_bound(int N) { return (N + 1) / 2 + 1; }  // ceil(N/2)+1
+static __host__ __device__ inline int mtgp_tmp_bound(int N) { return (N + 1) / 2 + 1; }  // ceil(N/2)+1
 static inline int mtgp_lstride(int N) { return (N + 2 + 1) & ~1; }

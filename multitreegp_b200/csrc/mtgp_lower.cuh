@@ -48,11 +48,13 @@ struct SlotAlloc {
 };
 
 
-// Lowers one tree.  op/ra/rb/rc: the tree's level-1 rows; out: its program (>= mtgp_lstride(N)
+// Lowers one tree (tmp_cap = temporaries the caller provisions per warp: a program may not need more).
+// op/ra/rb/rc: the tree's level-1 rows; out: its program (>= mtgp_lstride(N)
 // instructions).  Returns the meta word (MTGP_META_*) and the canonical-layout flag through *canonical_out.
 template <int NMAX>
 MTGP_LHD uint32_t mtgp_lower_tree(const uint8_t* op, const int16_t* ra, const int16_t* rb, const float* rc, int N,
-                                  const mtgp_node_table& tab, int tmp_base, uint2* out, bool* canonical_out) {
+                                  const mtgp_node_table& tab, int tmp_base, uint2* out, bool* canonical_out,
+                                  int tmp_cap = MTGP_MAX_SLOTS) {
   uint8_t kind[NMAX];
   uint8_t ref[NMAX];
   uint32_t payload[NMAX];
@@ -154,7 +156,7 @@ MTGP_LHD uint32_t mtgp_lower_tree(const uint8_t* op, const int16_t* ra, const in
       const int remaining = ref[acc_row] - ((x_acc || y_acc) ? 1 : 0);
       if (remaining > 0) {
         const int s = slots.alloc();
-        if (s < 0 || tmp_base + s >= MTGP_MAX_SLOTS) { overflow = true; break; }
+        if (s < 0 || s >= tmp_cap || tmp_base + s >= MTGP_MAX_SLOTS) { overflow = true; break; }  // tmp_cap: slots the kernels provision
         out[last].x = (out[last].x & ~0xFF00u) | ((uint32_t)(tmp_base + s) << 8);
         kind[acc_row] = DK_TMP;
         payload[acc_row] = (uint32_t)(tmp_base + s);

@@ -316,7 +316,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
           }
           const bool live_save = stepping && alive;
           // ---- SaveAt(ts): dense (linear) output for every ts[k] <= tnext ----
-          while (k < K && ts_k <= save_until) {
+          // (once the solve is over every remaining save point is drained, whatever ts holds -- a NaN in ts must not stall the loop)
+          while (k < K && (!stepping || ts_k <= save_until)) {
             const float tk = ts_k;
             const float coeff = (tprev == tnext) ? 0.0f : (tk - tprev) / (tnext - tprev);
             float xs[DR];

@@ -46,6 +46,8 @@ class RolloutData:
     def __post_init__(self) -> None:
         self.x0 = np.ascontiguousarray(self.x0, dtype=np.float32)
         self.ts = np.ascontiguousarray(self.ts, dtype=np.float32)
+        if self.ts.ndim != 1 or self.ts.size < 1 or not np.isfinite(self.ts).all() or (np.diff(self.ts) < 0).any():
+            raise ValueError("ts must be a non-empty, finite, non-decreasing vector of save times (diffrax.SaveAt(ts=ts))")
         B, D = self.x0.shape
         if self.targets is None:
             self.targets = np.zeros((B, 0), dtype=np.float32)

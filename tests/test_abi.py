@@ -33,7 +33,7 @@ def test_exports_match_header(L):
 def test_struct_layouts_match_header():
     assert C.sizeof(abi.NodeTable) == 4 + 64 + 4 * 64
     assert C.sizeof(abi.Bytecode) == 6 * 8
-    assert C.sizeof(abi.RolloutDesc) == 26 * 4 + 6 * 8
+    assert C.sizeof(abi.RolloutDesc) == 26 * 4 + 7 * 8   # + params_host (ABI 3)
     assert C.sizeof(abi.TrajectoryOut) == 5 * 8
 
 
