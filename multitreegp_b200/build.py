@@ -14,7 +14,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libmtgp_b200.so")
 SOURCES = ["mtgp_api.cu", "mtgp_encode.cu", "mtgp_rollout.cu", "mtgp_rollout_rk.cu", "mtgp_pointwise.cu",
            "mtgp_select.cu"]
-HEADERS = ["mtgp_internal.cuh", "mtgp_program.cuh", "mtgp_threaded.cuh", "mtgp_env.cuh", "mtgp_lower.cuh", "../../include/mtgp.h", "../../include/mtgp_math.h"]
+HEADERS = ["mtgp_internal.cuh", "mtgp_program.cuh", "mtgp_threaded.cuh", "mtgp_threaded_r8.cuh", "mtgp_env.cuh", "mtgp_lower.cuh", "../../include/mtgp.h", "../../include/mtgp_math.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -27,8 +27,9 @@ NVCC_FLAGS = [
 
 # The rollout kernels' device code stays uncompressed in the fat binary: sass_patch.py (jump-table merge of the
 # threaded-code interpreter) patches the embedded cubin in place.
-PER_SOURCE_FLAGS = {"mtgp_rollout.cu": ["--no-compress"], "mtgp_rollout_rk.cu": ["--no-compress"]}
-PATCHED_CUBINS = ("mtgp_rollout",)
+PER_SOURCE_FLAGS = {"mtgp_rollout.cu": ["--no-compress"], "mtgp_rollout_rk.cu": ["--no-compress"],
+                    "mtgp_pointwise.cu": ["--no-compress"]}
+PATCHED_CUBINS = ("mtgp_rollout", "mtgp_pointwise")
 
 
 def _nvcc() -> str:

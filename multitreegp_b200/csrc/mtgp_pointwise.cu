@@ -7,8 +7,12 @@
 // For each chunk a warp loads the variables once (coalesced float4 from the transposed data set,
 // which is L2-resident) into its shared-memory value file and then runs the programs of all G
 // individuals on it, so every data byte fetched from L2 is used G times.  Each lane evaluates R
-// points per dispatched instruction, which amortises the (warp-uniform) decode over 32*R points.
-#include "mtgp_internal.cuh"
+// points per dispatched instruction, which amortises the (warp-uniform) dispatch over 32*R points.
+// R = 8 (the two regular launch classes): programs are staged by cp.async.bulk + mbarrier, expanded once per
+// CTA to threaded code and run by the eight-values-per-lane interpreter of mtgp_threaded_r8.cuh.
+// R = 1 (worst-case provisioning for trees of extreme size): the compact-format interpreter.
+#include "mtgp_env.cuh"  // mbarrier / bulk-copy helpers
+#include "mtgp_threaded_r8.cuh"
 
 namespace {
 
@@ -16,7 +20,7 @@ namespace {
 #define MTGP_PW_R 8  // points per lane per dispatched instruction in the fast pointwise launch
 #endif
 #ifndef MTGP_PW_MIN_CTAS
-#define MTGP_PW_MIN_CTAS 8  // resident CTAs per SM the register allocation is tuned for
+#define MTGP_PW_MIN_CTAS 5  // resident CTAs per SM the register allocation is tuned for (shared memory allows 5 in the fast class)
 #endif
 constexpr int kPwWarps = 4;
 #ifndef MTGP_PW_GROUP
@@ -41,8 +45,8 @@ struct PointwiseParams {
   // this launch handles the individuals whose programs fit (cap_tmp temporaries, cap_instr instructions
   // incl. END per tree) but do not fit the previous, smaller class (prev_tmp, prev_instr; -1 = none)
   int cap_tmp, cap_instr, prev_tmp, prev_instr;
-  int pstride;     // instructions reserved per tree in shared memory
-  int slots_per_warp;
+  int pstride;     // instructions reserved per tree in shared memory (compact and threaded form alike)
+  int slots_per_warp;  // data + temporaries (+ 1 scratch slot for R = 8)
 };
 
 
@@ -56,7 +60,7 @@ __global__ void __launch_bounds__(kPwWarps * 32, MTGP_PW_MIN_CTAS) k_pointwise(c
   const int G = min(kPwGroup, P.P - ind0);
   const int words_per_ind = P.T * P.pstride;
   uint2* prog_s = reinterpret_cast<uint2*>(smem_raw);
-  float* acc_s = reinterpret_cast<float*>(smem_raw + (size_t)kPwGroup * words_per_ind * sizeof(uint2));
+  float* acc_s = reinterpret_cast<float*>(smem_raw + (size_t)kPwGroup * words_per_ind * (sizeof(uint2) + (R == 8 ? sizeof(mtgp_tinstr) : 0)));
   float* vf = acc_s + kPwGroup * kPwWarps * 32 + (size_t)wic * P.slots_per_warp * 32 * R;
 
   // which individuals of the group belong to this launch (by temporaries and program length)
@@ -69,7 +73,7 @@ __global__ void __launch_bounds__(kPwWarps * 32, MTGP_PW_MIN_CTAS) k_pointwise(c
       for (int t = 0; t < P.T; t++) {
         const uint32_t m = P.meta[(size_t)ind * P.T + t];
         need = max(need, (int)MTGP_META_TMP(m));
-        len = max(len, (int)MTGP_META_N(m) + 1);
+        len = max(len, (int)MTGP_META_TH(m));  // threaded instructions incl. header and END (>= compact length + 1)
       }
       const bool fits = (need <= P.cap_tmp) && (len <= P.cap_instr);
       const bool fits_prev = (need <= P.prev_tmp) && (len <= P.prev_instr);
@@ -82,25 +86,48 @@ __global__ void __launch_bounds__(kPwWarps * 32, MTGP_PW_MIN_CTAS) k_pointwise(c
   for (int g = 0; g < G; g++) any |= (s_need[g] != 0);
   if (!any) return;
 
-  // stage the programs of the group: only the instructions each tree actually has
-  for (int gt = wic; gt < G * P.T; gt += kPwWarps) {
-    if (!s_need[gt / P.T]) continue;
-    const size_t tree = (size_t)s_ind[gt / P.T] * P.T + gt % P.T;
-    const int n = (int)MTGP_META_N(P.meta[tree]) + 1;
-    const uint2* src = P.prog + tree * P.lstride;
-    uint2* dst = prog_s + (size_t)gt * P.pstride;
-    for (int i = lane; i < n; i += 32) dst[i] = __ldg(src + i);
+  // stage the programs of the group -- only the instructions each tree actually has -- with cp.async.bulk
+  // completing on one mbarrier (16-byte granules: program rows are 16-byte aligned, lstride is even)
+  __shared__ __align__(8) uint64_t s_bar;
+  if (threadIdx.x == 0) {
+    mtgp_dev::mbar_init(&s_bar, 1);
+    uint32_t total = 0;
+    for (int gt = 0; gt < G * P.T; gt++)
+      if (s_need[gt / P.T]) total += ((MTGP_META_N(P.meta[(size_t)s_ind[gt / P.T] * P.T + gt % P.T]) + 2u) & ~1u) * 8u;
+    mtgp_dev::mbar_expect_tx(&s_bar, total);
+    for (int gt = 0; gt < G * P.T; gt++) {
+      if (!s_need[gt / P.T]) continue;
+      const size_t tree = (size_t)s_ind[gt / P.T] * P.T + gt % P.T;
+      mtgp_dev::bulk_g2s(prog_s + (size_t)gt * P.pstride, P.prog + tree * P.lstride,
+                         ((MTGP_META_N(P.meta[tree]) + 2u) & ~1u) * 8u, &s_bar);
+    }
   }
   __syncthreads();
+  mtgp_dev::mbar_wait(&s_bar, 0);
+  mtgp_tinstr* th_s = reinterpret_cast<mtgp_tinstr*>(prog_s + (size_t)kPwGroup * words_per_ind);
+  if constexpr (R == 8) {
+    // expand to threaded code (slot stride 1024 B, no in-block trig): one thread per tree
+    for (int gt = threadIdx.x; gt < G * P.T; gt += blockDim.x) {
+      if (!s_need[gt / P.T]) continue;
+      const size_t tree = (size_t)s_ind[gt / P.T] * P.T + gt % P.T;
+      const int n = (int)MTGP_META_N(P.meta[tree]) + 1;  // with X_END
+      const uint2* src = prog_s + (size_t)gt * P.pstride;
+      mtgp_tinstr* dst = th_s + (size_t)gt * P.pstride;
+      int m = 1;
+      for (int i = 0; i < n; i++) m += mtgp_th_expand<1024, false>(src[i], dst + m);
+      mtgp_th_link(dst, m - 1);
+    }
+    __syncthreads();
+  }
 
-  float* lb = vf + lane * R;
+  float* lb = vf + lane * (R % 4 == 0 ? 4 : R);
   constexpr int chunk_pts = 32 * R;
+  auto point_of = [&](int c, int r) { return c * chunk_pts + (R % 4 == 0 ? (r / 4) * 128 + lane * 4 + (r % 4) : lane * R + r); };
   const int n_chunks = P.npad / chunk_pts;
   // per-lane partial sums of squared error, one per individual of the group, in shared memory
   for (int g = 0; g < kPwGroup; g++) acc_s[(g * kPwWarps + wic) * 32 + lane] = 0.0f;
 
   for (int c = wic; c < n_chunks; c += kPwWarps) {
-    const int pt0 = c * chunk_pts + lane * R;
     const bool ragged = (c + 1) * chunk_pts > P.n_points;  // warp-uniform: only the last chunk has padding
     // variables and targets of this chunk -> value file slots [0, n_vars) and [n_vars, n_vars+T)
     for (int v = 0; v < P.n_vars + P.T; v++) {
@@ -109,12 +136,12 @@ __global__ void __launch_bounds__(kPwWarps * 32, MTGP_PW_MIN_CTAS) k_pointwise(c
       if constexpr (R % 4 == 0) {
 #pragma unroll
         for (int i = 0; i < R / 4; i++) {
-          const float4 t4 = __ldg(reinterpret_cast<const float4*>(src + pt0) + i);
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(src + c * chunk_pts + i * 128 + lane * 4));
           d.v[4 * i] = t4.x; d.v[4 * i + 1] = t4.y; d.v[4 * i + 2] = t4.z; d.v[4 * i + 3] = t4.w;
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < R; i++) d.v[i] = __ldg(src + pt0 + i);
+        for (int i = 0; i < R; i++) d.v[i] = __ldg(src + point_of(c, i));
       }
       vf_store<R>(lb, v, d);
     }
@@ -124,7 +151,12 @@ __global__ void __launch_bounds__(kPwWarps * 32, MTGP_PW_MIN_CTAS) k_pointwise(c
 #pragma unroll
       for (int r = 0; r < R; r++) row[r] = 0.0f;
       for (int t = 0; t < P.T; t++) {
-        const Vec<R> pr = mtgp_interpret<R>(prog_s + (size_t)g * words_per_ind + (size_t)t * P.pstride, lb);
+        Vec<R> pr;
+        if constexpr (R == 8)
+          pr = mtgp_run_threaded8(mtgp_saddr_of(th_s + (size_t)g * words_per_ind + (size_t)t * P.pstride), mtgp_saddr_of(lb),
+                                  (uint32_t)(P.slots_per_warp - 1) * 1024u);
+        else
+          pr = mtgp_interpret<R>(prog_s + (size_t)g * words_per_ind + (size_t)t * P.pstride, lb);
         const Vec<R> yt = vf_load<R>(lb, P.n_vars + t);
 #pragma unroll
         for (int r = 0; r < R; r++) {
@@ -134,13 +166,13 @@ __global__ void __launch_bounds__(kPwWarps * 32, MTGP_PW_MIN_CTAS) k_pointwise(c
         if (P.pred) {
 #pragma unroll
           for (int r = 0; r < R; r++)
-            if (pt0 + r < P.n_points) P.pred[((size_t)s_ind[g] * P.n_points + pt0 + r) * P.T + t] = pr.v[r];
+            if (point_of(c, r) < P.n_points) P.pred[((size_t)s_ind[g] * P.n_points + point_of(c, r)) * P.T + t] = pr.v[r];
         }
       }
       float s = 0.0f;
       if (ragged) {
 #pragma unroll
-        for (int r = 0; r < R; r++) s = s + ((pt0 + r < P.n_points) ? row[r] : 0.0f);
+        for (int r = 0; r < R; r++) s = s + ((point_of(c, r) < P.n_points) ? row[r] : 0.0f);
       } else {
 #pragma unroll
         for (int r = 0; r < R; r++) s = s + row[r];
@@ -185,9 +217,9 @@ int launch_pw(PointwiseParams pp, int n_tmp, int pstride, int prev_tmp, int prev
   pp.prev_tmp = prev_tmp;
   pp.prev_instr = prev_instr;
   pp.pstride = pstride;
-  pp.slots_per_warp = pp.tmp_base + n_tmp;
-  const size_t smem = (size_t)kPwGroup * pp.T * pstride * sizeof(uint2) + (size_t)kPwGroup * kPwWarps * 32 * 4 +
-                      (size_t)kPwWarps * pp.slots_per_warp * 32 * R * 4;
+  pp.slots_per_warp = pp.tmp_base + n_tmp + (R == 8 ? 1 : 0);  // R = 8: one scratch slot for the slow operators
+  const size_t smem = (size_t)kPwGroup * pp.T * pstride * (sizeof(uint2) + (R == 8 ? sizeof(mtgp_tinstr) : 0)) +
+                      (size_t)kPwGroup * kPwWarps * 32 * 4 + (size_t)kPwWarps * pp.slots_per_warp * 32 * R * 4;
   if (smem > 227 * 1024) {
     mtgp_set_error("pointwise kernel needs %zu bytes of shared memory per CTA: over the 227 KB limit", smem);
     return MTGP_ERR_UNSUPPORTED;
@@ -228,11 +260,12 @@ int mtgp_launch_pointwise(const mtgp_programs& progs, const int32_t* live, int P
   //            R points per lane, small shared-memory footprint, 6-8 resident CTAs per SM
   //   medium : <= 8 temporaries, <= 128 instructions: still R points per lane, fewer resident CTAs
   //   worst  : anything a max_nodes-row array can hold (long combs grown by mutation): one point per lane
-  const int bound = mtgp_tmp_bound(N), worst_instr = progs.lstride;
-  const int t0 = bound < 4 ? bound : 4, i0 = worst_instr < 32 ? worst_instr : 32;
+  // (lengths are threaded-code instructions per tree, header and END included: MTGP_META_TH)
+  const int bound = mtgp_tmp_bound(N), worst_instr = MTGP_TH_MAX_EXPAND * progs.lstride + 2;
+  const int t0 = bound < 4 ? bound : 4, i0 = worst_instr < 40 ? worst_instr : 40;
   int rc = launch_pw<MTGP_PW_R>(pp, t0, i0, -1, -1, stream);
   if (rc != MTGP_OK || (t0 == bound && i0 == worst_instr)) return rc;
-  const int t1 = bound < 8 ? bound : 8, i1 = worst_instr < 128 ? worst_instr : 128;
+  const int t1 = bound < 8 ? bound : 8, i1 = worst_instr < 160 ? worst_instr : 160;
   rc = launch_pw<MTGP_PW_R>(pp, t1, i1, t0, i0, stream);
   if (rc != MTGP_OK || (t1 == bound && i1 == worst_instr)) return rc;
   rc = launch_pw<1>(pp, bound, worst_instr, t1, i1, stream);

@@ -19,8 +19,10 @@
 //
 // Instruction = 8 bytes:  .x = opcode | x kind << 4 | y kind << 6 | store_slot << 8 | x_slot << 16 | y_slot << 24
 //                         .y = immediate (float bits)          kinds: accumulator / memory slot / immediate
-// Slot s of a warp's value file is the 32*R floats at  base + s*32*R ; lane l owns elements
-// [l*R, l*R+R) -- conflict-free for R = 1 (4-byte) and R = 4 (16-byte) accesses.
+// Slot s of a warp's value file is the 32*R floats at  base + s*32*R.  R = 1: lane l owns element l.
+// R = 4k: the slot is k PLANES of 32 float4, lane l owns float4 l of every plane (lane base = base + 4 l,
+// plane i at + 128 i floats) -- every 16-byte access of a warp covers 512 contiguous bytes, conflict-free.
+// (Round 1 gave a lane its R values contiguously: a 32-byte lane stride, 2-way conflicts on every LDS.128.)
 #pragma once
 
 #include <cuda_runtime.h>
@@ -111,7 +113,7 @@ __host__ __device__ __forceinline__ Vec<R> vf_load(const float* lane_base, uint3
   if constexpr (R % 4 == 0) {
 #pragma unroll
     for (int i = 0; i < R / 4; i++) {
-      float4 t = reinterpret_cast<const float4*>(p)[i];
+      float4 t = *reinterpret_cast<const float4*>(p + 128 * i);
       r.v[4 * i] = t.x; r.v[4 * i + 1] = t.y; r.v[4 * i + 2] = t.z; r.v[4 * i + 3] = t.w;
     }
   } else {
@@ -126,7 +128,7 @@ __host__ __device__ __forceinline__ void vf_store(float* lane_base, uint32_t slo
   if constexpr (R % 4 == 0) {
 #pragma unroll
     for (int i = 0; i < R / 4; i++)
-      reinterpret_cast<float4*>(p)[i] = make_float4(a.v[4 * i], a.v[4 * i + 1], a.v[4 * i + 2], a.v[4 * i + 3]);
+      *reinterpret_cast<float4*>(p + 128 * i) = make_float4(a.v[4 * i], a.v[4 * i + 1], a.v[4 * i + 2], a.v[4 * i + 3]);
   } else {
 #pragma unroll
     for (int i = 0; i < R; i++) p[i] = a.v[i];

@@ -37,7 +37,8 @@
   X(SUB_AM) X(RSB_AM) X(RSB_AI) X(SUB_MM) X(RSB_MI) \
   X(LOAD_M) X(LOAD_I)
 #define MTGP_TH_OTHER(X) \
-  X(ST) X(LDY_M) X(LDY_I) X(LDY_A) X(SLOW_A) X(SLOW_M) X(SLOW_I) X(SIN_A) X(SIN_M) X(COS_A) X(COS_M) X(END)
+  X(ST) X(LDY_M) X(LDY_I) X(LDY_A) X(SLOW_A) X(SLOW_M) X(SLOW_I) X(SIN_A) X(SIN_M) X(COS_A) X(COS_M) \
+  X(DIV_A) X(DIV_M) X(DIV_I) X(END)
 
 enum mtgp_th : uint32_t {
 #define X(n) TH_##n, TH_##n##_ST,
@@ -64,10 +65,14 @@ struct __align__(16) mtgp_tinstr {
 
 // compact instruction -> up to 3 threaded instructions; .next holds the instruction's OWN handler
 // until mtgp_th_link() rewrites it.  Returns the count.
+// SLOT_BYTES: bytes between value-file slots (128 for one value per lane, 1024 for the pointwise kernel's 8);
+// TRIG_INBLOCK: sin / cos have in-block handlers (the rollout kernels) or leave the block like the other slow operators.
+template <int SLOT_BYTES = 128, bool TRIG_INBLOCK = true>
 __host__ __device__ __forceinline__ int mtgp_th_expand(uint2 c, mtgp_tinstr* out) {
   const uint32_t op = c.x & 15u, st = (c.x >> 8) & 0xFFu;
-  const uint32_t xk = (c.x >> 4) & 3u, yk = (c.x >> 6) & 3u, xs = ((c.x >> 16) & 0xFFu) * 128u, ys = (c.x >> 24) * 128u;
-  const uint32_t imm = c.y, nimm = c.y ^ 0x80000000u, sto = st * 128u;
+  const uint32_t xk = (c.x >> 4) & 3u, yk = (c.x >> 6) & 3u, xs = ((c.x >> 16) & 0xFFu) * (uint32_t)SLOT_BYTES,
+                 ys = (c.x >> 24) * (uint32_t)SLOT_BYTES;
+  const uint32_t imm = c.y, nimm = c.y ^ 0x80000000u, sto = st * (uint32_t)SLOT_BYTES;
   const bool has_st = st != MTGP_NO_SLOT;
   const uint32_t s1 = has_st ? 1u : 0u;
   auto put = [&](int i, uint32_t h, uint32_t a, uint32_t b, uint32_t cc) {
@@ -119,7 +124,7 @@ __host__ __device__ __forceinline__ int mtgp_th_expand(uint2 c, mtgp_tinstr* out
     default: sop = S_SIN + (op - X_SIN); binary = false; break;  // SIN COS EXP LOG SQRT TANH NEG ABS
   }
   int n = 0;
-  if ((op == X_SIN || op == X_COS) && xk != OK_IMM) {  // in-block handlers (fast path inside the PTX block)
+  if (TRIG_INBLOCK && (op == X_SIN || op == X_COS) && xk != OK_IMM) {  // in-block handlers (fast path inside the PTX block)
     const uint32_t h = (op == X_SIN) ? (xk == OK_ACC ? TH_SIN_A : TH_SIN_M) : (xk == OK_ACC ? TH_COS_A : TH_COS_M);
     put(n++, h, xk == OK_MEM ? xs : 0u, 0, 0);
     if (has_st) put(n++, TH_ST, 0, 0, sto);
@@ -127,7 +132,10 @@ __host__ __device__ __forceinline__ int mtgp_th_expand(uint2 c, mtgp_tinstr* out
   }
   if (op == X_LOAD) { put(n++, TH_LDY_I, 0, 0x80000000u, 0); }  // x + (-0.0) == x
   else if (binary) put(n++, yk == OK_ACC ? TH_LDY_A : (yk == OK_MEM ? TH_LDY_M : TH_LDY_I), 0, yk == OK_MEM ? ys : imm, 0);
-  put(n++, xk == OK_ACC ? TH_SLOW_A : (xk == OK_MEM ? TH_SLOW_M : TH_SLOW_I), xk == OK_MEM ? xs : imm, 0, sop);
+  if (op == X_DIV)  // x / y with y loaded by the LDY before it: in-block (IEEE div.rn)
+    put(n++, xk == OK_ACC ? TH_DIV_A : (xk == OK_MEM ? TH_DIV_M : TH_DIV_I), xk == OK_MEM ? xs : imm, 0, 0);
+  else
+    put(n++, xk == OK_ACC ? TH_SLOW_A : (xk == OK_MEM ? TH_SLOW_M : TH_SLOW_I), xk == OK_MEM ? xs : imm, 0, sop);
   if (has_st) put(n++, TH_ST, 0, 0, sto);
   return n;
 }
@@ -223,6 +231,10 @@ static __host__ __device__ __forceinline__ float mtgp_th_slow_op(uint32_t sop, f
 #define TH_B_SLOW_M(C, N) " add.u32 ad,%6," #C "1;\n ld.shared.f32 %4,[ad];\n mov.u32 %3," #C "3;\n" TH_LEAVE(C, N)
 #define TH_B_SLOW_I(C, N) " mov.b32 %4," #C "1;\n mov.u32 %3," #C "3;\n" TH_LEAVE(C, N)
 #define TH_B_END(C, N) " mov.u32 %3,0;\n bra DONE;\n"
+// x / y, y from the LDY before it (IEEE division: div.rn.f32)
+#define TH_B_DIV_A(C, N) TH_NEXT(N) " div.rn.f32 %0,%0,%5;\n" TH_GO(C, N)
+#define TH_B_DIV_M(C, N) TH_XM(C) TH_NEXT(N) " div.rn.f32 %0,t0,%5;\n" TH_GO(C, N)
+#define TH_B_DIV_I(C, N) TH_XI(C) TH_NEXT(N) " div.rn.f32 %0,t0,%5;\n" TH_GO(C, N)
 // sin / cos: the operand goes to t0, cf = 0 (sin) / 1 (cos: sin(x + pi/2), one quadrant on), then the common body
 #define TH_B_SIN_A(C, N) " mov.f32 t0,%0;\n mov.u32 cf,0;\n bra TRIG_" #C ";\n"
 #define TH_B_SIN_M(C, N) TH_XM(C) " mov.u32 cf,0;\n bra TRIG_" #C ";\n"
@@ -344,6 +356,9 @@ static __host__ __device__ MTGP_TH_INLINE float mtgp_run_threaded(mtgp_saddr ent
       case TH_SIN_M: acc = mtgp_sinf(M(w.a)); break;
       case TH_COS_A: acc = mtgp_cosf(acc); break;
       case TH_COS_M: acc = mtgp_cosf(M(w.a)); break;
+      case TH_DIV_A: acc = acc / yv; break;
+      case TH_DIV_M: acc = M(w.a) / yv; break;
+      case TH_DIV_I: acc = I(w.a) / yv; break;
       case TH_SLOW_A: acc = mtgp_th_slow_op(w.c, acc, yv); break;
       case TH_SLOW_M: acc = mtgp_th_slow_op(w.c, M(w.a), yv); break;
       case TH_SLOW_I: acc = mtgp_th_slow_op(w.c, I(w.a), yv); break;
