@@ -262,7 +262,13 @@ int mtgp_launch_pointwise(const mtgp_programs& progs, const int32_t* live, int P
   //   worst  : anything a max_nodes-row array can hold (long combs grown by mutation): one point per lane
   // (lengths are threaded-code instructions per tree, header and END included: MTGP_META_TH)
   const int bound = mtgp_tmp_bound(N), worst_instr = MTGP_TH_MAX_EXPAND * progs.lstride + 2;
-  const int t0 = bound < 4 ? bound : 4, i0 = worst_instr < 40 ? worst_instr : 40;
+#ifndef MTGP_PW_FAST_TMP
+#define MTGP_PW_FAST_TMP 4
+#endif
+#ifndef MTGP_PW_FAST_TH
+#define MTGP_PW_FAST_TH 40
+#endif
+  const int t0 = bound < MTGP_PW_FAST_TMP ? bound : MTGP_PW_FAST_TMP, i0 = worst_instr < MTGP_PW_FAST_TH ? worst_instr : MTGP_PW_FAST_TH;
   int rc = launch_pw<MTGP_PW_R>(pp, t0, i0, -1, -1, stream);
   if (rc != MTGP_OK || (t0 == bound && i0 == worst_instr)) return rc;
   const int t1 = bound < 8 ? bound : 8, i1 = worst_instr < 160 ? worst_instr : 160;

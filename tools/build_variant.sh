@@ -12,4 +12,4 @@ for o in api encode rollout rollout_rk pointwise select; do
   if [ "$o" == "$tu" ]; then objs="$objs /tmp/var_$name.o"; else objs="$objs ../build/mtgp_$o.o"; fi
 done
 nvcc -shared -o /root/repo/variants/libmtgp_$name.so $objs -gencode arch=compute_100a,code=sm_100a -lcudart
-cd /root/repo && python -m multitreegp_b200.sass_patch variants/libmtgp_$name.so 2>&1 | tail -1
+cd /root/repo && python -m multitreegp_b200.sass_patch variants/libmtgp_$name.so rollout pointwise 2>&1 | tail -1
