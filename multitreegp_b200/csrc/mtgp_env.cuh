@@ -53,7 +53,7 @@ constexpr int kMaxTrees = 32;
 // launch classes of the rollout kernels: programs with at most kFastTmp temporaries and kFastTh threaded
 // instructions per individual run with a small shared-memory footprint
 constexpr int kFastTmp = 8;
-constexpr int kFastTh = 96;
+constexpr int kFastTh = 136;  // full depth-6 trees (3 x 31 operators + the second readout copy) still fit; 32 CTAs x (6 KB + 1 KB reserved) per SM
 // worst case of the threaded form: every compact instruction expands to MTGP_TH_MAX_EXPAND, plus the header
 // and the ST per tree; the dynamic policy's readout is expanded twice
 __host__ __device__ inline int mtgp_worst_threaded(int T, int lstride) { return (T + 1) * (MTGP_TH_MAX_EXPAND * lstride + 2); }
@@ -337,6 +337,42 @@ __device__ __forceinline__ void sincos_checked(float x, float& s, float& c) {
   c = trig_pick(sk, ck, q + 1);
 }
 
+// Cold paths of the Acrobot functor, OUT OF LINE: they run when an angle has left the contract's fast ranges
+// (|theta| >= 4e4, |o + pi| >= 2 pi) -- practically never -- and would otherwise sit in the middle of the step
+// loop, whose instruction-cache footprint is what limits the kernel (profiles/r02_*: `no_instruction` stalls).
+#ifndef MTGP_COLD_NOINLINE
+#define MTGP_COLD_NOINLINE 0  // measured on C5: out of line 76.9 ms, inline 76.3 ms
+#endif
+#if MTGP_COLD_NOINLINE
+#define MTGP_COLD __noinline__
+#else
+#define MTGP_COLD __forceinline__
+#endif
+#ifndef MTGP_REACHED_FAST
+#define MTGP_REACHED_FAST 0  // measured on C5: no gain (fewer instructions, larger loop)
+#endif
+struct Trig5 { float s2, c2, c12, s1, c1h; };
+static __device__ MTGP_COLD Trig5 acrobot_trig_generic(float theta1, float theta2) {
+  const float half_pi = 1.57079637f;
+  Trig5 t;
+  int q;  // sin / cos of theta2 share one reduction (same bits as mtgp_sinf / mtgp_cosf)
+  const float r = mtgp_trig_reduce(theta2, &q);
+  const float sk = mtgp_sin_kernel(r), ck = mtgp_cos_kernel(r);
+  const float sv = (q & 1) ? ck : sk, cv = (q & 1) ? sk : ck;
+  t.s2 = (q & 2) ? -sv : sv;
+  t.c2 = ((q + 1) & 2) ? -cv : cv;
+  t.c12 = mtgp_cosf((theta1 + theta2) - half_pi);
+  t.s1 = mtgp_sinf(theta1);
+  t.c1h = mtgp_cosf(theta1 - half_pi);
+  return t;
+}
+static __device__ MTGP_COLD float wrap_generic(float o) {  // jnp.remainder(o + pi, 2 pi) - pi, any o
+  return mtgp_remainderf_py(o + 3.14159274f, 6.28318548f) - 3.14159274f;
+}
+static __device__ MTGP_COLD bool acrobot_reached_generic(float theta1, float theta2) {
+  return ((-mtgp_cosf(theta1)) - mtgp_cosf(theta1 + theta2)) > 1.5f;
+}
+
 // Loop-invariant sub-expressions of Acrobot.drift (acrobot.py:51-72), in the source's own grouping, so that
 // the drift is the same sequence of float32 operations whether they are computed per lane on the device or
 // once on the host (IEEE mul/add: same bits) for the trajectory-uniform-parameter kernels.
@@ -475,7 +511,7 @@ struct Env {
       } else {
 #pragma unroll
         for (int i = 0; i < 2; i++)
-          if (i < n_obs) y[i] = mtgp_remainderf_py(y[i] + pi, two_pi) - pi;
+          if (i < n_obs) y[i] = wrap_generic(y[i]);
       }
     }
   }
@@ -499,10 +535,8 @@ struct Env {
         s1 = sin_checked(theta1);
         c1h = cos_checked(theta1 - half_pi);
       } else {
-        sincos_contract(theta2, s2, c2);
-        c12 = mtgp_cosf((theta1 + theta2) - half_pi);
-        s1 = mtgp_sinf(theta1);
-        c1h = mtgp_cosf(theta1 - half_pi);
+        const Trig5 t = acrobot_trig_generic(theta1, theta2);
+        s2 = t.s2; c2 = t.c2; c12 = t.c12; s1 = t.s1; c1h = t.c1h;
       }
       const float d1 = AK(AK_D1A) + m2 * (AK(AK_D1B) + AK(AK_D1C) * c2) + moi1 + moi2;
       const float d2 = m2 * (AK(AK_D2A) + AK(AK_D2B) * c2) + moi2;
@@ -553,7 +587,18 @@ struct Env {
         if (!(qk > (float)fs_known)) sum = sum + c;
         return;
       }
-      const bool reached = ((-mtgp_cosf(xs[0])) - mtgp_cosf(xs[0] + xs[1])) > 1.5f;
+      // reached = -cos(theta1) - cos(theta1 + theta2) > 1.5 (acrobot.py:79).  A lane whose saved state is the inf
+      // pre-fill (its event has fired) gives cos(inf) = NaN and "not reached" -- no reason to send the whole warp
+      // through the Payne-Hanek call for it: when every lane is either non-finite or small, the branch-free path.
+      const bool nonfin = nonfinite_cmp(xs[0]) | nonfinite_cmp(xs[1]);
+      const bool small = fabsf(xs[0]) < 40000.0f && fabsf(xs[1]) < 40000.0f;
+      bool reached;
+      if (MTGP_REACHED_FAST && __all_sync(__activemask(), nonfin || small)) {  // (the adaptive kernel calls this under a per-lane condition)
+        const float a0 = nonfin ? 0.0f : xs[0], a1 = nonfin ? 0.0f : xs[0] + xs[1];
+        reached = !nonfin && (((-cos_checked(a0)) - cos_checked(a1)) > 1.5f);
+      } else {
+        reached = acrobot_reached_generic(xs[0], xs[1]);
+      }
       if (!(qk > 0.0f)) sum0 = sum0 + c;
       if (fs < 0) {
         if (reached) {

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kPwWarps * 32, MTGP_PW_MIN_CTAS) k_pointwise(c
       const uint2* src = prog_s + (size_t)gt * P.pstride;
       mtgp_tinstr* dst = th_s + (size_t)gt * P.pstride;
       int m = 1;
-      for (int i = 0; i < n; i++) m += mtgp_th_expand<1024, false>(src[i], dst + m);
+      for (int i = 0; i < n; i++) m += mtgp_th_expand<1024, false, true>(src[i], dst + m);
       mtgp_th_link(dst, m - 1);
     }
     __syncthreads();

@@ -343,12 +343,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
               sr_total = sr_total + row;
             } else {
               float ys[DR];
-              float nzk[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-              if (NOISE == 1) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(nz_base + (size_t)(P.cap_steps + k) * nzs));
-                nzk[0] = v.x; nzk[1] = v.y; nzk[2] = v.z; nzk[3] = v.w;
+#pragma unroll
+              for (int i = 0; i < DR; i++) ys[i] = 0.0f;
+              // the observation at the save point is needed only when the readout reads it or the caller asked for
+              // it; the dynamic policy's readout of the notebooks reads the latent state alone
+#ifndef MTGP_SAVE_SKIP_YS
+#define MTGP_SAVE_SKIP_YS 1
+#endif
+              const bool need_ys = !MTGP_SAVE_SKIP_YS || (KIND == MTGP_EVAL_STATIC) || readout_sees_y || (TRAJ_OUT && P.ys_o != nullptr);
+              if (need_ys) {
+                float nzk[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                if (NOISE == 1) {
+                  const float4 v = __ldg(reinterpret_cast<const float4*>(nz_base + (size_t)(P.cap_steps + k) * nzs));
+                  nzk[0] = v.x; nzk[1] = v.y; nzk[2] = v.z; nzk[3] = v.w;
+                }
+                env.template f_obs<NOISE, false>(tk, xs, ys, n_obs, P.obs_noise, P.partitionable, nzk);
               }
-              env.template f_obs<NOISE, false>(tk, xs, ys, n_obs, P.obs_noise, P.partitionable, nzk);
               if (KIND == MTGP_EVAL_STATIC || readout_sees_y) {
 #pragma unroll
                 for (int i = 0; i < D; i++)

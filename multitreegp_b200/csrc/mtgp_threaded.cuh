@@ -67,7 +67,13 @@ struct __align__(16) mtgp_tinstr {
 // until mtgp_th_link() rewrites it.  Returns the count.
 // SLOT_BYTES: bytes between value-file slots (128 for one value per lane, 1024 for the pointwise kernel's 8);
 // TRIG_INBLOCK: sin / cos have in-block handlers (the rollout kernels) or leave the block like the other slow operators.
-template <int SLOT_BYTES = 128, bool TRIG_INBLOCK = true>
+// DIV_INBLOCK: x / y has in-block handlers.  Only the pointwise kernel uses them: in the one-value block a
+// div.rn.f32 brings ptxas' division subroutine into the interpreter function, which then is no leaf any more
+// and costs the rollout kernels registers around every call (measured: 77 -> 83 ms on the C5 workload).
+#ifndef MTGP_TH_DIV_INBLOCK
+#define MTGP_TH_DIV_INBLOCK 0
+#endif
+template <int SLOT_BYTES = 128, bool TRIG_INBLOCK = true, bool DIV_INBLOCK = (MTGP_TH_DIV_INBLOCK != 0)>
 __host__ __device__ __forceinline__ int mtgp_th_expand(uint2 c, mtgp_tinstr* out) {
   const uint32_t op = c.x & 15u, st = (c.x >> 8) & 0xFFu;
   const uint32_t xk = (c.x >> 4) & 3u, yk = (c.x >> 6) & 3u, xs = ((c.x >> 16) & 0xFFu) * (uint32_t)SLOT_BYTES,
@@ -132,7 +138,7 @@ __host__ __device__ __forceinline__ int mtgp_th_expand(uint2 c, mtgp_tinstr* out
   }
   if (op == X_LOAD) { put(n++, TH_LDY_I, 0, 0x80000000u, 0); }  // x + (-0.0) == x
   else if (binary) put(n++, yk == OK_ACC ? TH_LDY_A : (yk == OK_MEM ? TH_LDY_M : TH_LDY_I), 0, yk == OK_MEM ? ys : imm, 0);
-  if (op == X_DIV)  // x / y with y loaded by the LDY before it: in-block (IEEE div.rn)
+  if (DIV_INBLOCK && op == X_DIV)  // x / y with y loaded by the LDY before it: in-block (IEEE div.rn)
     put(n++, xk == OK_ACC ? TH_DIV_A : (xk == OK_MEM ? TH_DIV_M : TH_DIV_I), xk == OK_MEM ? xs : imm, 0, 0);
   else
     put(n++, xk == OK_ACC ? TH_SLOW_A : (xk == OK_MEM ? TH_SLOW_M : TH_SLOW_I), xk == OK_MEM ? xs : imm, 0, sop);
@@ -231,10 +237,16 @@ static __host__ __device__ __forceinline__ float mtgp_th_slow_op(uint32_t sop, f
 #define TH_B_SLOW_M(C, N) " add.u32 ad,%6," #C "1;\n ld.shared.f32 %4,[ad];\n mov.u32 %3," #C "3;\n" TH_LEAVE(C, N)
 #define TH_B_SLOW_I(C, N) " mov.b32 %4," #C "1;\n mov.u32 %3," #C "3;\n" TH_LEAVE(C, N)
 #define TH_B_END(C, N) " mov.u32 %3,0;\n bra DONE;\n"
-// x / y, y from the LDY before it (IEEE division: div.rn.f32)
+// x / y, y from the LDY before it (IEEE division: div.rn.f32) -- see MTGP_TH_DIV_INBLOCK
+#if MTGP_TH_DIV_INBLOCK
 #define TH_B_DIV_A(C, N) TH_NEXT(N) " div.rn.f32 %0,%0,%5;\n" TH_GO(C, N)
 #define TH_B_DIV_M(C, N) TH_XM(C) TH_NEXT(N) " div.rn.f32 %0,t0,%5;\n" TH_GO(C, N)
 #define TH_B_DIV_I(C, N) TH_XI(C) TH_NEXT(N) " div.rn.f32 %0,t0,%5;\n" TH_GO(C, N)
+#else  // never emitted by the expansion; the labels exist because the jump table covers the whole enumeration
+#define TH_B_DIV_A(C, N) " mov.u32 %3,0xFFFF;\n bra DONE;\n"
+#define TH_B_DIV_M(C, N) " mov.u32 %3,0xFFFF;\n bra DONE;\n"
+#define TH_B_DIV_I(C, N) " mov.u32 %3,0xFFFF;\n bra DONE;\n"
+#endif
 // sin / cos: the operand goes to t0, cf = 0 (sin) / 1 (cos: sin(x + pi/2), one quadrant on), then the common body
 #define TH_B_SIN_A(C, N) " mov.f32 t0,%0;\n mov.u32 cf,0;\n bra TRIG_" #C ";\n"
 #define TH_B_SIN_M(C, N) TH_XM(C) " mov.u32 cf,0;\n bra TRIG_" #C ";\n"
