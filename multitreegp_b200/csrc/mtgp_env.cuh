@@ -183,6 +183,7 @@ static __device__ __noinline__ int th_build_chain(const uint32_t* meta_ind, cons
   }
   dst[m].next = TH_END; dst[m].a = 0; dst[m].b = 0; dst[m].c = 0;
   m++;
+  mtgp_th_fuse(dst, m - 1);
   mtgp_th_link(dst, m - 1);
   return m;
 }

@@ -238,7 +238,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
           for (int j = 0; j < NL; j++) bad |= !mtgp_isfinitef(lb[(slot_state + j) * 32]);
           ev_old_bad = bad;  // Event: cond_fn at (t0, y0)
         }
-        bool alive = true;
+        // a lane beyond B shadows a valid trajectory and never integrates: "dead" from the start, so that the
+        // loop's one ballot covers validity too (its outputs are discarded below)
+        bool alive = lane_valid;
         float tprev = t0, tnext = t0 + P.dt0;
         tnext = tnext < t1 ? tnext : t1;
         int steps = 0, k = 0;
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MTGP_ROLLOUT_MIN_CTAS) k_ro
         // remaining save points are emitted from the inf pre-fill of SaveAt -- by the same code.
         while (k < K) {
           const bool stepping = (tprev < t1) && (steps < P.max_steps) &&
-                                (__ballot_sync(0xFFFFFFFFu, alive && lane_valid) != 0u);
+                                (__ballot_sync(0xFFFFFFFFu, alive) != 0u);
           float save_until = mtgp_inff();
           if (stepping) {
             const float dt = tnext - tprev;
@@ -680,6 +682,11 @@ int mtgp_launch_rollout(const mtgp_programs& progs, const int32_t* live, int P, 
     if (upar) acrobot_derive(d.params_host[0], d.params_host[1], d.params_host[2], d.params_host[3], rp.envc);
   }
 #define DISPATCH(KIND, ENV) return launch_kind_env<KIND, ENV>(rp, progs.tmp_base, bound, noise_ws, upar, stream)
+#ifdef MTGP_DEV_ONLY_DYNAMIC_ACROBOT  // tuning builds (tools/build_variant.sh): one evaluator kind and environment, a fraction of the compile time
+  if (d.kind == MTGP_EVAL_DYNAMIC && d.env_id == MTGP_ENV_ACROBOT) DISPATCH(MTGP_EVAL_DYNAMIC, MTGP_ENV_ACROBOT);
+  mtgp_set_error("tuning build: dynamic-policy Acrobot only");
+  return MTGP_ERR_UNSUPPORTED;
+#else
   if (d.kind == MTGP_EVAL_SR) DISPATCH(MTGP_EVAL_SR, MTGP_ENV_NONE);
   if (d.kind == MTGP_EVAL_STATIC) {
     if (d.env_id == MTGP_ENV_ACROBOT) DISPATCH(MTGP_EVAL_STATIC, MTGP_ENV_ACROBOT);
@@ -691,7 +698,8 @@ int mtgp_launch_rollout(const mtgp_programs& progs, const int32_t* live, int P, 
     if (d.env_id == MTGP_ENV_HARMONIC) DISPATCH(MTGP_EVAL_DYNAMIC, MTGP_ENV_HARMONIC);
     if (d.env_id == MTGP_ENV_REACTOR) DISPATCH(MTGP_EVAL_DYNAMIC, MTGP_ENV_REACTOR);
   }
-#undef DISPATCH
   mtgp_set_error("unknown evaluator kind %d / environment %d", d.kind, d.env_id);
   return MTGP_ERR_INVALID_ARGUMENT;
+#endif
+#undef DISPATCH
 }

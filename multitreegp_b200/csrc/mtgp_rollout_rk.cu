@@ -81,11 +81,42 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
     warp_stage_programs(P, ind, lane, bar, bar_phase, wa);
     float* lb = wa.vf + lane;
     const mtgp_saddr lbytes = mtgp_saddr_of(lb);
-    for (int t = lane; t < P.T; t += 32) {
-      int off = 0;
-      for (int q = 0; q < t; q++) off += (int)MTGP_META_TH(P.meta[(size_t)ind * P.T + q]);
-      wa.woff[t] = off;
-      th_build_chain(P.meta + (size_t)ind * P.T, wa.prog_s, wa.th + off, t, 1, -1, -1, -1);
+    // Dynamic policy: when the readout reads neither an observation nor the control slot (the notebooks'
+    // variable lists: it reads the latent state alone), one interpreter call per vector-field evaluation runs
+    // the whole chain [readout -> slot_u][state eq j -> slot_f + j] as in k_rollout (three calls otherwise:
+    // the readout has to see zeros there, dynamic_evaluate.py:113).  slot_f: the latent part of the SV array,
+    // dead outside the save-point loop.
+    bool chain = false;
+    if (KIND == MTGP_EVAL_DYNAMIC) {
+      const int n_obs_rt = P.n_obs;
+      const uint32_t soff = compact_offset(P.meta + (size_t)ind * P.T, P.state_size);
+      const int n = (int)MTGP_META_N(P.meta[(size_t)ind * P.T + P.state_size]);
+      bool reads = false;
+      for (int i = lane; i < n; i += 32) {
+        const uint2 c = wa.prog_s[soff + i];
+        const uint32_t xk = (c.x >> 4) & 3u, yk = (c.x >> 6) & 3u, xs = (c.x >> 16) & 0xFFu, ys = c.x >> 24;
+        reads |= (xk == OK_MEM && ((int)xs < n_obs_rt || (int)xs == P.slot_u)) ||
+                 (yk == OK_MEM && ((int)ys < n_obs_rt || (int)ys == P.slot_u));
+      }
+      chain = __any_sync(0xFFFFFFFFu, reads) == 0;
+    }
+    if (chain) {
+      if (lane == 0) {
+        const uint32_t* mi = P.meta + (size_t)ind * P.T;
+        const int Dc = (KIND == MTGP_EVAL_SR) ? 0 : EnvDim<ENV>::D;
+        const int slot_f = P.slot_rk + 11 * (Dc + P.n_latent) + Dc;
+        const int off = th_build_chain(mi, wa.prog_s, wa.th, P.state_size, 1, -1, -1, -1);  // stand-alone readout (save points)
+        wa.woff[P.state_size] = 0;
+        wa.woff[0] = off;
+        th_build_chain(mi, wa.prog_s, wa.th + off, 0, P.state_size, slot_f, P.state_size, P.slot_u);
+      }
+    } else {
+      for (int t = lane; t < P.T; t += 32) {
+        int off = 0;
+        for (int q = 0; q < t; q++) off += (int)MTGP_META_TH(P.meta[(size_t)ind * P.T + q]);
+        wa.woff[t] = off;
+        th_build_chain(P.meta + (size_t)ind * P.T, wa.prog_s, wa.th + off, t, 1, -1, -1, -1);
+      }
     }
     __syncwarp();
 
@@ -98,6 +129,7 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
     const bool dopri = P.solver == MTGP_SOLVER_DOPRI5, pid = P.controller == MTGP_CONTROLLER_PID;
     const mtgp_saddr th_s = mtgp_saddr_of(wa.th);
     const mtgp_saddr prog_readout = th_s + 16u * (uint32_t)wa.woff[(KIND == MTGP_EVAL_DYNAMIC) ? NL : 0];
+    const mtgp_saddr prog_chain = th_s + 16u * (uint32_t)wa.woff[0];  // (chain only)
     // solver arrays in the value file: component i of array a is slot slot_rk + a*DT + i
     float* const Y = lb + (size_t)(P.slot_rk + 0 * DT) * 32;
     float* const Y1 = lb + (size_t)(P.slot_rk + 1 * DT) * 32;
@@ -125,7 +157,7 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
 #pragma unroll
           for (int i = 0; i < D; i++) x[i] = src[i * 32];
           env.template f_obs<NOISE ? 2 : 0>(t, x, y, n_obs, P.obs_noise, P.partitionable, nullptr);
-          if (KIND == MTGP_EVAL_STATIC) {
+          if (KIND == MTGP_EVAL_STATIC || chain) {
 #pragma unroll
             for (int i = 0; i < D; i++)
               if (i < n_obs) lb[i * 32] = y[i];
@@ -135,14 +167,20 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
               if (i < n_obs) lb[i * 32] = 0.0f;
             lb[P.slot_u * 32] = 0.0f;
           }
-          const float u = mtgp_run_threaded(prog_readout, lbytes);
+          float u;
+          if (chain) {  // readout and state equations in one call; the readout's ST leaves u in its slot
+            mtgp_run_threaded(prog_chain, lbytes);
+            u = lb[P.slot_u * 32];
+          } else {
+            u = mtgp_run_threaded(prog_readout, lbytes);
+          }
           env.template drift<false>(x, u, dx, P);
 #pragma unroll
           for (int i = 0; i < D; i++) {
             dst[i * 32] = scale * dx[i];
             if (raw) raw[i * 32] = dx[i];
           }
-          if (KIND == MTGP_EVAL_DYNAMIC) {
+          if (KIND == MTGP_EVAL_DYNAMIC && !chain) {
 #pragma unroll
             for (int i = 0; i < D; i++)
               if (i < n_obs) lb[i * 32] = y[i];
@@ -150,7 +188,7 @@ __global__ void __launch_bounds__(kRkWarps * 32, MTGP_RK_MIN_CTAS) k_rollout_rk(
           }
         }
         for (int j = 0; j < NL; j++) {
-          const float f = mtgp_run_threaded(th_s + 16u * (uint32_t)wa.woff[j], lbytes);
+          const float f = chain ? SV[(D + j) * 32] : mtgp_run_threaded(th_s + 16u * (uint32_t)wa.woff[j], lbytes);
           dst[(D + j) * 32] = scale * f;
           if (raw) raw[(D + j) * 32] = f;
         }
@@ -452,10 +490,14 @@ int launch_rk_class(RolloutParams rp, int tmp_base, int n_tmp, int th_cap, int w
 
 template <int KIND, int ENV>
 int launch_rk(RolloutParams rp, int tmp_base, int bound, cudaStream_t stream) {
+  // The adaptive kernel's value file is large (12 solver arrays), shared memory decides how many warps an SM holds,
+  // and the kernel is latency-bound: its fast class is provisioned for the programs of ordinary notebook trees
+  // (kRkFastTh threaded instructions: 16 resident warps per SM on the DynamicPolicy shapes instead of 14).
+  constexpr int kRkFastTh = 64;
   const int worst_th = mtgp_worst_threaded(rp.T, rp.lstride);
-  const bool all_fast = (bound <= kFastTmp) && (worst_th <= kFastTh);
+  const bool all_fast = (bound <= kFastTmp) && (worst_th <= kRkFastTh);
   rp.fast_tmp = all_fast ? bound : kFastTmp;
-  rp.fast_th = all_fast ? worst_th : kFastTh;
+  rp.fast_th = all_fast ? worst_th : kRkFastTh;
   int rc = launch_rk_class<KIND, ENV>(rp, tmp_base, rp.fast_tmp, rp.fast_th, 1, stream);
   if (rc == MTGP_OK && !all_fast) rc = launch_rk_class<KIND, ENV>(rp, tmp_base, bound, worst_th, 0, stream);
   return rc;

@@ -30,6 +30,12 @@
 
 #include "mtgp_program.cuh"
 
+#ifndef MTGP_TH_FUSE
+#define MTGP_TH_FUSE 0  // pair fusion (see MTGP_TH_FUSED): measured slower, off
+#endif
+#ifndef MTGP_TH_SETS
+#define MTGP_TH_SETS 2  // register sets of the instruction fetch: 2 = every handler exists twice (a / b), 1 = one copy (half the code)
+#endif
 // handler lists: arithmetic / load forms exist with and without a fused store (..._ST)
 #define MTGP_TH_ARITH(X) \
   X(ADD_AM) X(ADD_AI) X(ADD_MM) X(ADD_MI) X(ADD_AA) \
@@ -38,7 +44,24 @@
   X(LOAD_M) X(LOAD_I)
 #define MTGP_TH_OTHER(X) \
   X(ST) X(LDY_M) X(LDY_I) X(LDY_A) X(SLOW_A) X(SLOW_M) X(SLOW_I) X(SIN_A) X(SIN_M) X(COS_A) X(COS_M) \
-  X(DIV_A) X(DIV_M) X(DIV_I) X(END)
+  X(DIV_A) X(DIV_M) X(DIV_I) X(END) MTGP_TH_OTHER_F(X)
+// FUSED PAIRS (mtgp_th_fuse): two consecutive operator nodes of an accumulator chain behind ONE dispatch.
+// The head is a generic  r = fma(x, P, Q)  over x in {accumulator, memory} and y in {immediate, memory}:
+//   x + y = fma(x, 1, y)    x * y = fma(x, y, -0)    c - x = fma(x, -1, c)      -- each EXACTLY the IEEE result
+// of the plain operator (one rounding of the same exact value; (+0) + (-0) = +0 keeps the product's zero sign);
+// with an immediate y the pair (P, Q) is written at fusion time, with a memory y it is selected by a mask word
+// (two LOP3).  The tail is the same form on the accumulator.  F_<head: x y>_<tail: y>, each with a fused store.
+// MEASURED (C5 workload, one B200): fusing 29 % of the dispatches this way makes the kernel SLOWER -- 77 -> 106 ms;
+// the 32 extra handlers alone, never executed, cost 77 -> 85 ms.  The interpreter's hot code already fills the
+// 32 KB instruction cache; more handlers mean more misses per dispatch than the saved dispatches are worth.
+// Compiled out by default (MTGP_TH_FUSE = 0); the host tests build it in (tests/hostlib) to keep the arithmetic pinned.
+#if MTGP_TH_FUSE
+#define MTGP_TH_OTHER_F(X) X(FDATA)
+#define MTGP_TH_FUSED(X) X(F_AI_I) X(F_AI_M) X(F_MI_I) X(F_MI_M) X(F_AM_I) X(F_AM_M) X(F_MM_I) X(F_MM_M)
+#else
+#define MTGP_TH_OTHER_F(X)
+#define MTGP_TH_FUSED(X)
+#endif
 
 enum mtgp_th : uint32_t {
 #define X(n) TH_##n, TH_##n##_ST,
@@ -46,6 +69,9 @@ enum mtgp_th : uint32_t {
 #undef X
 #define X(n) TH_##n,
   MTGP_TH_OTHER(X)
+#undef X
+#define X(n) TH_##n, TH_##n##_ST,
+  MTGP_TH_FUSED(X)
 #undef X
   TH_COUNT
 };
@@ -159,10 +185,64 @@ __host__ __device__ __forceinline__ int mtgp_th_expand(uint2 c, mtgp_tinstr* out
 
 // header + n instructions (prog[0] = header, prog[1..n] = instructions with their OWN handler in .next):
 // rewrite .next to the successor's handler.
+// A fused head (mtgp_th_fuse) occupies two slots -- its own and a data slot -- and names the handler of the slot after both.
 __host__ __device__ __forceinline__ void mtgp_th_link(mtgp_tinstr* prog, int n) {
   prog[0].a = 0; prog[0].b = 0; prog[0].c = 0;
-  for (int j = 0; j < n; j++) prog[j].next = prog[j + 1].next;
+  for (int j = 0; j < n; j++) {
+#if MTGP_TH_FUSE
+    const bool fused = j > 0 && prog[j].next >= TH_F_AI_I && prog[j].next < TH_COUNT;
+#else
+    const bool fused = false;
+#endif
+    prog[j].next = prog[j + (fused ? 2 : 1)].next;
+  }
   prog[n].next = TH_END;
+}
+
+// Peephole over prog[1 .. n-1] (instructions with their OWN handler in .next, before mtgp_th_link): a store-free
+// + / * / c-x node followed by an accumulator-form + / * / c-x node becomes one fused instruction:
+//   head slot: .a = x offset (M heads), .b = P | y offset, .c = Q | op mask (0 = add, ~0 = mul)
+//   data slot: .a = P | y offset, .b = Q | op mask, .c = store offset
+__host__ __device__ __forceinline__ void mtgp_th_fuse(mtgp_tinstr* prog, int n) {
+#if MTGP_TH_FUSE
+  const uint32_t ONE = 0x3F800000u, MONE = 0xBF800000u, NZ = 0x80000000u;
+  for (int j = 1; j + 1 < n; j++) {
+    const uint32_t h = prog[j].next, t = prog[j + 1].next;
+    if (t >= TH_ST) continue;
+    const uint32_t tt = t & ~1u, st = t & 1u;
+    int head, tail;
+    uint32_t hb = prog[j].b, hc = 0, ta, tb;
+    switch (h) {  // (even handler = no store)
+      case TH_ADD_AI: head = 0; hc = hb; hb = ONE; break;
+      case TH_MUL_AI: head = 0; hc = NZ; break;
+      case TH_RSB_AI: head = 0; hc = hb; hb = MONE; break;
+      case TH_ADD_MI: head = 1; hc = hb; hb = ONE; break;
+      case TH_MUL_MI: head = 1; hc = NZ; break;
+      case TH_RSB_MI: head = 1; hc = hb; hb = MONE; break;
+      case TH_ADD_AM: head = 2; hc = 0u; break;
+      case TH_MUL_AM: head = 2; hc = 0xFFFFFFFFu; break;
+      case TH_ADD_MM: head = 3; hc = 0u; break;
+      case TH_MUL_MM: head = 3; hc = 0xFFFFFFFFu; break;
+      default: continue;
+    }
+    const uint32_t yb = prog[j + 1].b;
+    switch (tt) {
+      case TH_ADD_AI: tail = 0; ta = ONE; tb = yb; break;
+      case TH_MUL_AI: tail = 0; ta = yb; tb = NZ; break;
+      case TH_RSB_AI: tail = 0; ta = MONE; tb = yb; break;
+      case TH_ADD_AM: tail = 1; ta = yb; tb = 0u; break;
+      case TH_MUL_AM: tail = 1; ta = yb; tb = 0xFFFFFFFFu; break;
+      default: continue;
+    }
+    prog[j].next = TH_F_AI_I + 2u * (uint32_t)(2 * head + tail) + st;
+    prog[j].b = hb;
+    prog[j].c = hc;
+    prog[j + 1].next = TH_FDATA;
+    prog[j + 1].a = ta;
+    prog[j + 1].b = tb;  // .c keeps the store offset
+    j++;
+  }
+#endif
 }
 
 // slow operators: ordinary C on the contract's functions
@@ -192,11 +272,21 @@ static __host__ __device__ __forceinline__ float mtgp_th_slow_op(uint32_t sop, f
 // Macro parameters C / N: the register set of the current / next instruction (tokens a, b).
 #define TH_PARNUM_a "0"
 #define TH_PARNUM_b "1"
+#if MTGP_TH_SETS == 1
+// one register set: the fields a handler still needs after the fetch of its successor (the successor's handler
+// index, the store offset) are saved first; ptxas folds the copies into the jump-table load / the address add
+#define TH_NEXT(N) " mov.u32 nx," #N "0;\n add.u32 %1,%1,16;\n ld.shared.v4.u32 {" #N "0," #N "1," #N "2," #N "3},[%1];\n"
+#else
 #define TH_NEXT(N) " add.u32 %1,%1,16;\n ld.shared.v4.u32 {" #N "0," #N "1," #N "2," #N "3},[%1];\n"
+#endif
 #ifdef MTGP_TH_CENTRAL
 #define TH_GO(C, N) " bra DISP_" #C ";\n"               // shared dispatch of this register set
 #else
+#if MTGP_TH_SETS == 1
+#define TH_GO(C, N) " brx.idx nx, TBLa;\n"
+#else
 #define TH_GO(C, N) " brx.idx " #C "0, TBL" #N ";\n"    // own dispatch (its jump-table copy is merged by sass_patch.py)
+#endif
 #endif
 #define TH_XM(C) " add.u32 ad,%6," #C "1;\n ld.shared.f32 t0,[ad];\n"
 #define TH_YM(C) " add.u32 ae,%6," #C "2;\n ld.shared.f32 t1,[ae];\n"
@@ -205,9 +295,13 @@ static __host__ __device__ __forceinline__ float mtgp_th_slow_op(uint32_t sop, f
 #define TH_NONE(C) ""
 #define TH_XMYM(C) TH_XM(C) TH_YM(C)
 #define TH_XMYI(C) TH_XM(C) TH_YI(C)
-#define TH_STORE(C) " add.u32 ad,%6," #C "3;\n st.shared.f32 [ad],%0;\n"
-#define TH_NOSTORE(C) ""
-#define TH_OP(PRE, OP, X, Y, C, N, ST) PRE(C) TH_NEXT(N) " " OP " %0," X "," Y ";\n" ST(C) TH_GO(C, N)
+// a fused store: the address is formed before the successor is fetched (the fetch may overwrite the fields)
+#define TH_STORE(C) " add.u32 ad,%6," #C "3;\n st.shared.f32 [ad],%0;\n"  // address and store in one place (handlers that fetch afterwards)
+#define TH_STORE_A(C) " add.u32 sa,%6," #C "3;\n"
+#define TH_STORE_D " st.shared.f32 [sa],%0;\n"
+#define TH_NOSTORE_A(C) ""
+#define TH_NOSTORE_D ""
+#define TH_OP(PRE, OP, X, Y, C, N, ST) PRE(C) ST##_A(C) TH_NEXT(N) " " OP " %0," X "," Y ";\n" ST##_D TH_GO(C, N)
 
 #define TH_B_ADD_AM(C, N, ST) TH_OP(TH_YM, "add.rn.f32", "%0", "t1", C, N, ST)
 #define TH_B_ADD_AI(C, N, ST) TH_OP(TH_YI, "add.rn.f32", "%0", "t1", C, N, ST)
@@ -224,10 +318,10 @@ static __host__ __device__ __forceinline__ float mtgp_th_slow_op(uint32_t sop, f
 #define TH_B_RSB_AI(C, N, ST) TH_OP(TH_YI, "sub.rn.f32", "t1", "%0", C, N, ST)
 #define TH_B_SUB_MM(C, N, ST) TH_OP(TH_XMYM, "sub.rn.f32", "t0", "t1", C, N, ST)
 #define TH_B_RSB_MI(C, N, ST) TH_OP(TH_XMYI, "sub.rn.f32", "t1", "t0", C, N, ST)
-#define TH_B_LOAD_M(C, N, ST) TH_XM(C) TH_NEXT(N) " mov.f32 %0,t0;\n" ST(C) TH_GO(C, N)
-#define TH_B_LOAD_I(C, N, ST) TH_XI(C) TH_NEXT(N) " mov.f32 %0,t0;\n" ST(C) TH_GO(C, N)
+#define TH_B_LOAD_M(C, N, ST) TH_XM(C) ST##_A(C) TH_NEXT(N) " mov.f32 %0,t0;\n" ST##_D TH_GO(C, N)
+#define TH_B_LOAD_I(C, N, ST) TH_XI(C) ST##_A(C) TH_NEXT(N) " mov.f32 %0,t0;\n" ST##_D TH_GO(C, N)
 
-#define TH_B_ST(C, N) TH_NEXT(N) TH_STORE(C) TH_GO(C, N)
+#define TH_B_ST(C, N) TH_STORE(C) TH_NEXT(N) TH_GO(C, N)
 #define TH_B_LDY_M(C, N) " add.u32 ae,%6," #C "2;\n ld.shared.f32 %5,[ae];\n" TH_NEXT(N) TH_GO(C, N)
 #define TH_B_LDY_I(C, N) " mov.b32 %5," #C "2;\n" TH_NEXT(N) TH_GO(C, N)
 #define TH_B_LDY_A(C, N) " mov.f32 %5,%0;\n" TH_NEXT(N) TH_GO(C, N)
@@ -247,6 +341,36 @@ static __host__ __device__ __forceinline__ float mtgp_th_slow_op(uint32_t sop, f
 #define TH_B_DIV_M(C, N) " mov.u32 %3,0xFFFF;\n bra DONE;\n"
 #define TH_B_DIV_I(C, N) " mov.u32 %3,0xFFFF;\n bra DONE;\n"
 #endif
+#define TH_B_FDATA(C, N) " mov.u32 %3,0xFFFF;\n bra DONE;\n"  // a data slot is never dispatched
+// fused pairs: the data slot goes to the OTHER register set, the instruction after it to this handler's own
+// set once the head has consumed its fields, and execution continues in the same set (no extra registers:
+// the interpreter's register budget is the rollout kernels' -- a larger one makes the caller spill around every call)
+#define TH_F_DATA(N) " ld.shared.v4.u32 {" #N "0," #N "1," #N "2," #N "3},[%1+16];\n"
+#define TH_F_NEXT(C) " mov.u32 nx," #C "0;\n add.u32 %1,%1,32;\n ld.shared.v4.u32 {" #C "0," #C "1," #C "2," #C "3},[%1];\n"
+#define TH_F_SEL(M, K) " lop3.b32 fp," M "," K ",0x3F800000,0xE2;\n lop3.b32 fq," M "," K ",0x80000000,0xB8;\n"  // K ? (m, -0) : (1, m)
+#define TH_FH_PRE_AI(C) ""
+#define TH_FH_PRE_MI(C) " add.u32 ad,%6," #C "1;\n ld.shared.b32 m0,[ad];\n"
+#define TH_FH_PRE_AM(C) " add.u32 ae,%6," #C "2;\n ld.shared.b32 m1,[ae];\n"
+#define TH_FH_PRE_MM(C) TH_FH_PRE_MI(C) TH_FH_PRE_AM(C)
+#define TH_FH_OP_AI(C) " mov.b32 fp," #C "2;\n mov.b32 fq," #C "3;\n fma.rn.f32 %0,%0,fp,fq;\n"
+#define TH_FH_OP_MI(C) " mov.b32 fp," #C "2;\n mov.b32 fq," #C "3;\n fma.rn.f32 %0,m0,fp,fq;\n"
+#define TH_FH_OP_AM(C) " mov.b32 fk," #C "3;\n" TH_F_SEL("m1", "fk") " fma.rn.f32 %0,%0,fp,fq;\n"
+#define TH_FH_OP_MM(C) " mov.b32 fk," #C "3;\n" TH_F_SEL("m1", "fk") " fma.rn.f32 %0,m0,fp,fq;\n"
+#define TH_FT_I(N) " mov.b32 fp," #N "1;\n mov.b32 fq," #N "2;\n fma.rn.f32 %0,%0,fp,fq;\n"
+#define TH_FT_M(N) " add.u32 ae,%6," #N "1;\n ld.shared.b32 m1,[ae];\n mov.b32 fk," #N "2;\n" TH_F_SEL("m1", "fk") " fma.rn.f32 %0,%0,fp,fq;\n"
+#define TH_F_STORE(N) " add.u32 ad,%6," #N "3;\n st.shared.f32 [ad],%0;\n"
+#define TH_F_OP(H, T, C, N, ST) \
+  TH_F_DATA(N) TH_FH_PRE_##H(C) TH_FH_OP_##H(C) TH_F_NEXT(C) TH_FT_##T(N) ST(N) " brx.idx nx, TBL" #C ";\n"
+#define TH_F_ST_TH_STORE(N) TH_F_STORE(N)
+#define TH_F_ST_TH_NOSTORE(N) ""
+#define TH_B_F_AI_I(C, N, ST) TH_F_OP(AI, I, C, N, TH_F_ST_##ST)
+#define TH_B_F_AI_M(C, N, ST) TH_F_OP(AI, M, C, N, TH_F_ST_##ST)
+#define TH_B_F_MI_I(C, N, ST) TH_F_OP(MI, I, C, N, TH_F_ST_##ST)
+#define TH_B_F_MI_M(C, N, ST) TH_F_OP(MI, M, C, N, TH_F_ST_##ST)
+#define TH_B_F_AM_I(C, N, ST) TH_F_OP(AM, I, C, N, TH_F_ST_##ST)
+#define TH_B_F_AM_M(C, N, ST) TH_F_OP(AM, M, C, N, TH_F_ST_##ST)
+#define TH_B_F_MM_I(C, N, ST) TH_F_OP(MM, I, C, N, TH_F_ST_##ST)
+#define TH_B_F_MM_M(C, N, ST) TH_F_OP(MM, M, C, N, TH_F_ST_##ST)
 // sin / cos: the operand goes to t0, cf = 0 (sin) / 1 (cos: sin(x + pi/2), one quadrant on), then the common body
 #define TH_B_SIN_A(C, N) " mov.f32 t0,%0;\n mov.u32 cf,0;\n bra TRIG_" #C ";\n"
 #define TH_B_SIN_M(C, N) TH_XM(C) " mov.u32 cf,0;\n bra TRIG_" #C ";\n"
@@ -281,10 +405,15 @@ static __host__ __device__ __forceinline__ float mtgp_th_slow_op(uint32_t sop, f
 #define TH_LABELS_ARITH_b(n) "H_" #n "_b, H_" #n "_ST_b, "
 #define TH_LABELS_OTHER_a(n) "H_" #n "_a, "
 #define TH_LABELS_OTHER_b(n) "H_" #n "_b, "
+#if MTGP_TH_SETS == 1
+#define TH_CODE_ARITH(n) "H_" #n "_a:\n" TH_B_##n(a, a, TH_NOSTORE) "H_" #n "_ST_a:\n" TH_B_##n(a, a, TH_STORE)
+#define TH_CODE_OTHER(n) "H_" #n "_a:\n" TH_B_##n(a, a)
+#else
 #define TH_CODE_ARITH(n)                                                                       \
   "H_" #n "_a:\n" TH_B_##n(a, b, TH_NOSTORE) "H_" #n "_b:\n" TH_B_##n(b, a, TH_NOSTORE)        \
   "H_" #n "_ST_a:\n" TH_B_##n(a, b, TH_STORE) "H_" #n "_ST_b:\n" TH_B_##n(b, a, TH_STORE)
 #define TH_CODE_OTHER(n) "H_" #n "_a:\n" TH_B_##n(a, b) "H_" #n "_b:\n" TH_B_##n(b, a)
+#endif
 
 // Runs from the instruction at pc (handler nh, register set `parity`) until END (returns 0) or a slow
 // operator (returns its opcode with xv / yv set; pc / nh / parity then name the instruction after it).
@@ -295,10 +424,18 @@ __device__ __forceinline__ uint32_t mtgp_th_block(float& acc, uint32_t& pc, uint
       "{\n"
       " .reg .u32 a0,a1,a2,a3,b0,b1,b2,b3,ad,ae;\n"
       " .reg .f32 t0,t1,t2,t3,t4,t5,t6,t7;\n"
-      " .reg .u32 qi,cf;\n"
+      " .reg .u32 qi,cf,nx,sa;\n"
+      " .reg .b32 m0,m1,fp,fq,fk;\n"
       " .reg .pred pq;\n"
-      "TBLa: .branchtargets " MTGP_TH_ARITH(TH_LABELS_ARITH_a) MTGP_TH_OTHER(TH_LABELS_OTHER_a) "DONE;\n"
-      "TBLb: .branchtargets " MTGP_TH_ARITH(TH_LABELS_ARITH_b) MTGP_TH_OTHER(TH_LABELS_OTHER_b) "DONE;\n"
+      "TBLa: .branchtargets " MTGP_TH_ARITH(TH_LABELS_ARITH_a) MTGP_TH_OTHER(TH_LABELS_OTHER_a) MTGP_TH_FUSED(TH_LABELS_ARITH_a) "DONE;\n"
+#if MTGP_TH_SETS == 1
+      " ld.shared.v4.u32 {a0,a1,a2,a3},[%1];\n"
+      " brx.idx %2, TBLa;\n"
+      MTGP_TH_ARITH(TH_CODE_ARITH)
+      MTGP_TH_OTHER(TH_CODE_OTHER)
+      TH_TRIG_BODY(a, a)
+#else
+      "TBLb: .branchtargets " MTGP_TH_ARITH(TH_LABELS_ARITH_b) MTGP_TH_OTHER(TH_LABELS_OTHER_b) MTGP_TH_FUSED(TH_LABELS_ARITH_b) "DONE;\n"
       " setp.ne.u32 pq,%7,0;\n"
       " @pq bra ENTRY_b;\n"
       " ld.shared.v4.u32 {a0,a1,a2,a3},[%1];\n"
@@ -312,7 +449,9 @@ __device__ __forceinline__ uint32_t mtgp_th_block(float& acc, uint32_t& pc, uint
 #endif
       MTGP_TH_ARITH(TH_CODE_ARITH)
       MTGP_TH_OTHER(TH_CODE_OTHER)
+      MTGP_TH_FUSED(TH_CODE_ARITH)
       TH_TRIG_BODY(a, b) TH_TRIG_BODY(b, a)
+#endif
       "DONE:\n"
       "}\n"
       : "+f"(acc), "+r"(pc), "+r"(nh), "=r"(status), "=f"(xv), "+f"(yv), "+r"(lane), "+r"(parity)
@@ -374,7 +513,28 @@ static __host__ __device__ MTGP_TH_INLINE float mtgp_run_threaded(mtgp_saddr ent
       case TH_SLOW_A: acc = mtgp_th_slow_op(w.c, acc, yv); break;
       case TH_SLOW_M: acc = mtgp_th_slow_op(w.c, M(w.a), yv); break;
       case TH_SLOW_I: acc = mtgp_th_slow_op(w.c, I(w.a), yv); break;
-      default: return acc;  // TH_END
+      default: {
+#if !MTGP_TH_FUSE
+        return acc;  // TH_END
+#else
+        if (hh < TH_F_AI_I || hh >= TH_COUNT) return acc;  // TH_END
+        // fused pair: generic fma forms (see MTGP_TH_FUSED); the data slot follows
+        const mtgp_tinstr d = prog[++j];
+        const uint32_t f = hh - TH_F_AI_I, head = f >> 2, tail = (f >> 1) & 1u;
+        auto pq = [&](uint32_t mask, float m, float& P, float& Q) {
+          P = mask ? m : 1.0f;
+          Q = mask ? -0.0f : m;
+        };
+        float P, Q;
+        const float x = (head == 1 || head == 3) ? M(w.a) : acc;
+        if (head <= 1) { P = I(w.b); Q = I(w.c); } else pq(w.c, M(w.b), P, Q);
+        acc = fmaf(x, P, Q);
+        if (tail == 0) { P = I(d.a); Q = I(d.b); } else pq(d.b, M(d.a), P, Q);
+        acc = fmaf(acc, P, Q);
+        if (f & 1u) memcpy(const_cast<unsigned char*>(vb) + d.c, &acc, 4);
+        break;
+#endif
+      }
     }
     if (st) memcpy(const_cast<unsigned char*>(vb) + w.c, &acc, 4);
   }

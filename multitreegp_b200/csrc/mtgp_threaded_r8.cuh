@@ -97,6 +97,7 @@
 #define T8_B_COS_A(C, N) " mov.u32 %10,0xFFFF;\n bra DONE;\n"
 #define T8_B_COS_M(C, N) " mov.u32 %10,0xFFFF;\n bra DONE;\n"
 #define T8_B_END(C, N) " mov.u32 %10,0;\n bra DONE;\n"
+#define T8_B_FDATA(C, N) " mov.u32 %10,0xFFFF;\n bra DONE;\n"  // (pair fusion is the rollout kernels'; never emitted here)
 
 #define T8_CODE_ARITH(n)                                                                       \
   "H_" #n "_a:\n" T8_B_##n(a, b, T8_NOSTORE) "H_" #n "_b:\n" T8_B_##n(b, a, T8_NOSTORE)        \

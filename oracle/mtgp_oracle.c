@@ -830,3 +830,27 @@ ORACLE_API int oracle_num_threads(void) {
   return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Test entry points: the environment functions alone.  tests/test_reference_shim_golden.py     */
+/* compares them with outputs of the reference's OWN environment classes, recorded by           */
+/* tools/record_reference_shim_golden.py (the reference imported from /root/reference over a    */
+/* numpy stand-in for jax).  d / b: descriptor and trajectory whose parameters apply.            */
+/* ------------------------------------------------------------------------------------------ */
+ORACLE_API void oracle_env_drift(const mtgp_rollout_desc* d, int b, const float* x, float u, float* dx) {
+  env_t e;
+  env_init(&e, d, b);
+  env_drift(&e, x, u, dx);
+}
+ORACLE_API void oracle_env_f_obs(const mtgp_rollout_desc* d, int b, float t, const float* x, float* y) {
+  env_t e;
+  env_init(&e, d, b);
+  env_f_obs(&e, t, x, y);
+}
+ORACLE_API float oracle_env_cond(int env_id, const float* y, int n) { return env_cond(env_id, y, n); }
+ORACLE_API float oracle_env_fitness(const mtgp_rollout_desc* d, int b, const float* xs, const float* us,
+                                    const float* target, const float* ts, int K) {
+  env_t e;
+  env_init(&e, d, b);
+  return env_fitness(&e, xs, us, target, ts, K);
+}

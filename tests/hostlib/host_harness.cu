@@ -52,6 +52,7 @@ int hostlib_eval_tree(const float* tree, int N, const mtgp_node_table* tab, cons
   std::vector<mtgp_tinstr> th(1 + MTGP_TH_MAX_EXPAND * n_instr);
   int m = 1;
   for (int i = 0; i < n_instr; i++) m += mtgp_th_expand(prog[i], th.data() + m);
+  mtgp_th_fuse(th.data(), m - 1);  // the rollout kernels' pair fusion (generic fma forms)
   mtgp_th_link(th.data(), m - 1);
   if (m != (int)MTGP_META_TH(meta)) return -1;
   for (int p = 0; p < n_pts; p++) {

@@ -22,7 +22,7 @@ def hostlib():
     deps = [src] + [os.path.join(HERE, "..", "multitreegp_b200", "csrc", f) for f in ("mtgp_lower.cuh", "mtgp_program.cuh", "mtgp_threaded.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(p) > os.path.getmtime(so) for p in deps):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler",
-                               "-ffp-contract=off", "-Xcompiler", "-w", "-shared", "-o", so, src])
+                               "-ffp-contract=off", "-Xcompiler", "-w", "-DMTGP_TH_FUSE=1", "-shared", "-o", so, src])
     L = C.CDLL(so)
     L.hostlib_eval_tree.restype = C.c_int
     return L

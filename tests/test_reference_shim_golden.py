@@ -1,0 +1,112 @@
+"""CPU oracle vs fixtures recorded from the reference's OWN code (tools/record_reference_shim_golden.py).
+
+The fixtures hold outputs of /root/reference/MultiTreeGP itself -- GeneticProgramming.__init__ / vmap_foriloop and the
+three environment classes -- executed over tools/refshim (numpy float32 stand-in for jax).  They pin everything of the
+hot path that is the reference's own code; diffrax's loop and jax.random stay restated from their published algorithms
+(tests/test_reference_golden.py takes over on a machine with jax + diffrax).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from multitreegp_b200 import abi
+from multitreegp_b200.node_library import NodeLibrary
+from multitreegp_b200.rollout_data import RolloutData
+from oracle import pyoracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+RTOL = 1e-5  # BASELINE.json north_star: rtol 1e-5 against the reference
+
+
+def _load(name):
+    path = os.path.join(HERE, "golden", "refshim", name)
+    if not os.path.exists(path):
+        pytest.skip(f"{name} not recorded")
+    return np.load(path, allow_pickle=False)
+
+
+TREE_CASES = {
+    "dynamic": ([("+", 2, 0.5), ("-", 2, 0.1), ("*", 2, 0.5), ("sin", 1, 0.1), ("cos", 1, 0.1)],
+                [["y1", "y2", "y3", "y4", "a1", "a2", "u"], ["a1", "a2"]], [2, 1]),
+    "arith": ([("+", 2, 0.5), ("-", 2, 0.2), ("*", 2, 0.5), ("/", 2, 0.2)], [["x0", "x1"]], [2]),
+}
+
+
+@pytest.mark.parametrize("case", sorted(TREE_CASES))
+def test_node_library_equals_reference_constructor(case):
+    """NodeLibrary == the id assignment GeneticProgramming.__init__ itself produced (genetic_programming.py:132-199)."""
+    g = _load("refshim_trees.npz")
+    ops, variables, layers = TREE_CASES[case]
+    lib = NodeLibrary(ops, variables, layers)
+    ref = dict(zip((str(s) for s in g[f"{case}_node_strings"]), (int(i) for i in g[f"{case}_node_ids"])))
+    assert lib.string_to_node == ref
+    assert np.array_equal(lib.slots, g[f"{case}_slots"])
+
+
+@pytest.mark.parametrize("case", sorted(TREE_CASES))
+def test_tree_values_equal_reference_interpreter(case):
+    """oracle_tree_eval == GeneticProgramming.vmap_foriloop (body_fun, :356-401) on the recorded trees."""
+    g = _load("refshim_trees.npz")
+    ops, variables, layers = TREE_CASES[case]
+    table = NodeLibrary(ops, variables, layers).table()
+    pop, data, ref = g[f"{case}_pop"], g[f"{case}_data"], g[f"{case}_values"]
+    got = np.empty_like(ref)
+    for p in range(pop.shape[0]):
+        for d in range(data.shape[0]):
+            for t in range(pop.shape[1]):
+                got[p, d, t] = pyoracle.tree_eval(pop[p, t], table, data[d])
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    if case == "arith":  # + - * / are IEEE-exact on both sides: bit for bit (NaN sign / payload aside)
+        m = ~np.isnan(ref)
+        assert np.array_equal(got[m].view(np.uint32), ref[m].view(np.uint32))
+    else:  # numpy's float32 sin / cos vs the contract's: a few ulp
+        np.testing.assert_allclose(got, ref, rtol=RTOL, atol=1e-6, equal_nan=True)
+    assert np.isfinite(ref).mean() > 0.5
+
+
+ENVS = {"acrobot": (abi.ENV_ACROBOT, 0), "harmonic": (abi.ENV_HARMONIC, 1), "reactor": (abi.ENV_REACTOR, 1)}
+
+
+def _desc(env_id, params, D, ts, targets):
+    rd = RolloutData(kind=abi.EVAL_STATIC, env_id=env_id, x0=np.zeros((1, D), np.float32), ts=ts, dt0=0.1,
+                     max_fitness=1e4, targets=targets, params=np.asarray(params, np.float32).reshape(1, -1))
+    return rd.to_desc_host()
+
+
+@pytest.mark.parametrize("env", sorted(ENVS))
+def test_environment_functions_equal_reference_classes(env):
+    """drift / f_obs / cond_fn_nan / fitness_function of the oracle == the reference's environment classes."""
+    g = _load("refshim_env.npz")
+    env_id, n_targets = ENVS[env]
+    L = pyoracle.lib()
+    L.oracle_env_cond.restype = C.c_float
+    L.oracle_env_fitness.restype = C.c_float
+    ts = g["ts"]
+    xs, us = g[f"{env}_x"], g[f"{env}_u"]
+    D = xs.shape[1]
+    for ip, ps in enumerate(g[f"{env}_params"]):
+        desc, keep = _desc(env_id, ps, D, ts, np.zeros((1, n_targets), np.float32))
+        drift, fobs = np.empty_like(xs), np.empty_like(xs)
+        for i in range(xs.shape[0]):
+            x = np.ascontiguousarray(xs[i])
+            L.oracle_env_drift(C.byref(desc), 0, C.c_void_p(x.ctypes.data), C.c_float(us[i]), C.c_void_p(drift[i].ctypes.data))
+            L.oracle_env_f_obs(C.byref(desc), 0, C.c_float(0.3), C.c_void_p(x.ctypes.data), C.c_void_p(fobs[i].ctypes.data))
+        scale = np.abs(g[f"{env}_drift"][ip]).max(axis=0)  # a component that cancels to ~0 is judged on its column's scale
+        np.testing.assert_allclose(drift, g[f"{env}_drift"][ip], rtol=RTOL, atol=RTOL * scale.max())
+        np.testing.assert_allclose(fobs, g[f"{env}_f_obs"][ip], rtol=RTOL, atol=1e-5)
+        fit = np.empty(g[f"{env}_fitness"].shape[1], np.float32)
+        for j in range(fit.size):
+            tx = np.ascontiguousarray(g[f"{env}_traj_x"][j])
+            tu = np.ascontiguousarray(g[f"{env}_traj_u"][j].reshape(-1))
+            tg = np.ascontiguousarray(g[f"{env}_targets"][j])
+            fit[j] = L.oracle_env_fitness(C.byref(desc), 0, C.c_void_p(tx.ctypes.data), C.c_void_p(tu.ctypes.data),
+                                          C.c_void_p(tg.ctypes.data), C.c_void_p(ts.ctypes.data), C.c_int(ts.size))
+        np.testing.assert_allclose(fit, g[f"{env}_fitness"][ip], rtol=RTOL)
+        del keep
+    cs = g[f"{env}_cond_states"]
+    cond = np.array([L.oracle_env_cond(C.c_int(env_id), C.c_void_p(np.ascontiguousarray(c).ctypes.data), C.c_int(D)) for c in cs],
+                    np.float32)
+    assert np.array_equal(cond, g[f"{env}_cond"])
+    assert (cond < 0).any() and (cond > 0).any()
