@@ -110,3 +110,68 @@ def test_environment_functions_equal_reference_classes(env):
                     np.float32)
     assert np.array_equal(cond, g[f"{env}_cond"])
     assert (cond < 0).any() and (cond > 0).any()
+
+
+POP_OPS = [("+", 2, 0.5), ("-", 2, 0.2), ("*", 2, 0.5), ("/", 2, 0.1), ("sin", 1, 0.1)]
+
+
+def test_evaluate_population_equals_reference_wrappers():
+    """oracle pointwise fitness + size_parsimony * live rows == GeneticProgramming.evaluate_population itself
+    (reshape, jit_eval = jit(shard_map(vmap(partial_ff))), coefficient / node split, parsimony :424, best :426-431)."""
+    g = _load("refshim_trees.npz")
+    lib = NodeLibrary(POP_OPS, [["x0", "x1"]], [2])
+    pops = g["pop_populations"]
+    flat = pops.reshape(-1, *pops.shape[2:])
+    base = pyoracle.pointwise_population(flat, lib.table(), g["pop_X"], g["pop_Y"], max_fitness=1e5)
+    fit = base + np.float32(g["pop_parsimony"]) * pyoracle.live_count(flat).astype(np.float32)
+    ref = g["pop_fitness"].reshape(-1)
+    np.testing.assert_allclose(fit, ref, rtol=RTOL)
+    assert bool(g["pop_returned_population_is_input"])
+    best = int(np.argmin(ref))
+    assert np.array_equal(g["pop_best_solution"], flat[best]) and g["pop_best_fitness"] == ref[best]
+    order = np.sort(ref)
+    if order[1] - order[0] > RTOL * abs(order[0]):  # the winner is decided beyond the tolerance
+        assert int(np.argmin(fit)) == best
+    assert len(np.unique(ref)) > len(ref) // 2
+
+
+@pytest.mark.gpu
+def test_cuda_evaluate_population_equals_reference_wrappers():
+    """The product path (pointwise evaluator -> C ABI -> k_pointwise with the fused parsimony term, EvaluationDriver)
+    against the same reference-recorded fitness matrix and best-of-generation."""
+    from multitreegp_b200.evaluators import pointwise_evaluate
+    from multitreegp_b200.strategy_eval import EvaluationDriver
+    g = _load("refshim_trees.npz")
+    ev = pointwise_evaluate.Evaluator().bind(POP_OPS, [["x0", "x1"]], [2])
+    pops = g["pop_populations"]
+    drv = EvaluationDriver(3, pops.shape[1], ev, num_populations=pops.shape[0], size_parsinomy=float(g["pop_parsimony"]))
+    fit, same = drv.evaluate_population(pops, (g["pop_X"], g["pop_Y"]))
+    assert same is pops
+    np.testing.assert_allclose(np.asarray(fit), g["pop_fitness"], rtol=RTOL)
+    bf, bs = drv.get_statistics(0)
+    ref = g["pop_fitness"].reshape(-1)
+    order = np.sort(ref)
+    if order[1] - order[0] > RTOL * abs(order[0]):
+        assert np.array_equal(np.asarray(bs), g["pop_best_solution"])
+    np.testing.assert_allclose(bf, g["pop_best_fitness"], rtol=RTOL)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(TREE_CASES))
+def test_cuda_tree_values_equal_reference_interpreter(case):
+    """k_encode -> k_lower -> k_pointwise predictions == GeneticProgramming.vmap_foriloop on the recorded trees."""
+    from multitreegp_b200.evaluators import pointwise_evaluate
+    g = _load("refshim_trees.npz")
+    ops, variables, layers = TREE_CASES[case]
+    n_trees = sum(layers)
+    ev = pointwise_evaluate.Evaluator().bind(ops, [sorted({v for vl in variables for v in vl}, key=[v for vl in variables for v in vl].index)], [n_trees])
+    pop, data, ref = g[f"{case}_pop"], g[f"{case}_data"], g[f"{case}_values"]
+    Y = np.zeros((data.shape[0], n_trees), np.float32)
+    for p in range(pop.shape[0]):
+        _, pred = ev.evaluate_candidate(pop[p], (data, Y))
+        if case == "arith":
+            m = ~np.isnan(ref[p])
+            assert np.array_equal(np.isnan(pred), np.isnan(ref[p]))
+            assert np.array_equal(pred[m].view(np.uint32), ref[p][m].view(np.uint32))
+        else:
+            np.testing.assert_allclose(pred, ref[p], rtol=RTOL, atol=1e-6, equal_nan=True)

@@ -145,10 +145,47 @@ def record_env():
     return out
 
 
+# ---- evaluate_population: the reference's own wrappers around a fitness function ---------------------
+def record_population():
+    """GeneticProgramming.evaluate_population (genetic_programming.py:403-433) end to end -- reshape of the islands,
+    jit_eval = jit(shard_map(vmap(partial_ff))) (:249-269; jit / shard_map are inert here, vmap is a loop), the split
+    into (coefficients, nodes), the parsimony term (:424), best-of-generation (:426-431) -- around a fitness function
+    with the signature the evaluators have.  The function is the pointwise regression fitness of SURVEY.md App. G,
+    written with the reference's primitives (tree_evaluator = vmap_foriloop)."""
+    rng = np.random.default_rng(99)
+    ops = [("+", lambda x, y: x + y, 2, 0.5), ("-", lambda x, y: x - y, 2, 0.2), ("*", lambda x, y: x * y, 2, 0.5),
+           ("/", lambda x, y: x / y, 2, 0.1), ("sin", lambda x: jnp.sin(x), 1, 0.1)]
+    variables, layers, depth, max_nodes = [["x0", "x1"]], [2], 4, 24
+    num_pop, pop_size, parsimony = 2, 20, 0.003
+
+    def fitness_function(coefficients, nodes, data, tree_evaluator):
+        candidate = jnp.concatenate([nodes, coefficients], axis=-1)  # as SR_evaluator.py:33 / feedforward_evaluate.py:39 do
+        X, Y = data
+        pred = jax.vmap(tree_evaluator, in_axes=[None, 0])(candidate, X)
+        fitness = jnp.mean(jnp.sum(jnp.square(pred - Y), axis=-1))
+        fitness = jnp.where(jnp.isnan(fitness) | jnp.isinf(fitness), F(1e5), fitness)
+        return jnp.clip(fitness, 0, 1e5)
+
+    gp = GeneticProgramming(3, pop_size, fitness_function, ops, variables, jnp.array(layers), num_populations=num_pop,
+                            max_init_depth=depth, max_nodes=max_nodes, size_parsinomy=parsimony)
+    lib = NodeLibrary(ops, variables, layers)
+    pops = sample_population(rng, num_pop * pop_size, lib, max_init_depth=depth, max_nodes=max_nodes)
+    pops = pops.reshape(num_pop, pop_size, *pops.shape[1:])
+    X = rng.normal(size=(64, 2)).astype(F)
+    Y = np.stack([X[:, 0] * X[:, 1] + F(0.5), np.sin(X[:, 0]) - X[:, 1]], axis=1).astype(F)
+    with np.errstate(all="ignore"):
+        fitness, same = gp.evaluate_population(A(pops), (A(X), A(Y)))
+    return dict(pop_populations=pops, pop_X=X, pop_Y=Y, pop_fitness=np.asarray(fitness, dtype=F),
+                pop_parsimony=np.array(parsimony, dtype=F), pop_best_fitness=np.asarray(gp.best_fitnesses[0], dtype=F),
+                pop_best_solution=np.asarray(gp.best_solutions[0], dtype=F),
+                pop_returned_population_is_input=np.array(np.array_equal(np.asarray(same), pops)))
+
+
 def main():
     meta = dict(recorder="tools/record_reference_shim_golden.py", reference=REF, numpy=np.__version__,
                 note="reference code executed over tools/refshim (numpy float32), noise-free f_obs")
     trees, env = record_trees(), record_env()
+    trees.update(record_population())
     np.savez_compressed(os.path.join(OUT, "refshim_trees.npz"), meta=np.array(repr(meta)), **trees)
     np.savez_compressed(os.path.join(OUT, "refshim_env.npz"), meta=np.array(repr(meta)), **env)
     print("recorded", sorted(trees), sorted(env))

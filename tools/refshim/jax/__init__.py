@@ -21,6 +21,10 @@ def jit(f=None, **_kw):
     return f if f is not None else (lambda g: g)
 
 
+def device_put(x, *_a, **_k):
+    return x
+
+
 def devices(_kind=None):
     return [object()]
 
