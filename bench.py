@@ -533,6 +533,18 @@ def main():
                                 "sample": f"{n} of {P} individuals x {w['B']} trajectories x {w['n_sched']} steps "
                                           f"({steps} rollout-steps in {dt:.1f} s = {100.0 * n / P:.2f} % of the population; "
                                           "oracle/mtgp_oracle.c with OpenMP, a C port of the reference path, NOT JAX)"}
+        # the same port doing the WORK the reference does under vmap o switch: every node function on every one of the
+        # max_nodes rows (BASELINE.md 3.3 "reference-faithful"); a quarter of the sample, same values
+        from oracle import pyoracle as po
+        po.lib().oracle_set_all_branches(1)
+        try:
+            rate_f, n_f, steps_f, dt_f, _ = cpu_time_rollout(w, target_s=0.0, n=max(32, (n // 4) - (n // 4) % 8))
+        finally:
+            po.lib().oracle_set_all_branches(0)
+        line["cpu_baseline"]["all_branches"] = {
+            "value": rate_f, "unit": "rollout-steps/s",
+            "sample": f"{n_f} individuals ({steps_f} rollout-steps in {dt_f:.1f} s); every node function evaluated on "
+                      "every row, as XLA does for lax.switch under vmap (genetic_programming.py:372)"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -38,6 +38,12 @@
 static int g_math_mode = 0;
 ORACLE_API void oracle_set_math(int mode) { g_math_mode = mode; }
 ORACLE_API int oracle_get_math(void) { return g_math_mode; }
+/* Reference-faithful WORK: under vmap, lax.switch over a batched index becomes a select over ALL
+   node functions (genetic_programming.py:372), so XLA computes every branch of every row.  With mode 1 the
+   interpreter does the same work -- every node function of the table on every row, the unselected results
+   discarded -- and returns the same values.  Timing only (bench.py's cpu_baseline); default 0. */
+static int g_all_branches = 0;
+ORACLE_API void oracle_set_all_branches(int mode) { g_all_branches = mode; }
 
 static inline float m_sin(float x) { return g_math_mode ? sinf(x) : mtgp_sinf(x); }
 static inline float m_cos(float x) { return g_math_mode ? cosf(x) : mtgp_cosf(x); }
@@ -223,6 +229,12 @@ ORACLE_API float oracle_tree_eval(const float* tree /* [N,4] */, int N, const mt
     if (f < 0) f = 0;                                    /* lax.switch clamps its index */
     if (f > tab->n_ids - 1) f = tab->n_ids - 1;
     float v = apply_node(tab->opcode[f], tab->arg[f], x, y, data);
+    if (g_all_branches) { /* the select over every branch: same value, all the work */
+      for (int g = 0; g < tab->n_ids; g++) {
+        volatile float w = apply_node(tab->opcode[g], tab->arg[g], x, y, data);
+        if (g == f) v = w;
+      }
+    }
     val[i] = (f_idx == 1.0f) ? coefficient : v;          /* select(f_idx == 1, coefficient, switch(...)) (:372) */
   }
   return val[N - 1];
