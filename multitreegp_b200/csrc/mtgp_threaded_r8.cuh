@@ -19,11 +19,19 @@
 #if defined(__CUDA_ARCH__)
 // operands: %0..%7 acc  %8 pc  %9 nh  %10 status  %11 lane (byte address of the lane's base in the value file)
 //           %12 parity  %13 scratch (byte offset of the scratch slot that receives the y vector of a slow operator)
+#ifndef MTGP_TH8_SETS
+#define MTGP_TH8_SETS 1  // register sets of the instruction fetch (see MTGP_TH_SETS): 1 = one copy of every handler (C4: 15.2 ms; 2 sets: 19.7 ms -- the eight-value handlers are long and two copies do not fit the instruction cache)
+#endif
+#if MTGP_TH8_SETS == 1
+#define T8_NEXT(N) " mov.u32 nx,i" #N "0;\n add.u32 %8,%8,16;\n ld.shared.v4.u32 {i" #N "0,i" #N "1,i" #N "2,i" #N "3},[%8];\n"
+#define T8_GO(C, N) " brx.idx nx, TBLa;\n"
+#else
 #define T8_NEXT(N) " add.u32 %8,%8,16;\n ld.shared.v4.u32 {i" #N "0,i" #N "1,i" #N "2,i" #N "3},[%8];\n"
 #ifdef MTGP_TH_CENTRAL
 #define T8_GO(C, N) " bra DISP_" #C ";\n"
 #else
 #define T8_GO(C, N) " brx.idx i" #C "0, TBL" #N ";\n"
+#endif
 #endif
 #define T8_LDV(V, AD) " ld.shared.v4.f32 {" V "0," V "1," V "2," V "3},[" AD "];\n ld.shared.v4.f32 {" V "4," V "5," V "6," V "7},[" AD "+512];\n"
 #define T8_STV(V0, V1, V2, V3, V4, V5, V6, V7, AD) \
@@ -37,6 +45,11 @@
 #define T8_XMYI(C) T8_XM(C) T8_YI(C)
 #define T8_STORE(C) " add.u32 ad,%11,i" #C "3;\n" T8_STV("%0", "%1", "%2", "%3", "%4", "%5", "%6", "%7", "ad")
 #define T8_NOSTORE(C) ""
+// the store address is formed before the successor is fetched (with one register set the fetch overwrites the fields)
+#define T8_STORE_A(C) " add.u32 sa,%11,i" #C "3;\n"
+#define T8_STORE_D T8_STV("%0", "%1", "%2", "%3", "%4", "%5", "%6", "%7", "sa")
+#define T8_NOSTORE_A(C) ""
+#define T8_NOSTORE_D ""
 // operand name of value r:  A = accumulator, X / Y = loaded vectors, XI / YI = broadcast immediates
 #define T8_A(r) "%" #r
 #define T8_X(r) "x" #r
@@ -47,7 +60,7 @@
 #define T8_ALL(OP, XF, YF) \
   T8_L(OP, XF, YF, 0) T8_L(OP, XF, YF, 1) T8_L(OP, XF, YF, 2) T8_L(OP, XF, YF, 3) T8_L(OP, XF, YF, 4) T8_L(OP, XF, YF, 5) \
   T8_L(OP, XF, YF, 6) T8_L(OP, XF, YF, 7)
-#define T8_OP(PRE, OP, XF, YF, C, N, ST) PRE(C) T8_NEXT(N) T8_ALL(OP, XF, YF) ST(C) T8_GO(C, N)
+#define T8_OP(PRE, OP, XF, YF, C, N, ST) PRE(C) ST##_A(C) T8_NEXT(N) T8_ALL(OP, XF, YF) ST##_D T8_GO(C, N)
 
 #define T8_B_ADD_AM(C, N, ST) T8_OP(T8_YM, "add.rn.f32", T8_A, T8_Y, C, N, ST)
 #define T8_B_ADD_AI(C, N, ST) T8_OP(T8_YI, "add.rn.f32", T8_A, T8_YIM, C, N, ST)
@@ -67,10 +80,10 @@
 #define T8_MOV_X(r) " mov.f32 %" #r ",x" #r ";\n"
 #define T8_MOV_XI(r) " mov.f32 %" #r ",xi;\n"
 #define T8_REP(F) F(0) F(1) F(2) F(3) F(4) F(5) F(6) F(7)
-#define T8_B_LOAD_M(C, N, ST) T8_XM(C) T8_NEXT(N) T8_REP(T8_MOV_X) ST(C) T8_GO(C, N)
-#define T8_B_LOAD_I(C, N, ST) T8_XI(C) T8_NEXT(N) T8_REP(T8_MOV_XI) ST(C) T8_GO(C, N)
+#define T8_B_LOAD_M(C, N, ST) T8_XM(C) ST##_A(C) T8_NEXT(N) T8_REP(T8_MOV_X) ST##_D T8_GO(C, N)
+#define T8_B_LOAD_I(C, N, ST) T8_XI(C) ST##_A(C) T8_NEXT(N) T8_REP(T8_MOV_XI) ST##_D T8_GO(C, N)
 
-#define T8_B_ST(C, N) T8_NEXT(N) T8_STORE(C) T8_GO(C, N)
+#define T8_B_ST(C, N) T8_STORE(C) T8_NEXT(N) T8_GO(C, N)
 // the divisor / second operand vector, kept in y0..y7 for the DIV_* or SLOW_* that follows
 #define T8_MOV_YA(r) " mov.f32 y" #r ",%" #r ";\n"
 #define T8_MOV_YI(r) " mov.f32 y" #r ",yi;\n"
@@ -99,20 +112,29 @@
 #define T8_B_END(C, N) " mov.u32 %10,0;\n bra DONE;\n"
 #define T8_B_FDATA(C, N) " mov.u32 %10,0xFFFF;\n bra DONE;\n"  // (pair fusion is the rollout kernels'; never emitted here)
 
+#if MTGP_TH8_SETS == 1
+#define T8_CODE_ARITH(n) "H_" #n "_a:\n" T8_B_##n(a, a, T8_NOSTORE) "H_" #n "_ST_a:\n" T8_B_##n(a, a, T8_STORE)
+#define T8_CODE_OTHER(n) "H_" #n "_a:\n" T8_B_##n(a, a)
+#else
 #define T8_CODE_ARITH(n)                                                                       \
   "H_" #n "_a:\n" T8_B_##n(a, b, T8_NOSTORE) "H_" #n "_b:\n" T8_B_##n(b, a, T8_NOSTORE)        \
   "H_" #n "_ST_a:\n" T8_B_##n(a, b, T8_STORE) "H_" #n "_ST_b:\n" T8_B_##n(b, a, T8_STORE)
 #define T8_CODE_OTHER(n) "H_" #n "_a:\n" T8_B_##n(a, b) "H_" #n "_b:\n" T8_B_##n(b, a)
+#endif
 
 __device__ __forceinline__ uint32_t mtgp_th8_block(float (&acc)[8], uint32_t& pc, uint32_t& nh, uint32_t& parity,
                                                    uint32_t lane, uint32_t scratch) {
   uint32_t status;
   asm volatile(
       "{\n"
-      " .reg .u32 ia0,ia1,ia2,ia3,ib0,ib1,ib2,ib3,ad,ae;\n"
+      " .reg .u32 ia0,ia1,ia2,ia3,ib0,ib1,ib2,ib3,ad,ae,nx,sa;\n"
       " .reg .f32 x0,x1,x2,x3,x4,x5,x6,x7,y0,y1,y2,y3,y4,y5,y6,y7,xi,yi;\n"
       " .reg .pred pq;\n"
       "TBLa: .branchtargets " MTGP_TH_ARITH(TH_LABELS_ARITH_a) MTGP_TH_OTHER(TH_LABELS_OTHER_a) "DONE;\n"
+#if MTGP_TH8_SETS == 1
+      " ld.shared.v4.u32 {ia0,ia1,ia2,ia3},[%8];\n"
+      " brx.idx %9, TBLa;\n"
+#else
       "TBLb: .branchtargets " MTGP_TH_ARITH(TH_LABELS_ARITH_b) MTGP_TH_OTHER(TH_LABELS_OTHER_b) "DONE;\n"
       " setp.ne.u32 pq,%12,0;\n"
       " @pq bra ENTRY_b;\n"
@@ -121,6 +143,7 @@ __device__ __forceinline__ uint32_t mtgp_th8_block(float (&acc)[8], uint32_t& pc
       "ENTRY_b:\n"
       " ld.shared.v4.u32 {ib0,ib1,ib2,ib3},[%8];\n"
       " brx.idx %9, TBLb;\n"
+#endif
 #ifdef MTGP_TH_CENTRAL
       "DISP_a:\n brx.idx ia0, TBLb;\n"
       "DISP_b:\n brx.idx ib0, TBLa;\n"
