@@ -396,6 +396,10 @@ struct DeviceScratch {
   std::mutex mu;
   void* ptr = nullptr;
   size_t bytes = 0;
+  // the host entry points overlap the population upload with the evaluation (see mtgp_population_fitness_host):
+  // one copy stream, two compute streams, events; created on first use, owned with the scratch
+  cudaStream_t copy_s = nullptr, comp_s[2] = {nullptr, nullptr};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 std::mutex g_scratch_table_mu;
 std::map<int, std::unique_ptr<DeviceScratch>> g_scratch;
@@ -442,6 +446,12 @@ int mtgp_release_scratch(void) {
     if (kv.second->ptr) cudaFree(kv.second->ptr);
     kv.second->ptr = nullptr;
     kv.second->bytes = 0;
+    if (kv.second->copy_s) {
+      cudaStreamDestroy(kv.second->copy_s);
+      for (int i = 0; i < 2; i++) cudaStreamDestroy(kv.second->comp_s[i]);
+      for (int i = 0; i < 6; i++) cudaEventDestroy(kv.second->ev[i]);
+      kv.second->copy_s = nullptr;
+    }
   }
   return MTGP_OK;
 }
@@ -455,12 +465,22 @@ int mtgp_population_fitness_host(const float* population_host, int P, int T, int
   if (!dh || !population_host || !fitness_host) { mtgp_set_error("NULL host buffer"); return MTGP_ERR_INVALID_ARGUMENT; }
   cudaStream_t s = (cudaStream_t)stream;
   const size_t pop_bytes = (size_t)P * T * N * 4 * sizeof(float);
-  const size_t ws_bytes = mtgp_workspace_bytes(P, T, N, dh);
+  // populations worth overlapping (>= 32 MB of rows) are evaluated as a prologue slice + the rest (see below)
+  const bool split = pop_bytes >= ((size_t)32 << 20) && P >= 64;
+  const size_t PA = split ? (size_t)((P / 8 + 7) & ~7) : 0;
+  const size_t ws_a = split ? mtgp_workspace_bytes((int)PA, T, N, dh) : 0;
+  const size_t ws_b = split ? mtgp_workspace_bytes((int)(P - PA), T, N, dh) : 0;
+  const size_t ws_bytes = split ? align_up(ws_a, 256) + ws_b : mtgp_workspace_bytes(P, T, N, dh);
   const size_t B = dh->B, K = dh->K, D = dh->D;
   if ((rc = validate_ts_host(dh->ts, dh->K))) return rc;
   DeviceScratch* sc = scratch_of_current_device();
   if (!sc) { mtgp_set_error("cudaGetDevice failed"); return MTGP_ERR_CUDA; }
   std::lock_guard<std::mutex> scratch_lock(sc->mu);  // the scratch is this call's until it has synchronised
+  if (split && !sc->copy_s) {
+    MTGP_CUDA_TRY(cudaStreamCreateWithFlags(&sc->copy_s, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) MTGP_CUDA_TRY(cudaStreamCreateWithFlags(&sc->comp_s[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 6; i++) MTGP_CUDA_TRY(cudaEventCreateWithFlags(&sc->ev[i], cudaEventDisableTiming));
+  }
   // layout of the scratch: population | fitness | data arrays | workspace
   size_t off_pop = 0, off_fit, off_x0, off_ts, off_tg, off_keys, off_par, off_ys, off_ws, total;
   {
@@ -486,7 +506,6 @@ int mtgp_population_fitness_host(const float* population_host, int P, int T, int
   } else {                                                                                              \
     dd.field = nullptr;                                                                                 \
   }
-  MTGP_CUDA_TRY(cudaMemcpyAsync(base + off_pop, population_host, pop_bytes, cudaMemcpyHostToDevice, s));
   H2D(x0, off_x0, B * D * 4)
   H2D(ts, off_ts, K * 4)
   H2D(targets, off_tg, B * (size_t)dh->n_targets * 4)
@@ -496,9 +515,40 @@ int mtgp_population_fitness_host(const float* population_host, int P, int T, int
 #undef H2D
   const float* pop_d = reinterpret_cast<const float*>(base + off_pop);
   float* fit_d = reinterpret_cast<float*>(base + off_fit);
-  rc = mtgp_population_fitness(pop_d, 4, pop_d + 3, 4, P, T, N, table, &dd, size_parsimony, fit_d, nullptr,
-                               base + off_ws, ws_bytes, stream);
-  if (rc) return rc;
+  if (!split) {
+    MTGP_CUDA_TRY(cudaMemcpyAsync(base + off_pop, population_host, pop_bytes, cudaMemcpyHostToDevice, s));
+    rc = mtgp_population_fitness(pop_d, 4, pop_d + 3, 4, P, T, N, table, &dd, size_parsimony, fit_d, nullptr,
+                                 base + off_ws, ws_bytes, stream);
+    if (rc) return rc;
+  } else {
+    // Upload overlapped with evaluation: a small PROLOGUE slice of the population (1/8) is uploaded and starts
+    // evaluating while the rest is still crossing PCIe; the two evaluations run on their own streams, so the warps
+    // of the second fill the SM slots the first one frees (both kernels are persistent).  Individuals are
+    // independent (genetic_programming.py:252 vmaps over them), so slicing changes no result.
+    cudaStream_t cs = sc->copy_s, k0 = sc->comp_s[0], k1 = sc->comp_s[1];
+    cudaEvent_t ev_data = sc->ev[0], ev_a = sc->ev[1], ev_b = sc->ev[2], done_a = sc->ev[3], done_b = sc->ev[4];
+    const size_t row_bytes = (size_t)T * N * 4 * sizeof(float);
+    MTGP_CUDA_TRY(cudaEventRecord(ev_data, s));  // the data arrays (and whatever the caller queued before) are on s
+    MTGP_CUDA_TRY(cudaStreamWaitEvent(cs, ev_data, 0));
+    MTGP_CUDA_TRY(cudaMemcpyAsync(base + off_pop, population_host, PA * row_bytes, cudaMemcpyHostToDevice, cs));
+    MTGP_CUDA_TRY(cudaEventRecord(ev_a, cs));
+    MTGP_CUDA_TRY(cudaMemcpyAsync(base + off_pop + PA * row_bytes, reinterpret_cast<const unsigned char*>(population_host) + PA * row_bytes,
+                                  (size_t)(P - PA) * row_bytes, cudaMemcpyHostToDevice, cs));
+    MTGP_CUDA_TRY(cudaEventRecord(ev_b, cs));
+    MTGP_CUDA_TRY(cudaStreamWaitEvent(k0, ev_a, 0));
+    rc = mtgp_population_fitness(pop_d, 4, pop_d + 3, 4, (int)PA, T, N, table, &dd, size_parsimony, fit_d, nullptr,
+                                 base + off_ws, ws_a, k0);
+    if (rc) { cudaStreamSynchronize(k0); return rc; }
+    MTGP_CUDA_TRY(cudaEventRecord(done_a, k0));
+    MTGP_CUDA_TRY(cudaStreamWaitEvent(k1, ev_b, 0));
+    const float* pop_b = pop_d + PA * (size_t)T * N * 4;
+    rc = mtgp_population_fitness(pop_b, 4, pop_b + 3, 4, (int)(P - PA), T, N, table, &dd, size_parsimony, fit_d + PA, nullptr,
+                                 base + off_ws + align_up(ws_a, 256), ws_b, k1);
+    if (rc) { cudaStreamSynchronize(k0); cudaStreamSynchronize(k1); return rc; }
+    MTGP_CUDA_TRY(cudaEventRecord(done_b, k1));
+    MTGP_CUDA_TRY(cudaStreamWaitEvent(s, done_a, 0));
+    MTGP_CUDA_TRY(cudaStreamWaitEvent(s, done_b, 0));
+  }
   MTGP_CUDA_TRY(cudaMemcpyAsync(fitness_host, fit_d, (size_t)P * 4, cudaMemcpyDeviceToHost, s));
   MTGP_CUDA_TRY(cudaStreamSynchronize(s));
   return MTGP_OK;

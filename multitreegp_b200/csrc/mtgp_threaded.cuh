@@ -275,11 +275,24 @@ static __host__ __device__ __forceinline__ float mtgp_th_slow_op(uint32_t sop, f
 #define TH_PARNUM_a "0"
 #define TH_PARNUM_b "1"
 #if MTGP_TH_SETS == 1
-// one register set: the fields a handler still needs after the fetch of its successor (the successor's handler
-// index, the store offset) are saved first; ptxas folds the copies into the jump-table load / the address add
+// one register set: the successor's handler index is saved before the fetch overwrites it (ptxas folds the copy into
+// the jump-table load).  In the arithmetic handlers the fetch is the LAST thing before the branch (TH_NEXT_LATE): issued
+// earlier, ptxas loads into other registers and copies four words back; the branch latency covers the load either way.
 #define TH_NEXT(N) " mov.u32 nx," #N "0;\n add.u32 %1,%1,16;\n ld.shared.v4.u32 {" #N "0," #N "1," #N "2," #N "3},[%1];\n"
+#ifndef MTGP_TH_FETCH_LATE
+#define MTGP_TH_FETCH_LATE 1
+#endif
+#if MTGP_TH_FETCH_LATE
+#define TH_NEXT_EARLY(N) ""
+#define TH_NEXT_LATE(N) TH_NEXT(N)
+#else
+#define TH_NEXT_EARLY(N) TH_NEXT(N)
+#define TH_NEXT_LATE(N) ""
+#endif
 #else
 #define TH_NEXT(N) " add.u32 %1,%1,16;\n ld.shared.v4.u32 {" #N "0," #N "1," #N "2," #N "3},[%1];\n"
+#define TH_NEXT_EARLY(N) TH_NEXT(N)
+#define TH_NEXT_LATE(N) ""
 #endif
 #ifdef MTGP_TH_CENTRAL
 #define TH_GO(C, N) " bra DISP_" #C ";\n"               // shared dispatch of this register set
@@ -303,7 +316,7 @@ static __host__ __device__ __forceinline__ float mtgp_th_slow_op(uint32_t sop, f
 #define TH_STORE_D " st.shared.f32 [sa],%0;\n"
 #define TH_NOSTORE_A(C) ""
 #define TH_NOSTORE_D ""
-#define TH_OP(PRE, OP, X, Y, C, N, ST) PRE(C) ST##_A(C) TH_NEXT(N) " " OP " %0," X "," Y ";\n" ST##_D TH_GO(C, N)
+#define TH_OP(PRE, OP, X, Y, C, N, ST) PRE(C) ST##_A(C) TH_NEXT_EARLY(N) " " OP " %0," X "," Y ";\n" ST##_D TH_NEXT_LATE(N) TH_GO(C, N)
 
 #define TH_B_ADD_AM(C, N, ST) TH_OP(TH_YM, "add.rn.f32", "%0", "t1", C, N, ST)
 #define TH_B_ADD_AI(C, N, ST) TH_OP(TH_YI, "add.rn.f32", "%0", "t1", C, N, ST)
@@ -320,8 +333,8 @@ static __host__ __device__ __forceinline__ float mtgp_th_slow_op(uint32_t sop, f
 #define TH_B_RSB_AI(C, N, ST) TH_OP(TH_YI, "sub.rn.f32", "t1", "%0", C, N, ST)
 #define TH_B_SUB_MM(C, N, ST) TH_OP(TH_XMYM, "sub.rn.f32", "t0", "t1", C, N, ST)
 #define TH_B_RSB_MI(C, N, ST) TH_OP(TH_XMYI, "sub.rn.f32", "t1", "t0", C, N, ST)
-#define TH_B_LOAD_M(C, N, ST) TH_XM(C) ST##_A(C) TH_NEXT(N) " mov.f32 %0,t0;\n" ST##_D TH_GO(C, N)
-#define TH_B_LOAD_I(C, N, ST) TH_XI(C) ST##_A(C) TH_NEXT(N) " mov.f32 %0,t0;\n" ST##_D TH_GO(C, N)
+#define TH_B_LOAD_M(C, N, ST) TH_XM(C) ST##_A(C) TH_NEXT_EARLY(N) " mov.f32 %0,t0;\n" ST##_D TH_NEXT_LATE(N) TH_GO(C, N)
+#define TH_B_LOAD_I(C, N, ST) TH_XI(C) ST##_A(C) TH_NEXT_EARLY(N) " mov.f32 %0,t0;\n" ST##_D TH_NEXT_LATE(N) TH_GO(C, N)
 
 #define TH_B_ST(C, N) TH_STORE(C) TH_NEXT(N) TH_GO(C, N)
 #define TH_B_LDY_M(C, N) " add.u32 ae,%6," #C "2;\n ld.shared.f32 %5,[ae];\n" TH_NEXT(N) TH_GO(C, N)

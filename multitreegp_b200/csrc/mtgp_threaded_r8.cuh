@@ -25,6 +25,9 @@
 #if MTGP_TH8_SETS == 1
 #define T8_NEXT(N) " mov.u32 nx,i" #N "0;\n add.u32 %8,%8,16;\n ld.shared.v4.u32 {i" #N "0,i" #N "1,i" #N "2,i" #N "3},[%8];\n"
 #define T8_GO(C, N) " brx.idx nx, TBLa;\n"
+#ifndef MTGP_TH8_FETCH_LATE
+#define MTGP_TH8_FETCH_LATE 1  // arithmetic handlers fetch their successor last (see TH_NEXT_LATE in mtgp_threaded.cuh)
+#endif
 #else
 #define T8_NEXT(N) " add.u32 %8,%8,16;\n ld.shared.v4.u32 {i" #N "0,i" #N "1,i" #N "2,i" #N "3},[%8];\n"
 #ifdef MTGP_TH_CENTRAL
@@ -60,7 +63,14 @@
 #define T8_ALL(OP, XF, YF) \
   T8_L(OP, XF, YF, 0) T8_L(OP, XF, YF, 1) T8_L(OP, XF, YF, 2) T8_L(OP, XF, YF, 3) T8_L(OP, XF, YF, 4) T8_L(OP, XF, YF, 5) \
   T8_L(OP, XF, YF, 6) T8_L(OP, XF, YF, 7)
-#define T8_OP(PRE, OP, XF, YF, C, N, ST) PRE(C) ST##_A(C) T8_NEXT(N) T8_ALL(OP, XF, YF) ST##_D T8_GO(C, N)
+#if MTGP_TH8_SETS == 1 && MTGP_TH8_FETCH_LATE
+#define T8_NEXT_EARLY(N) ""
+#define T8_NEXT_LATE(N) T8_NEXT(N)
+#else
+#define T8_NEXT_EARLY(N) T8_NEXT(N)
+#define T8_NEXT_LATE(N) ""
+#endif
+#define T8_OP(PRE, OP, XF, YF, C, N, ST) PRE(C) ST##_A(C) T8_NEXT_EARLY(N) T8_ALL(OP, XF, YF) ST##_D T8_NEXT_LATE(N) T8_GO(C, N)
 
 #define T8_B_ADD_AM(C, N, ST) T8_OP(T8_YM, "add.rn.f32", T8_A, T8_Y, C, N, ST)
 #define T8_B_ADD_AI(C, N, ST) T8_OP(T8_YI, "add.rn.f32", T8_A, T8_YIM, C, N, ST)

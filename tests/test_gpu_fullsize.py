@@ -106,3 +106,22 @@ def test_empty_and_maximum_sizes(engine, oracle):
     from multitreegp_b200._lib import MtgpError
     with pytest.raises(MtgpError):
         engine.rollout_fitness(_dev(engine, np.zeros((2, 1, 600, 4), np.float32)), lib.table(), dd)
+
+
+def test_host_entry_overlapped_upload_equals_device_entry(engine):
+    """mtgp_population_fitness_host uploads populations of 32 MB and more as a prologue slice + the rest, evaluated on two
+    streams while the upload is still running: the fitness vector must be the device entry point's, bit for bit
+    (and a population below the threshold, which takes the single-upload path, likewise)."""
+    from multitreegp_b200.engine import DeviceData
+    from tests import util
+    rng = np.random.default_rng(17)
+    for P in (12000, 2000):  # 3 trees x 63 rows x 16 B = 3 024 B per individual: 36 MB / 6 MB
+        lib, pop, data = util.control_case("acrobot", abi.EVAL_DYNAMIC, rng, P=P, B=8, T_end=1.0, dt0=0.05, obs_noise=0.1,
+                                           depth=6, N=63)
+        assert (pop.nbytes >= (32 << 20)) == (P == 12000)
+        dev = engine.rollout_fitness(_dev(engine, pop), lib.table(), DeviceData(data, engine.device),
+                                     size_parsimony=0.01)["fitness"].cpu().numpy()
+        host = engine.rollout_fitness_host(pop, lib.table(), data, size_parsimony=0.01)
+        assert (host.view(np.uint32) == dev.view(np.uint32)).all()
+        again = engine.rollout_fitness_host(pop, lib.table(), data, size_parsimony=0.01)  # streams / events reused
+        assert (again.view(np.uint32) == dev.view(np.uint32)).all()
