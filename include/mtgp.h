@@ -242,7 +242,11 @@ MTGP_API int mtgp_rollout(mtgp_bytecode bc, int P, int T, int N, const mtgp_node
  *   fitness[p] += size_parsimony * sum_t live[p,t]      (genetic_programming.py:424)
  * on device buffers (what the XLA-FFI handler forwards to), and the same with HOST buffers
  * (population, data and fitness in host memory; H2D/D2H copies are part of the call) -- the
- * latter is what bench.py times as `e2e`. */
+ * latter is what bench.py times as `e2e`.  The host form orders itself after the work already queued on `stream`,
+ * synchronises before it returns, and may use library-owned streams in between: populations of 32 MB and more are
+ * uploaded as a prologue slice + the rest and evaluated on two internal streams while the upload is still running
+ * (individuals are independent, the results are the bits of the single-launch path); pinned host memory is what
+ * makes that overlap real.  The scratch and the streams are per device (mtgp_release_scratch frees them). */
 MTGP_API int mtgp_population_fitness(const float* nodes, int nodes_stride, const float* coef, int coef_stride,
                             int P, int T, int N, const mtgp_node_table* table,
                             const mtgp_rollout_desc* desc, float size_parsimony, float* fitness,
