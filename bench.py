@@ -687,6 +687,19 @@ def bench_pointwise(eng, dev, K, peaks, peak_src, with_cpu, world=1, rank=0):
                                 f"(n_vars + 1) x 4 B / t is the streaming model of SURVEY 8(d), quoted against the {peak_src} copy "
                                 "peak only as that model asks; it is NOT an HBM roofline fraction"}}
     if world == 1:
+        # end to end through the evaluator's host call: pinned host population (408 MB), X, Y -> fitness in host memory
+        import torch as _t
+        pop_h = _t.from_numpy(np.ascontiguousarray(pop)).pin_memory()
+        for _ in range(2):
+            eng.pointwise_fitness_host(pop_h.numpy(), table, X, Y)
+        t0 = time.perf_counter()
+        for _ in range(K):
+            eng.pointwise_fitness_host(pop_h.numpy(), table, X, Y)
+        ms_e = (time.perf_counter() - t0) * 1e3 / K
+        out["e2e"] = {"value": node_evals / (ms_e * 1e-3), "unit": "live node-evals/s", "ms_per_step": ms_e,
+                      "h2d_bytes_per_step": int(pop.nbytes + X.nbytes + Y.nbytes), "d2h_bytes_per_step": int(4 * C4["P"]),
+                      "note": "mtgp_population_fitness_pointwise_host: upload in four slices, evaluated on two streams as they land"}
+        del pop_h
         ms8, live8, *_ = run(8)
         out["wide_variant"] = {"n_vars": 8, "ms_per_step": ms8, "value": live8 * C4["n_points"] / (ms8 * 1e-3),
                                "unit": "live node-evals/s"}

@@ -399,7 +399,7 @@ struct DeviceScratch {
   // the host entry points overlap the population upload with the evaluation (see mtgp_population_fitness_host):
   // one copy stream, two compute streams, events; created on first use, owned with the scratch
   cudaStream_t copy_s = nullptr, comp_s[2] = {nullptr, nullptr};
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 std::mutex g_scratch_table_mu;
 std::map<int, std::unique_ptr<DeviceScratch>> g_scratch;
@@ -439,6 +439,15 @@ int validate_ts_host(const float* ts, int K) {
 }
 }  // namespace
 
+// call with s.mu held: the streams / events of the overlapped uploads
+static int scratch_streams(DeviceScratch& sc) {
+  if (sc.copy_s) return MTGP_OK;
+  MTGP_CUDA_TRY(cudaStreamCreateWithFlags(&sc.copy_s, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) MTGP_CUDA_TRY(cudaStreamCreateWithFlags(&sc.comp_s[i], cudaStreamNonBlocking));
+  for (int i = 0; i < 8; i++) MTGP_CUDA_TRY(cudaEventCreateWithFlags(&sc.ev[i], cudaEventDisableTiming));
+  return MTGP_OK;
+}
+
 int mtgp_release_scratch(void) {
   std::lock_guard<std::mutex> lk(g_scratch_table_mu);
   for (auto& kv : g_scratch) {
@@ -449,7 +458,7 @@ int mtgp_release_scratch(void) {
     if (kv.second->copy_s) {
       cudaStreamDestroy(kv.second->copy_s);
       for (int i = 0; i < 2; i++) cudaStreamDestroy(kv.second->comp_s[i]);
-      for (int i = 0; i < 6; i++) cudaEventDestroy(kv.second->ev[i]);
+      for (int i = 0; i < 8; i++) cudaEventDestroy(kv.second->ev[i]);
       kv.second->copy_s = nullptr;
     }
   }
@@ -476,11 +485,7 @@ int mtgp_population_fitness_host(const float* population_host, int P, int T, int
   DeviceScratch* sc = scratch_of_current_device();
   if (!sc) { mtgp_set_error("cudaGetDevice failed"); return MTGP_ERR_CUDA; }
   std::lock_guard<std::mutex> scratch_lock(sc->mu);  // the scratch is this call's until it has synchronised
-  if (split && !sc->copy_s) {
-    MTGP_CUDA_TRY(cudaStreamCreateWithFlags(&sc->copy_s, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) MTGP_CUDA_TRY(cudaStreamCreateWithFlags(&sc->comp_s[i], cudaStreamNonBlocking));
-    for (int i = 0; i < 6; i++) MTGP_CUDA_TRY(cudaEventCreateWithFlags(&sc->ev[i], cudaEventDisableTiming));
-  }
+  if (split && (rc = scratch_streams(*sc))) return rc;
   // layout of the scratch: population | fitness | data arrays | workspace
   size_t off_pop = 0, off_fit, off_x0, off_ts, off_tg, off_keys, off_par, off_ys, off_ws, total;
   {
@@ -567,7 +572,13 @@ int mtgp_population_fitness_pointwise_host(const float* population_host, int P, 
   }
   cudaStream_t s = (cudaStream_t)stream;
   const size_t pop_bytes = (size_t)P * T * N * 4 * sizeof(float);
-  const size_t ws_bytes = mtgp_workspace_bytes_pointwise(P, T, N, n_points, n_vars);
+  // populations of 32 MB and more: four slices, uploaded back to back on a copy stream and evaluated on two compute
+  // streams as they land (the kernel takes longer than the upload of a slice, so only the first upload is exposed)
+  const bool split = pop_bytes >= ((size_t)32 << 20) && P >= 64;
+  const int n_chunks = split ? 4 : 1;
+  const int Pc = split ? (((P + n_chunks - 1) / n_chunks + 7) & ~7) : P;
+  const size_t ws_one = mtgp_workspace_bytes_pointwise(Pc, T, N, n_points, n_vars);
+  const size_t ws_bytes = split ? 2 * align_up(ws_one, 256) : ws_one;
   size_t o = align_up(pop_bytes, 256);
   const size_t off_fit = o; o = align_up(o + (size_t)P * 4, 256);
   const size_t off_x = o; o = align_up(o + (size_t)n_points * n_vars * 4, 256);
@@ -576,19 +587,50 @@ int mtgp_population_fitness_pointwise_host(const float* population_host, int P, 
   DeviceScratch* sc = scratch_of_current_device();
   if (!sc) { mtgp_set_error("cudaGetDevice failed"); return MTGP_ERR_CUDA; }
   std::lock_guard<std::mutex> scratch_lock(sc->mu);
+  if (split && (rc = scratch_streams(*sc))) return rc;
   void* base_v = nullptr;
   if ((rc = scratch_reserve(*sc, o + ws_bytes, &base_v))) return rc;
   unsigned char* base = static_cast<unsigned char*>(base_v);
-  MTGP_CUDA_TRY(cudaMemcpyAsync(base, population_host, pop_bytes, cudaMemcpyHostToDevice, s));
   MTGP_CUDA_TRY(cudaMemcpyAsync(base + off_x, X_host, (size_t)n_points * n_vars * 4, cudaMemcpyHostToDevice, s));
   MTGP_CUDA_TRY(cudaMemcpyAsync(base + off_y, Y_host, (size_t)n_points * T * 4, cudaMemcpyHostToDevice, s));
   const float* pop_d = reinterpret_cast<const float*>(base);
   float* fit_d = reinterpret_cast<float*>(base + off_fit);
-  rc = mtgp_population_fitness_pointwise(pop_d, 4, pop_d + 3, 4, P, T, N, table,
-                                         reinterpret_cast<const float*>(base + off_x),
-                                         reinterpret_cast<const float*>(base + off_y), n_points, n_vars, max_fitness,
-                                         size_parsimony, fit_d, base + off_ws, ws_bytes, stream);
-  if (rc) return rc;
+  const float* X_d = reinterpret_cast<const float*>(base + off_x);
+  const float* Y_d = reinterpret_cast<const float*>(base + off_y);
+  if (!split) {
+    MTGP_CUDA_TRY(cudaMemcpyAsync(base, population_host, pop_bytes, cudaMemcpyHostToDevice, s));
+    rc = mtgp_population_fitness_pointwise(pop_d, 4, pop_d + 3, 4, P, T, N, table, X_d, Y_d, n_points, n_vars, max_fitness,
+                                           size_parsimony, fit_d, base + off_ws, ws_bytes, stream);
+    if (rc) return rc;
+  } else {
+    const size_t row_bytes = (size_t)T * N * 4 * sizeof(float);
+    cudaStream_t cs = sc->copy_s;
+    MTGP_CUDA_TRY(cudaEventRecord(sc->ev[0], s));  // X, Y (and whatever the caller queued before) are on s
+    MTGP_CUDA_TRY(cudaStreamWaitEvent(cs, sc->ev[0], 0));
+    for (int c = 0; c < n_chunks; c++) {
+      const int p0 = c * Pc, pn = (P - p0 < Pc) ? P - p0 : Pc;
+      if (pn <= 0) break;
+      MTGP_CUDA_TRY(cudaMemcpyAsync(base + (size_t)p0 * row_bytes,
+                                    reinterpret_cast<const unsigned char*>(population_host) + (size_t)p0 * row_bytes,
+                                    (size_t)pn * row_bytes, cudaMemcpyHostToDevice, cs));
+      MTGP_CUDA_TRY(cudaEventRecord(sc->ev[1 + c], cs));
+    }
+    for (int c = 0; c < n_chunks; c++) {
+      const int p0 = c * Pc, pn = (P - p0 < Pc) ? P - p0 : Pc;
+      if (pn <= 0) break;
+      cudaStream_t k = sc->comp_s[c & 1];  // slices c and c + 2 share a stream and a workspace half, in order
+      MTGP_CUDA_TRY(cudaStreamWaitEvent(k, sc->ev[1 + c], 0));
+      const float* pc = pop_d + (size_t)p0 * T * N * 4;
+      rc = mtgp_population_fitness_pointwise(pc, 4, pc + 3, 4, pn, T, N, table, X_d, Y_d, n_points, n_vars, max_fitness,
+                                             size_parsimony, fit_d + p0, base + off_ws + (size_t)(c & 1) * align_up(ws_one, 256),
+                                             ws_one, k);
+      if (rc) { cudaStreamSynchronize(sc->comp_s[0]); cudaStreamSynchronize(sc->comp_s[1]); return rc; }
+    }
+    for (int i = 0; i < 2; i++) {
+      MTGP_CUDA_TRY(cudaEventRecord(sc->ev[5 + i], sc->comp_s[i]));
+      MTGP_CUDA_TRY(cudaStreamWaitEvent(s, sc->ev[5 + i], 0));
+    }
+  }
   MTGP_CUDA_TRY(cudaMemcpyAsync(fitness_host, fit_d, (size_t)P * 4, cudaMemcpyDeviceToHost, s));
   MTGP_CUDA_TRY(cudaStreamSynchronize(s));
   return MTGP_OK;

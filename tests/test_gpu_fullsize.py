@@ -125,3 +125,22 @@ def test_host_entry_overlapped_upload_equals_device_entry(engine):
         assert (host.view(np.uint32) == dev.view(np.uint32)).all()
         again = engine.rollout_fitness_host(pop, lib.table(), data, size_parsimony=0.01)  # streams / events reused
         assert (again.view(np.uint32) == dev.view(np.uint32)).all()
+
+
+def test_pointwise_host_entry_overlapped_upload_equals_device_entry(engine):
+    """mtgp_population_fitness_pointwise_host with a population above the 32 MB threshold (four slices on two streams,
+    a ragged last slice) and below it: the bits of the device entry point."""
+    import bench
+    from multitreegp_b200.node_library import NodeLibrary
+    from bench_support.synthetic import pointwise_data, sample_population
+    rng = np.random.default_rng(23)
+    lib = NodeLibrary(bench.OPS_SR, [["x0", "x1"]], [1])
+    X, Y = pointwise_data(rng, 700, 2)
+    for P in (9001, 500):  # 255 rows x 16 B = 4 080 B per individual: 36.7 MB / 2 MB
+        pop = sample_population(rng, P, lib, 6, 255)
+        assert (pop.nbytes >= (32 << 20)) == (P == 9001)
+        dev = engine.pointwise_fitness(_dev(engine, pop), lib.table(), _dev(engine, X), _dev(engine, Y),
+                                       size_parsimony=0.002).cpu().numpy()
+        for _ in range(2):  # streams / events / workspace halves reused
+            host = engine.pointwise_fitness_host(pop, lib.table(), X, Y, size_parsimony=0.002)
+            assert (host.view(np.uint32) == dev.view(np.uint32)).all()
