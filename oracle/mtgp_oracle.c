@@ -866,3 +866,18 @@ ORACLE_API float oracle_env_fitness(const mtgp_rollout_desc* d, int b, const flo
   env_init(&e, d, b);
   return env_fitness(&e, xs, us, target, ts, K);
 }
+
+/* the evaluators' vector field (_drift of feedforward_evaluate.py:104-110 / dynamic_evaluate.py:107-118 /
+   SR_evaluator.py:85-88) at one point: y [D + state_size] -> dy, trajectory b of the descriptor */
+ORACLE_API int oracle_vector_field(const float* cand /* [T,N,4] */, int T, int N, const mtgp_node_table* tab,
+                                   const mtgp_rollout_desc* d, int b, float t, const float* y, float* dy) {
+  rollout_ctx c;
+  float scratch[MTGP_MAX_NODES + 1];
+  if (N > MTGP_MAX_NODES) return -1;
+  c.d = d; c.tab = tab; c.cand = cand; c.T = T; c.N = N;
+  c.target = d->targets ? d->targets + (size_t)b * d->n_targets : NULL;
+  c.scratch = scratch;
+  if (d->kind != MTGP_EVAL_SR) env_init(&c.env, d, b);
+  vector_field(&c, t, y, dy);
+  return 0;
+}

@@ -175,3 +175,64 @@ def test_cuda_tree_values_equal_reference_interpreter(case):
             assert np.array_equal(pred[m].view(np.uint32), ref[p][m].view(np.uint32))
         else:
             np.testing.assert_allclose(pred, ref[p], rtol=RTOL, atol=1e-6, equal_nan=True)
+
+
+EV_CASES = {"static_harmonic": ("harmonic", abi.EVAL_STATIC), "static_acrobot": ("acrobot", abi.EVAL_STATIC),
+            "dynamic_acrobot": ("acrobot", abi.EVAL_DYNAMIC), "dynamic_reactor": ("reactor", abi.EVAL_DYNAMIC)}
+
+
+def _ev_case(g, name):
+    from tests import util
+    env_name, kind = EV_CASES[name]
+    env = util.ENVS[env_name](0.05, 0.0)
+    S = 2 if kind == abi.EVAL_DYNAMIC else 0
+    lib = util.control_library(env, kind, 2)
+    data = RolloutData(kind=kind, env_id=env.env_id, x0=g[f"ev_{name}_x0"], ts=g[f"ev_{name}_ts"], dt0=0.05, max_fitness=1e4,
+                       targets=g[f"ev_{name}_targets"], obs_keys=np.zeros((g[f"ev_{name}_x0"].shape[0], 2), np.uint32),
+                       params=g[f"ev_{name}_params"], n_obs=env.n_obs, state_size=S, obs_noise=0.0)
+    return lib, g[f"ev_{name}_pop"], data, S
+
+
+@pytest.mark.parametrize("name", sorted(EV_CASES))
+def test_evaluators_around_the_solve_equal_reference_classes(name):
+    """The reference's feedforward / dynamic Evaluator classes, run unmodified with diffrax.diffeqsolve replaced by an
+    injection of the oracle's saved states: what they hand to the solver, their post-pass over the save points (f_obs,
+    readout), env.fitness_function, the penalty + mean + clip of __call__ and _drift -- against the oracle's."""
+    g = _load("refshim_evaluators.npz")
+    lib, pop, data, S = _ev_case(g, name)
+    orc = pyoracle.rollout_population(pop, lib.table(), data, trajectories=True)
+    sol = np.concatenate([orc["xs"], orc["activities"]], axis=-1) if S else orc["xs"]
+    # the saved states that were injected are the oracle's solve of today (regression pin of the restated solve)
+    assert np.array_equal(sol.view(np.uint32), g[f"ev_{name}_sol_ys"].view(np.uint32))
+    # what the reference handed to diffeqsolve as y0: x0 (static) / concatenate([x0, zeros(state_size)]) (dynamic_evaluate.py:89)
+    want_y0 = np.concatenate([data.x0, np.zeros((data.B, S), np.float32)], axis=1)
+    assert np.array_equal(g[f"ev_{name}_y0"], np.broadcast_to(want_y0, g[f"ev_{name}_y0"].shape))
+    # post-pass at the save points; rows after an event are the inf pre-fill of SaveAt on both sides
+    fin = np.isfinite(g[f"ev_{name}_ys"])
+    assert np.array_equal(fin, np.isfinite(orc["ys"]))
+    np.testing.assert_allclose(orc["ys"][fin], g[f"ev_{name}_ys"][fin], rtol=RTOL, atol=1e-5)
+    fu = np.isfinite(g[f"ev_{name}_us"])
+    assert np.array_equal(fu, np.isfinite(orc["us"]))
+    np.testing.assert_allclose(orc["us"][fu], g[f"ev_{name}_us"][fu], rtol=RTOL, atol=1e-5)
+    ft = np.isfinite(g[f"ev_{name}_traj_fitness"])
+    assert np.array_equal(ft, np.isfinite(orc["traj_fitness"]))
+    np.testing.assert_allclose(orc["traj_fitness"][ft], g[f"ev_{name}_traj_fitness"][ft], rtol=RTOL)
+    np.testing.assert_allclose(orc["fitness"], g[f"ev_{name}_fitness"], rtol=RTOL)
+    # the vector field at the sampled points
+    L = pyoracle.lib()
+    L.oracle_vector_field.restype = C.c_int
+    desc, keep = data.to_desc_host()
+    pts, ref = g[f"ev_{name}_points"], g[f"ev_{name}_drift"]
+    got = np.empty_like(ref)
+    table = lib.table()
+    for p in range(pop.shape[0]):
+        cand = np.ascontiguousarray(pop[p])
+        for k in range(pts.shape[1]):
+            y = np.ascontiguousarray(pts[p, k])
+            assert L.oracle_vector_field(C.c_void_p(cand.ctypes.data), cand.shape[0], cand.shape[1], C.byref(table), C.byref(desc),
+                                         0, C.c_float(0.25), C.c_void_p(y.ctypes.data), C.c_void_p(got[p, k].ctypes.data)) == 0
+    del keep
+    assert np.array_equal(np.isfinite(got), np.isfinite(ref))
+    m = np.isfinite(ref)
+    scale = np.abs(ref[m]).max()
+    np.testing.assert_allclose(got[m], ref[m], rtol=RTOL, atol=1e-6 * scale)

@@ -181,11 +181,91 @@ def record_population():
                 pop_returned_population_is_input=np.array(np.array_equal(np.asarray(same), pops)))
 
 
+# ---- the evaluators around diffrax.diffeqsolve ----------------------------------------------------------
+def record_evaluators():
+    """feedforward_evaluate.Evaluator / dynamic_evaluate.Evaluator (the reference's classes, unmodified) with the ONE
+    third-party call they make -- diffrax.diffeqsolve -- replaced by an injection of the saved states the oracle's own
+    solve returns for the same inputs.  Everything else is the reference executing: the vmap over trajectories and the
+    data tuple layout (evaluate_candidate), env.initialize_parameters, the initial state handed to the solver, the
+    post-pass over the save points (f_obs scan, readout, dynamic_evaluate.py:98-103 / feedforward_evaluate.py:95-99),
+    env.fitness_function, the NaN / inf penalty + mean + clip of __call__ (:48-51), and _drift (the vector field,
+    evaluated directly at sampled points).  Observation noise is off (jax.random is third-party)."""
+    import diffrax  # the shim
+    from MultiTreeGP.evaluators import dynamic_evaluate, feedforward_evaluate
+    from multitreegp_b200 import abi
+    from oracle import pyoracle
+    from tests import util
+    pyoracle.build()
+    ref_env = {"acrobot": Acrobot, "harmonic": HarmonicOscillator, "reactor": StirredTankReactor}
+    ops_ref = [("+", lambda x, y: x + y, 2, 0.5), ("-", lambda x, y: x - y, 2, 0.1), ("*", lambda x, y: x * y, 2, 0.5),
+               ("sin", lambda x: jnp.sin(x), 1, 0.1), ("cos", lambda x: jnp.cos(x), 1, 0.1)]
+    out = {}
+    rng = np.random.default_rng(314)
+    for name, env_name, kind in (("static_harmonic", "harmonic", abi.EVAL_STATIC), ("static_acrobot", "acrobot", abi.EVAL_STATIC),
+                                 ("dynamic_acrobot", "acrobot", abi.EVAL_DYNAMIC), ("dynamic_reactor", "reactor", abi.EVAL_DYNAMIC)):
+        P, B, S = 6, 4, (2 if kind == abi.EVAL_DYNAMIC else 0)
+        lib, pop, data = util.control_case(env_name, kind, rng, P=P, B=B, T_end=4.0, dt_save=0.2, dt0=0.05, obs_noise=0.0,
+                                           param_mode="Different" if env_name != "acrobot" else "Constant")
+        _, variables, layers = util.control_library_args(util.ENVS[env_name](0.05, 0.0), kind, 2)
+        gp = GeneticProgramming(2, 20, (lambda *a, **k: 0.0), ops_ref, variables, jnp.array(layers), max_init_depth=4, max_nodes=30)
+        assert gp.string_to_node == lib.string_to_node
+        env = ref_env[env_name](0.05, 0.0)
+        ev = (dynamic_evaluate.Evaluator(env, S, 0.05) if kind == abi.EVAL_DYNAMIC else feedforward_evaluate.Evaluator(env, 0.05))
+        orc = pyoracle.rollout_population(pop, lib.table(), data, trajectories=True)
+        sol_ys = np.concatenate([orc["xs"], orc["activities"]], axis=-1) if kind == abi.EVAL_DYNAMIC else orc["xs"]
+        D = data.x0.shape[1]
+        keys = np.zeros((B, 2), np.uint32)
+        params = tuple(A(data.params[:, i]) for i in range(data.params.shape[1]))
+        ref_data = (A(data.x0), A(data.ts), A(data.targets), jnp.asarray(keys), jnp.asarray(keys), params)
+        r_ys = np.empty((P, B, data.K, env.n_obs), F); r_us = np.empty((P, B, data.K, 1), F)
+        r_fit = np.empty((P, B), F); r_call = np.empty(P, F); y0s = np.empty((P, B, D + S), F)
+        n_pts = 5
+        pts = np.empty((P, n_pts, D + S), F); drifts = np.empty((P, n_pts, D + S), F)
+        with np.errstate(all="ignore"), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for p in range(P):
+                diffrax.INJECT[:] = [sol_ys[p, b] for b in range(B)]
+                diffrax.CALLS.clear()
+                res = ev.evaluate_candidate(A(pop[p]), ref_data, gp.vmap_foriloop)
+                xs_r, ys_r, us_r, fit_r = res[0], res[1], res[2], res[-1]
+                assert np.array_equal(np.asarray(xs_r), orc["xs"][p], equal_nan=True)
+                r_ys[p], r_us[p], r_fit[p] = np.asarray(ys_r), np.asarray(us_r).reshape(B, data.K, 1), np.asarray(fit_r)
+                for b in range(B):
+                    c = diffrax.CALLS[b]
+                    y0s[p, b] = c["y0"]
+                    assert c["t0"] == float(data.ts[0]) and c["t1"] == float(data.ts[-1]) and c["dt0"] == F(0.05)
+                    assert c["max_steps"] == 16 ** 4 and c["throw"] is False and c["has_event"]
+                diffrax.INJECT[:] = [sol_ys[p, b] for b in range(B)]
+                r_call[p] = F(ev(A(pop[p][..., 3:]), A(pop[p][..., :3]), ref_data, gp.vmap_foriloop))
+                # the vector field at sampled points of trajectory 0's neighbourhood
+                e0 = copy_env(ev.env, tuple(q[0] for q in params), ref_data[1])
+                tgt = ref_data[2][0]
+                for k in range(n_pts):
+                    pt = (np.concatenate([data.x0[0], np.zeros(S, F)]) + rng.normal(size=D + S).astype(F) * F(0.7)).astype(F)
+                    args = ((e0, A(pop[p][:S]), A(pop[p][S:]), None, tgt, gp.vmap_foriloop) if kind == abi.EVAL_DYNAMIC
+                            else (e0, A(pop[p]), None, tgt, gp.vmap_foriloop))
+                    pts[p, k] = pt
+                    drifts[p, k] = np.asarray(ev._drift(F(0.25), A(pt), args), dtype=F).reshape(-1)
+        out.update({f"ev_{name}_pop": pop, f"ev_{name}_x0": data.x0, f"ev_{name}_ts": data.ts, f"ev_{name}_targets": data.targets,
+                    f"ev_{name}_params": data.params, f"ev_{name}_sol_ys": sol_ys, f"ev_{name}_y0": y0s, f"ev_{name}_ys": r_ys,
+                    f"ev_{name}_us": r_us, f"ev_{name}_traj_fitness": r_fit, f"ev_{name}_fitness": r_call,
+                    f"ev_{name}_points": pts, f"ev_{name}_drift": drifts})
+    return out
+
+
+def copy_env(env, params, ts):
+    import copy
+    e = copy.copy(env)
+    e.initialize_parameters(params, ts)
+    return e
+
+
 def main():
     meta = dict(recorder="tools/record_reference_shim_golden.py", reference=REF, numpy=np.__version__,
                 note="reference code executed over tools/refshim (numpy float32), noise-free f_obs")
     trees, env = record_trees(), record_env()
     trees.update(record_population())
+    np.savez_compressed(os.path.join(OUT, "refshim_evaluators.npz"), meta=np.array(repr(meta)), **record_evaluators())
     np.savez_compressed(os.path.join(OUT, "refshim_trees.npz"), meta=np.array(repr(meta)), **trees)
     np.savez_compressed(os.path.join(OUT, "refshim_env.npz"), meta=np.array(repr(meta)), **env)
     print("recorded", sorted(trees), sorted(env))

@@ -30,3 +30,14 @@ def bitcast_convert_type(val, new_type):
 
 def stop_gradient(x):
     return x
+
+
+def scan(f, init, xs, length=None):
+    """lax.scan over the leading axis of xs (an array or a tuple of arrays): (carry, stacked ys)."""
+    from . import _take, _size, _stack  # the vmap helpers
+    n = _size(xs, 0) if xs is not None else int(length)
+    carry, ys = init, []
+    for i in range(n):
+        carry, y = f(carry, _take(xs, 0, i) if xs is not None else None)
+        ys.append(y)
+    return carry, _stack(ys)
