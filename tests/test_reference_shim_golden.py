@@ -236,3 +236,36 @@ def test_evaluators_around_the_solve_equal_reference_classes(name):
     m = np.isfinite(ref)
     scale = np.abs(ref[m]).max()
     np.testing.assert_allclose(got[m], ref[m], rtol=RTOL, atol=1e-6 * scale)
+
+
+def test_sr_evaluator_around_the_solve_equals_reference_class():
+    """SR_evaluator.Evaluator (reference class, unmodified, injected solve): the MSE fitness of evaluate_time_series
+    (:24,81-82), the penalty + mean + clip of __call__ (:42-45) and _drift (:85-88) -- against the oracle's."""
+    g = _load("refshim_evaluators.npz")
+    from tests import util
+    lib = NodeLibrary(util.OPS_SR, [["x0", "x1"]], [2])
+    pop = g["ev_sr_pop"]
+    data = RolloutData(kind=abi.EVAL_SR, env_id=abi.ENV_NONE, x0=g["ev_sr_x0"], ts=g["ev_sr_ts"], dt0=float(g["ev_sr_dt0"]),
+                       max_fitness=1e5, ys_true=g["ev_sr_ys_true"])
+    orc = pyoracle.rollout_population(pop, lib.table(), data, trajectories=True)
+    assert np.array_equal(orc["xs"].view(np.uint32), g["ev_sr_sol_ys"].view(np.uint32))
+    ft = np.isfinite(g["ev_sr_traj_fitness"])
+    assert np.array_equal(ft, np.isfinite(orc["traj_fitness"])) and ft.any()
+    np.testing.assert_allclose(orc["traj_fitness"][ft], g["ev_sr_traj_fitness"][ft], rtol=RTOL)
+    np.testing.assert_allclose(orc["fitness"], g["ev_sr_fitness"], rtol=RTOL)
+    L = pyoracle.lib()
+    L.oracle_vector_field.restype = C.c_int
+    desc, keep = data.to_desc_host()
+    table = lib.table()
+    pts, ref = g["ev_sr_points"], g["ev_sr_drift"]
+    got = np.empty_like(ref)
+    for p in range(pop.shape[0]):
+        cand = np.ascontiguousarray(pop[p])
+        for k in range(pts.shape[1]):
+            y = np.ascontiguousarray(pts[p, k])
+            assert L.oracle_vector_field(C.c_void_p(cand.ctypes.data), cand.shape[0], cand.shape[1], C.byref(table), C.byref(desc),
+                                         0, C.c_float(0.0), C.c_void_p(y.ctypes.data), C.c_void_p(got[p, k].ctypes.data)) == 0
+    del keep
+    m = ~np.isnan(ref)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert np.array_equal(got[m].view(np.uint32), ref[m].view(np.uint32))  # + - * / : bit for bit

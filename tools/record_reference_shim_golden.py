@@ -250,6 +250,35 @@ def record_evaluators():
                     f"ev_{name}_params": data.params, f"ev_{name}_sol_ys": sol_ys, f"ev_{name}_y0": y0s, f"ev_{name}_ys": r_ys,
                     f"ev_{name}_us": r_us, f"ev_{name}_traj_fitness": r_fit, f"ev_{name}_fitness": r_call,
                     f"ev_{name}_points": pts, f"ev_{name}_drift": drifts})
+    # --- SR_evaluator.Evaluator: evaluate_time_series around the solve (MSE fitness), __call__, _drift ---
+    from MultiTreeGP.evaluators import SR_evaluator
+    lib, pop, data = util.sr_case(rng, P=8, B=4, T_end=3.0)
+    ops_sr = [("+", lambda x, y: x + y, 2, 0.5), ("-", lambda x, y: x - y, 2, 0.1), ("*", lambda x, y: x * y, 2, 0.5),
+              ("/", lambda x, y: x / y, 2, 0.1)]
+    gp = GeneticProgramming(2, 20, (lambda *a, **k: 0.0), ops_sr, [["x0", "x1"]], jnp.array([2]), max_init_depth=4, max_nodes=30)
+    assert gp.string_to_node == lib.string_to_node
+    ev = SR_evaluator.Evaluator(dt0=float(data.dt0))
+    orc = pyoracle.rollout_population(pop, lib.table(), data, trajectories=True)
+    P, B = pop.shape[0], data.x0.shape[0]
+    keys = np.zeros((B, 2), np.uint32)
+    ref_data = (A(data.x0), A(data.ts), A(data.ys_true), jnp.asarray(keys))
+    r_fit = np.empty((P, B), F); r_call = np.empty(P, F)
+    pts = (rng.normal(size=(P, 5, 2)) * 1.5).astype(F); drifts = np.empty_like(pts)
+    with np.errstate(all="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for p in range(P):
+            diffrax.INJECT[:] = [orc["xs"][p, b] for b in range(B)]
+            diffrax.CALLS.clear()
+            fit_r, pred = ev.evaluate_candidate(A(pop[p]), ref_data, gp.vmap_foriloop)
+            assert np.array_equal(np.asarray(pred), orc["xs"][p], equal_nan=True)
+            assert all(np.array_equal(c["y0"], data.x0[b]) and c["throw"] is False and c["has_event"] for b, c in enumerate(diffrax.CALLS))
+            r_fit[p] = np.asarray(fit_r)
+            diffrax.INJECT[:] = [orc["xs"][p, b] for b in range(B)]
+            r_call[p] = F(ev(A(pop[p][..., 3:]), A(pop[p][..., :3]), ref_data, gp.vmap_foriloop))
+            for k in range(pts.shape[1]):
+                drifts[p, k] = np.asarray(ev._drift(F(0.0), A(pts[p, k]), (A(pop[p]), gp.vmap_foriloop)), dtype=F)
+    out.update(ev_sr_pop=pop, ev_sr_x0=data.x0, ev_sr_ts=data.ts, ev_sr_ys_true=data.ys_true, ev_sr_dt0=np.array(data.dt0, F),
+               ev_sr_sol_ys=orc["xs"], ev_sr_traj_fitness=r_fit, ev_sr_fitness=r_call, ev_sr_points=pts, ev_sr_drift=drifts)
     return out
 
 

@@ -23,6 +23,8 @@ class EulerHeun(_Opaque): pass
 
 class DirectAdjoint(_Opaque): pass
 class AbstractStepSizeController(_Opaque): pass
+class AbstractSolver(_Opaque): pass
+class SpaceTimeLevyArea(_Opaque): pass
 
 
 class _Solution:
