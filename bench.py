@@ -457,9 +457,12 @@ def main():
                         "issue_slots_busy_pct": ncu_field("k_rollout", "issue_active_pct"),
                         "executed_fp32_frac_of_fma_peak": ncu_field("k_rollout", "executed_fp32_frac_of_fma_peak"),
                         "warp_instructions_per_warp_step": ncu_field("k_rollout", "warp_instructions_per_warp_step"),
+                        "warp_instructions_per_32_lane_steps": ncu_field("k_rollout", "warp_instructions_per_32_lane_steps"),
+                        "lane_waste": ncu_field("k_rollout", "lane_waste"),
                         "note": "counters of the ncu --set full capture named by `commit` (not of this run); "
-                                "warp-instructions per warp-step = smsp__inst_executed.sum / (executed rollout-steps / 32 "
-                                "lanes, a warp-step counted while any of its lanes still integrates)"},
+                                "warp_instructions_per_warp_step = smsp__inst_executed.sum / warp-steps actually executed (a warp "
+                                "steps while any of its lanes still integrates); ..._per_32_lane_steps = the same sum / (executed "
+                                "rollout-steps / 32), which also charges the dead lanes that ride along (lane_waste)"},
                 "peak_note": f"non-tensor FP32: 148 SM x 128 lanes x 2 (FMA) x {sm_mhz:.0f} MHz ({peak_src} clock); "
                              "the kernel is bound by instruction issue (interpreter dispatch), not by the FP32 pipe"}
 

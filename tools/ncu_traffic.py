@@ -1,7 +1,7 @@
 """Writes profiles/r02_traffic.json (the ncu-derived fields bench.py quotes in its roofline block) from
 the two --set full captures made by tools/gpu_final.sh:
 
-    python tools/ncu_traffic.py gpurun_out/prof_rollout_full.ncu-rep gpurun_out/prof_pointwise_full.ncu-rep
+    python tools/ncu_traffic.py gpurun_out/prof_rollout_full.ncu-rep gpurun_out/prof_pointwise_full.ncu-rep [commit]
 """
 import csv, io, json, os, subprocess, sys
 
@@ -47,7 +47,25 @@ def block(rep, population, warp_steps=None):
         "source": os.path.basename(rep) + " (ncu --set full --clock-control none, one launch at the bench size)",
     }
     if warp_steps:
-        b["warp_instructions_per_warp_step"] = inst / warp_steps
+        # two denominators, both reported: (a) warp-steps the kernel actually executed (a warp steps while ANY of its
+        # lanes still integrates) = the execution count of the step loop's own instructions in the source page;
+        # (b) lane-steps / 32, which charges the lanes that ride along dead (9-10 % on C5) to the instruction count
+        b["warp_instructions_per_32_lane_steps"] = inst / warp_steps
+        src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(src)))
+        ci = rows[1].index("Instructions Executed")
+        counts = []
+        for r in rows[2:]:
+            try:
+                counts.append(int(r[ci]))
+            except (ValueError, IndexError):
+                pass
+        import collections
+        tot = sum(counts)
+        executed_warp_steps = collections.Counter(c for c in counts if c > tot / 1e5).most_common(1)[0][0]
+        b["executed_warp_steps"] = executed_warp_steps
+        b["warp_instructions_per_warp_step"] = inst / executed_warp_steps
+        b["lane_waste"] = 1.0 - warp_steps / executed_warp_steps
     return b
 
 
@@ -58,7 +76,9 @@ if __name__ == "__main__":
         line = json.load(fh)
     warp_steps = line["config"]["executed_rollout_steps_per_step"] / 32.0
     out = {"k_rollout": block(roll, 65536, warp_steps), "k_pointwise": block(pw, 100000)}
-    commit = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    # the commit the CAPTURED build was made from (argv[3] when the capture is processed after later commits)
+    commit = sys.argv[3] if len(sys.argv) > 3 else \
+        subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
     dirty = subprocess.run(["git", "-C", ROOT, "status", "--porcelain", "--", "multitreegp_b200"], capture_output=True,
                            text=True).stdout.strip()
     for b in out.values():
