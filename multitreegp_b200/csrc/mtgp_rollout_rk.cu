@@ -498,10 +498,16 @@ int launch_rk(RolloutParams rp, int tmp_base, int bound, cudaStream_t stream) {
   // The adaptive kernel's value file is large (12 solver arrays), shared memory decides how many warps an SM holds,
   // and the kernel is latency-bound: its fast class is provisioned for the programs of ordinary notebook trees
   // (kRkFastTh threaded instructions: 16 resident warps per SM on the DynamicPolicy shapes instead of 14).
-  constexpr int kRkFastTh = 64;
+#ifndef MTGP_RK_FAST_TH
+#define MTGP_RK_FAST_TH 64
+#endif
+#ifndef MTGP_RK_FAST_TMP
+#define MTGP_RK_FAST_TMP kFastTmp
+#endif
+  constexpr int kRkFastTh = MTGP_RK_FAST_TH, kRkFastTmp = MTGP_RK_FAST_TMP;
   const int worst_th = mtgp_worst_threaded(rp.T, rp.lstride);
-  const bool all_fast = (bound <= kFastTmp) && (worst_th <= kRkFastTh);
-  rp.fast_tmp = all_fast ? bound : kFastTmp;
+  const bool all_fast = (bound <= kRkFastTmp) && (worst_th <= kRkFastTh);
+  rp.fast_tmp = all_fast ? bound : kRkFastTmp;
   rp.fast_th = all_fast ? worst_th : kRkFastTh;
   int rc = launch_rk_class<KIND, ENV>(rp, tmp_base, rp.fast_tmp, rp.fast_th, 1, stream);
   if (rc == MTGP_OK && !all_fast) rc = launch_rk_class<KIND, ENV>(rp, tmp_base, bound, worst_th, 0, stream);
