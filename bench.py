@@ -701,7 +701,7 @@ def bench_pointwise(eng, dev, K, peaks, peak_src, with_cpu, world=1, rank=0):
         ms_e = (time.perf_counter() - t0) * 1e3 / K
         out["e2e"] = {"value": node_evals / (ms_e * 1e-3), "unit": "live node-evals/s", "ms_per_step": ms_e,
                       "h2d_bytes_per_step": int(pop.nbytes + X.nbytes + Y.nbytes), "d2h_bytes_per_step": int(4 * C4["P"]),
-                      "note": "mtgp_population_fitness_pointwise_host: upload in four slices, evaluated on two streams as they land"}
+                      "note": "mtgp_population_fitness_pointwise_host: upload in eight slices, evaluated on two streams as they land"}
         del pop_h
         ms8, live8, *_ = run(8)
         out["wide_variant"] = {"n_vars": 8, "ms_per_step": ms8, "value": live8 * C4["n_points"] / (ms8 * 1e-3),

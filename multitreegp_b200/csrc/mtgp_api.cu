@@ -399,7 +399,7 @@ struct DeviceScratch {
   // the host entry points overlap the population upload with the evaluation (see mtgp_population_fitness_host):
   // one copy stream, two compute streams, events; created on first use, owned with the scratch
   cudaStream_t copy_s = nullptr, comp_s[2] = {nullptr, nullptr};
-  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[12] = {};
 };
 std::mutex g_scratch_table_mu;
 std::map<int, std::unique_ptr<DeviceScratch>> g_scratch;
@@ -444,7 +444,7 @@ static int scratch_streams(DeviceScratch& sc) {
   if (sc.copy_s) return MTGP_OK;
   MTGP_CUDA_TRY(cudaStreamCreateWithFlags(&sc.copy_s, cudaStreamNonBlocking));
   for (int i = 0; i < 2; i++) MTGP_CUDA_TRY(cudaStreamCreateWithFlags(&sc.comp_s[i], cudaStreamNonBlocking));
-  for (int i = 0; i < 8; i++) MTGP_CUDA_TRY(cudaEventCreateWithFlags(&sc.ev[i], cudaEventDisableTiming));
+  for (int i = 0; i < 12; i++) MTGP_CUDA_TRY(cudaEventCreateWithFlags(&sc.ev[i], cudaEventDisableTiming));
   return MTGP_OK;
 }
 
@@ -458,7 +458,7 @@ int mtgp_release_scratch(void) {
     if (kv.second->copy_s) {
       cudaStreamDestroy(kv.second->copy_s);
       for (int i = 0; i < 2; i++) cudaStreamDestroy(kv.second->comp_s[i]);
-      for (int i = 0; i < 8; i++) cudaEventDestroy(kv.second->ev[i]);
+      for (int i = 0; i < 12; i++) cudaEventDestroy(kv.second->ev[i]);
       kv.second->copy_s = nullptr;
     }
   }
@@ -572,10 +572,13 @@ int mtgp_population_fitness_pointwise_host(const float* population_host, int P, 
   }
   cudaStream_t s = (cudaStream_t)stream;
   const size_t pop_bytes = (size_t)P * T * N * 4 * sizeof(float);
-  // populations of 32 MB and more: four slices, uploaded back to back on a copy stream and evaluated on two compute
+  // populations of 32 MB and more: eight slices, uploaded back to back on a copy stream and evaluated on two compute
   // streams as they land (the kernel takes longer than the upload of a slice, so only the first upload is exposed)
   const bool split = pop_bytes >= ((size_t)32 << 20) && P >= 64;
-  const int n_chunks = split ? 4 : 1;
+#ifndef MTGP_PW_UPLOAD_SLICES
+#define MTGP_PW_UPLOAD_SLICES 8  // (<= 8: one event per slice; C4 end to end: 2 slices 21.5 ms, 4: 19.9 ms, 8: 18.9 ms)
+#endif
+  const int n_chunks = split ? MTGP_PW_UPLOAD_SLICES : 1;
   const int Pc = split ? (((P + n_chunks - 1) / n_chunks + 7) & ~7) : P;
   const size_t ws_one = mtgp_workspace_bytes_pointwise(Pc, T, N, n_points, n_vars);
   const size_t ws_bytes = split ? 2 * align_up(ws_one, 256) : ws_one;
@@ -627,8 +630,8 @@ int mtgp_population_fitness_pointwise_host(const float* population_host, int P, 
       if (rc) { cudaStreamSynchronize(sc->comp_s[0]); cudaStreamSynchronize(sc->comp_s[1]); return rc; }
     }
     for (int i = 0; i < 2; i++) {
-      MTGP_CUDA_TRY(cudaEventRecord(sc->ev[5 + i], sc->comp_s[i]));
-      MTGP_CUDA_TRY(cudaStreamWaitEvent(s, sc->ev[5 + i], 0));
+      MTGP_CUDA_TRY(cudaEventRecord(sc->ev[10 + i], sc->comp_s[i]));
+      MTGP_CUDA_TRY(cudaStreamWaitEvent(s, sc->ev[10 + i], 0));
     }
   }
   MTGP_CUDA_TRY(cudaMemcpyAsync(fitness_host, fit_d, (size_t)P * 4, cudaMemcpyDeviceToHost, s));
