@@ -475,7 +475,10 @@ int mtgp_population_fitness_host(const float* population_host, int P, int T, int
   cudaStream_t s = (cudaStream_t)stream;
   const size_t pop_bytes = (size_t)P * T * N * 4 * sizeof(float);
   // populations worth overlapping (>= 32 MB of rows) are evaluated as a prologue slice + the rest (see below)
-  const bool split = pop_bytes >= ((size_t)32 << 20) && P >= 64;
+#ifndef MTGP_HOST_SPLIT_MIN_MB
+#define MTGP_HOST_SPLIT_MIN_MB 32  // (8 measured on a 24 MB population: 12.8 vs 12.2 ms -- the second launch costs more than the upload it hides)
+#endif
+  const bool split = pop_bytes >= ((size_t)MTGP_HOST_SPLIT_MIN_MB << 20) && P >= 64;
   const size_t PA = split ? (size_t)((P / 8 + 7) & ~7) : 0;
   const size_t ws_a = split ? mtgp_workspace_bytes((int)PA, T, N, dh) : 0;
   const size_t ws_b = split ? mtgp_workspace_bytes((int)(P - PA), T, N, dh) : 0;
